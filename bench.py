@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- MultiSURF fit throughput (sample-pair*features/s) on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c2|c4]
+
+A "step" is one pass of the scoring hot path (encode of the active columns, n x n
+distances, neighbour selection, weight accumulation, reduction) over one synthetic data
+set.  `value` is measured with the raw matrix already resident in HBM; `e2e` is the same
+metric through the estimator API (`MultiSURF(backend='gpu').fit`) from host buffers, with
+the host->device upload, the on-GPU column scan and the device->host read of the weights
+inside the timed region.
+
+Default workload (BASELINE.json configs[2], the config the metric's "1/2/4/8 B200" is
+quoted on): MultiSURF on synthetic 0/1/2 genotypes, 4000 samples x 100000 SNPs, epistatic
+label.  With N > 1 GPUs (one process per GPU under torchrun) the target
+rows are sharded across ranks and the partial weight vectors are combined by one NCCL
+allreduce; weak scaling keeps the per-GPU work (rows_per_gpu x n x p) fixed by growing n
+with sqrt(N).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "multisurf_fit_pair_features_per_s"
+UNIT = "sample-pair*features/s"
+
+
+# --------------------------------------------------------------------------- #
+# workloads
+# --------------------------------------------------------------------------- #
+def make_workload(name, n_gpus, scaling, n_override=None, p_override=None):
+    from datasets import epistatic_genotypes
+
+    if name == "c3":
+        n, p = 4000, 100_000
+        algo, star = "MultiSURF", False
+    elif name == "c2":
+        n, p = 10_000, 10_000
+        algo, star = "ReliefF", False
+    elif name == "c4":
+        n, p = 20_000, 50_000
+        algo, star = "MultiSURF", True
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    if n_override:
+        n = n_override
+    if p_override:
+        p = p_override
+    if scaling == "weak" and n_gpus > 1:
+        n = int(round(n * np.sqrt(n_gpus) / 8.0)) * 8
+    if name == "c3":
+        x, y = epistatic_genotypes(42, n, p)
+        desc = f"C3: MultiSURF on int8 0/1/2 genotypes {n} samples x {p} SNPs, epistatic label"
+    elif name == "c2":
+        from sklearn.datasets import make_classification
+
+        x, y = make_classification(n_samples=n, n_features=p, n_informative=20, n_redundant=100, random_state=42)
+        desc = f"C2: ReliefF k=10 on continuous make_classification {n} x {p}"
+    else:
+        rs = np.random.RandomState(43)
+        x = np.empty((n, p), np.float32)
+        h = p // 2
+        x[:, :h] = rs.randint(0, 3, (n, h))
+        x[:, h:] = rs.standard_normal((n, p - h)).astype(np.float32)
+        y = np.zeros(n, np.int64)
+        y[(x[:, 25] == 1) & (x[:, 75] == 1)] = 1
+        need = n // 2 - int(y.sum())
+        y[rs.choice(np.flatnonzero(y == 0), need, replace=False)] = 1
+        x[:, h] += 1.0 * y
+        desc = f"C4: MultiSURF* on mixed {n} x {p} (half genotype, half gaussian)"
+    return dict(name=name, x=x, y=y, n=n, p=p, algo=algo, star=star, desc=desc)
+
+
+def make_estimator(w):
+    import fastselect_b200 as fsb
+
+    if w["algo"] == "ReliefF":
+        return fsb.ReliefF(n_features_to_select=10, n_neighbors=10, backend="gpu")
+    return fsb.MultiSURF(n_features_to_select=10, backend="gpu", use_star=w["star"])
+
+
+# --------------------------------------------------------------------------- #
+# clocks during the timed region
+# --------------------------------------------------------------------------- #
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples = index, threading.Event(), []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [s.strip() for s in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for q, nm in enumerate(names) if any(s[2 + q].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- #
+# CPU baseline (oracle port on a bounded sample)
+# --------------------------------------------------------------------------- #
+def cpu_sample(w, n_s=1000, p_s=4000):
+    n_s, p_s = min(n_s, w["n"]), min(p_s, w["p"])
+    return w["x"][:n_s, :p_s], w["y"][:n_s], n_s, p_s
+
+
+def run_cpu_port(w, xs, ys):
+    """One timed pass of the oracle (C restatement of the reference CPU kernel, OpenMP over
+    target instances like the reference's prange)."""
+    from oracle import ref_oracle as R
+
+    if w["algo"] == "ReliefF":
+        x32, y_enc, cp, recip, isd = R.relieff_prep(xs, ys, 10)
+        t0 = time.perf_counter()
+        R.relieff_scores(x32, y_enc, recip, isd, 10, cp, 0)
+    else:
+        x32, recip, isd = R.multisurf_prep(xs, 10)
+        yc = np.unique(ys, return_inverse=True)[1].astype(np.int64)
+        t0 = time.perf_counter()
+        R.multisurf_scores(x32, yc, recip, isd, w["star"])
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(w):
+    from oracle import ref_oracle as R
+
+    xs, ys, n_s, p_s = cpu_sample(w)
+    dt = run_cpu_port(w, xs, ys)
+    return {"value": n_s * n_s * p_s / dt, "unit": UNIT, "cores": R.max_threads(), "kind": "port",
+            "sample": f"first {n_s} samples x {p_s} features of the workload, one fit, {dt:.2f} s"}
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: the
+    reference is Python/Numba and does not travel to the GPU box) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_oracle as R
+
+    R.build()
+    w = make_workload(args.workload, 1, "weak", args.n, args.p)
+    xs, ys, n_s, p_s = cpu_sample(w)
+    for _ in range(args.warmup):
+        run_cpu_port(w, xs[:200], ys[:200])
+    t = sum(run_cpu_port(w, xs, ys) for _ in range(args.steps))
+    value = args.steps * n_s * n_s * p_s / t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (CPU)",
+            "data": "synthetic", "config": {"workload": w["desc"], "n": w["n"], "p": w["p"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": R.max_threads(), "kind": "port",
+                             "sample": f"first {n_s} samples x {p_s} features per step"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- #
+# own arm
+# --------------------------------------------------------------------------- #
+def own_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from fastselect_b200 import _native
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    _native.load()
+    if _native.device_count() < 1:
+        raise SystemExit("bench.py: no usable sm_100 GPU (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    os.environ["FASTSELECT_B200_DEVICE"] = str(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w = make_workload(args.workload, world, args.scaling, args.n, args.p)
+    n, p = w["n"], w["p"]
+    est = make_estimator(w)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    # ---- resident-data timing: the estimator's own session, kept open
+    from fastselect_b200._shard import shard_rows
+
+    x_in = w["x"]
+    sess, _ = est._open_session(x_in, w["y"])
+    lo, hi = shard_rows(n, world, rank)
+    buf = torch.empty(p, dtype=torch.float64, device="cuda")
+    last_stats = {}
+
+    def step():
+        # set_features invalidates the cached working set: every step re-encodes the columns
+        sess.ds.set_features(sess.is_discrete, sess.recip, sess.arith)
+        nonlocal last_stats
+        _, last_stats = sess.ds.score(sess.algo, sess.use_star, sess.k, sess.class_probs, None, lo, hi,
+                                      out_device_ptr=buf.data_ptr(), want_stats=True)
+        if world > 1:
+            dist.all_reduce(buf)
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg = {}
+    e0.record()
+    for _ in range(args.steps):
+        step()
+        for k_, v in last_stats.items():
+            agg[k_] = agg.get(k_, 0) + v
+    e1.record()
+    barrier()
+    sampler.stop_flag.set()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    units = float(n) * n * p
+    value = units * args.steps / (ms / 1e3)
+    weights = (buf.cpu().numpy() / n).astype(np.float32)
+    sess.close()
+
+    # ---- end to end through the estimator API from host buffers
+    e2e_steps = max(1, min(args.steps, 3))
+    make_estimator(w).fit(x_in[: min(n, 256), : min(p, 512)], w["y"][: min(n, 256)])   # warm the API path
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        fitted = make_estimator(w).fit(x_in, w["y"])
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    e2e_value = units * e2e_steps / dt
+    h2d = int(x_in.nbytes + 4 * n + p * 5 + p * 4)
+    d2h = int(p * (8 + 8 + 4) + p * 8)
+    same = bool(np.allclose(fitted.feature_importances_, weights, rtol=1e-6, atol=1e-9))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (per-phase CUDA events from fs_stats)
+    steps = args.steps
+    phases = {k_: agg.get(k_, 0.0) / steps for k_ in ("ms_gather", "ms_dist_tensor", "ms_dist_general", "ms_select",
+                                                      "ms_accum_tensor", "ms_accum_general", "ms_reduce", "ms_total")}
+    rows = hi - lo
+    u_rank = float(rows) * n * p
+    top = max(("ms_dist_tensor", "ms_dist_general", "ms_accum_tensor", "ms_accum_general"), key=lambda q: phases[q])
+    if top.endswith("tensor"):
+        # 3 MAC = 6 int-ops per (pair, feature) for either one-hot contraction
+        achieved = 6.0 * u_rank / (phases[top] / 1e3) / 1e12
+        bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak = 2.0 * bf16
+        roof = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TOP/s int8",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": ("2 x measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "2 x fallback 1.4 PF")}
+    else:
+        # CUDA-core kernels re-use every loaded element >= 64 times: algorithmic bytes are one
+        # read of both operand slabs plus the D slab write
+        byts = (rows + n) * p * 4.0 + rows * n * 8.0
+        achieved = byts / (phases[top] / 1e3) / 1e9
+        peak = peaks.get("hbm_gbs", 6650.0)
+        roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "measured copy (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
+                "note": "issue-bound CUDA-core kernel; HBM fraction is low by construction"}
+
+    cpu = cpu_baseline(w)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "u8 one-hot / int32 accum (genotype), f32 terms + f64 accum (continuous)",
+            "data": "synthetic",
+            "config": {"workload": w["desc"], "n": n, "p": p, "algo": w["algo"] + ("*" if w["star"] else ""),
+                       "rows_per_gpu": rows, "sharding": f"target rows x{world}, one NCCL allreduce",
+                       "l2": "inputs larger than L2 (no flush needed)", "step": "encode + distances + select + accumulate"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "seconds_per_fit": dt / e2e_steps, "matches_resident_run": same},
+            "gpu_launches": int(agg.get("launches", 0)),
+            "roofline": roof, "phases_ms": phases, "cpu_baseline": cpu,
+            "top_features": fitted.top_features_.tolist(),
+            "stats": {k_: int(agg[k_] / steps) for k_ in ("n_tensor_cols", "n_general_cols", "onehot_k",
+                                                           "pairs_selected", "n_chunks") if k_ in agg}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--p", type=int, default=None)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        own_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,207 @@
+"""ctypes binding of libfastselect_b200.so (the C ABI declared in include/fastselect_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no sm_100 GPU is
+usable, :func:`require_gpu` raises ``RuntimeError`` and nothing is computed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+FS_RELIEFF, FS_SURF, FS_MULTISURF = 0, 1, 2
+FS_U8, FS_I8, FS_F32, FS_F64 = 0, 1, 2, 3
+FS_ARITH_F32, FS_ARITH_F64 = 0, 1
+FS_DISTINCT_CAP = 16
+
+_DTYPES = {np.dtype(np.uint8): FS_U8, np.dtype(np.int8): FS_I8,
+           np.dtype(np.float32): FS_F32, np.dtype(np.float64): FS_F64}
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfastselect_b200.so")
+
+
+class FsStats(C.Structure):
+    _fields_ = [("ms_total", C.c_float), ("ms_gather", C.c_float), ("ms_dist_tensor", C.c_float),
+                ("ms_dist_general", C.c_float), ("ms_select", C.c_float), ("ms_accum_tensor", C.c_float),
+                ("ms_accum_general", C.c_float), ("ms_reduce", C.c_float), ("launches", C.c_int32),
+                ("n_chunks", C.c_int32), ("n_tensor_cols", C.c_int64), ("n_general_cols", C.c_int64),
+                ("onehot_k", C.c_int64), ("pairs_selected", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (built in-tree by ``__graft_entry__.build()`` / csrc/Makefile)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"fastselect_b200: {LIB_PATH} is missing - build it with "
+            "`make -C fastselect_b200/csrc` (or __graft_entry__.build()). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.fs_last_error.restype = C.c_char_p
+    lib.fs_device_count.restype = C.c_int
+    lib.fs_abi_version.restype = C.c_int
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.fs_dataset_create.argtypes = [C.POINTER(vp), vp, C.c_int, i64, i64, i64, vp, i32, i32, vp]
+    lib.fs_dataset_create_device.argtypes = lib.fs_dataset_create.argtypes
+    lib.fs_dataset_column_stats.argtypes = [vp, vp, vp, vp]
+    lib.fs_dataset_set_features.argtypes = [vp, vp, vp, C.c_int]
+    lib.fs_dataset_destroy.argtypes = [vp]
+    lib.fs_dataset_row_order.argtypes = [vp, vp]
+    lib.fs_score.argtypes = [vp, C.c_int, C.c_int, i32, vp, vp, i64, i64, i64, vp, C.c_int, C.POINTER(FsStats)]
+    lib.fs_debug_rows.argtypes = [vp, C.c_int, C.c_int, i32, vp, vp, i64, vp, i64, vp, vp, vp, vp]
+    _lib = lib
+    return lib
+
+
+def device_count() -> int:
+    """Usable sm_100 GPUs; 0 when the library or a GPU is missing (never raises)."""
+    try:
+        return int(load().fs_device_count())
+    except (RuntimeError, OSError):
+        return 0
+
+
+def _raise(rc, what):
+    msg = load().fs_last_error().decode("utf-8", "replace")
+    if rc == -2:
+        raise RuntimeError(f"{what}: {msg}")
+    if rc == -4:
+        raise MemoryError(f"{what}: {msg}")
+    if rc == -1:
+        raise ValueError(f"{what}: {msg}")
+    raise RuntimeError(f"{what} failed ({rc}): {msg}")
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def default_device() -> int:
+    for key in ("FASTSELECT_B200_DEVICE", "LOCAL_RANK"):
+        v = os.environ.get(key)
+        if v is not None and v.strip() != "":
+            return int(v)
+    return 0
+
+
+class Dataset:
+    """A device-resident data set (``fs_dataset``): upload + on-GPU column scan.
+
+    Not stored on fitted estimators (they stay picklable); always used as a
+    context manager so the device memory is released deterministically."""
+
+    def __init__(self, x: np.ndarray, y_enc: np.ndarray, n_classes: int, device: int | None = None,
+                 stream: int = 0):
+        lib = load()
+        if x.dtype not in _DTYPES:
+            raise TypeError(f"unsupported dtype {x.dtype}")
+        if x.ndim != 2:
+            raise ValueError("x must be 2-D")
+        if x.strides[1] != x.itemsize or x.strides[0] % x.itemsize or x.strides[0] < x.shape[1] * x.itemsize:
+            x = np.ascontiguousarray(x)
+        self.n, self.p = x.shape
+        self._keep = x
+        y_enc = np.ascontiguousarray(y_enc, np.int32)
+        h = C.c_void_p()
+        dev = default_device() if device is None else device
+        rc = lib.fs_dataset_create(C.byref(h), _ptr(x), _DTYPES[x.dtype], self.n, self.p,
+                                   x.strides[0] // x.itemsize, _ptr(y_enc), int(n_classes), dev,
+                                   C.c_void_p(stream))
+        if rc != 0:
+            _raise(rc, "fs_dataset_create")
+        self._h = h
+        self._keep = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().fs_dataset_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def column_stats(self):
+        cmin = np.empty(self.p, np.float64)
+        cmax = np.empty(self.p, np.float64)
+        cnt = np.empty(self.p, np.int32)
+        rc = load().fs_dataset_column_stats(self._h, _ptr(cmin), _ptr(cmax), _ptr(cnt))
+        if rc != 0:
+            _raise(rc, "fs_dataset_column_stats")
+        return cmin, cmax, cnt
+
+    def set_features(self, is_discrete, recip, arith):
+        is_discrete = np.ascontiguousarray(is_discrete, np.uint8)
+        recip = np.ascontiguousarray(recip, np.float32)
+        rc = load().fs_dataset_set_features(self._h, _ptr(is_discrete), _ptr(recip), int(arith))
+        if rc != 0:
+            _raise(rc, "fs_dataset_set_features")
+
+    def row_order(self):
+        perm = np.empty(self.n, np.int64)
+        rc = load().fs_dataset_row_order(self._h, _ptr(perm))
+        if rc != 0:
+            _raise(rc, "fs_dataset_row_order")
+        return perm
+
+    def score(self, algo, use_star=False, k=0, class_probs=None, feat_idx=None, row_begin=0, row_end=None,
+              out_device_ptr=None, want_stats=False):
+        """Partial weight sums (float64, before the final ``/ n``) of the target rows
+        ``[row_begin, row_end)``.  With ``out_device_ptr`` the result is written to that
+        device buffer (for an in-place NCCL allreduce) and ``None`` is returned."""
+        row_end = self.n if row_end is None else row_end
+        if feat_idx is not None:
+            feat_idx = np.ascontiguousarray(feat_idx, np.int64)
+            n_kept = feat_idx.size
+        else:
+            n_kept = self.p
+        cp = None if class_probs is None else np.ascontiguousarray(class_probs, np.float32)
+        stats = FsStats() if want_stats else None
+        out = None
+        if out_device_ptr is None:
+            out = np.empty(n_kept, np.float64)
+            dst, on_dev = _ptr(out), 0
+        else:
+            dst, on_dev = C.c_void_p(out_device_ptr), 1
+        rc = load().fs_score(self._h, int(algo), int(bool(use_star)), int(k), _ptr(cp), _ptr(feat_idx), n_kept,
+                             int(row_begin), int(row_end), dst, on_dev,
+                             C.byref(stats) if stats is not None else None)
+        if rc != 0:
+            _raise(rc, "fs_score")
+        return (out, stats.as_dict()) if want_stats else out
+
+    def debug_rows(self, algo, targets, use_star=False, k=0, class_probs=None, feat_idx=None):
+        targets = np.ascontiguousarray(targets, np.int64)
+        nt = targets.size
+        if feat_idx is not None:
+            feat_idx = np.ascontiguousarray(feat_idx, np.int64)
+            n_kept = feat_idx.size
+        else:
+            n_kept = self.p
+        cp = None if class_probs is None else np.ascontiguousarray(class_probs, np.float32)
+        dist = np.empty((nt, self.n), np.float64)
+        thresh = np.empty(nt, np.float64)
+        mask = np.empty((nt, self.n), np.int8)
+        wsum = np.empty(n_kept, np.float64)
+        rc = load().fs_debug_rows(self._h, int(algo), int(bool(use_star)), int(k), _ptr(cp), _ptr(feat_idx), n_kept,
+                                  _ptr(targets), nt, _ptr(dist), _ptr(thresh), _ptr(mask), _ptr(wsum))
+        if rc != 0:
+            _raise(rc, "fs_debug_rows")
+        return dict(dist=dist, thresh=thresh, mask=mask, wsum=wsum)

@@ -1,0 +1,221 @@
+// accum_general.cu -- CUDA-core per-feature weight accumulation for continuous
+// (and wide discrete) columns, the ReliefF neighbour gather, and the final
+// reduction of the partial weight vectors.
+//
+// Replaces the hit/miss accumulation loops and normalisation of the reference
+// kernels (MultiSURF.py:198-251, SURF.py:165-195, ReliefF.py:181-216) in the
+// matrix form  wsum[f] = sum_i sum_j c_ij * term_f(i, j),  where c_ij is the
+// coefficient of the pair's neighbour code for target i (RowInfo::coef: sign and
+// 1/|H_i|, 1/|M_i| folded in).
+//
+// accum_general_kernel: one thread per feature column (coalesced 128-byte row
+// segments per warp), 16 target rows held in registers, the samples j streamed
+// once per 16 targets; the 16 x 128 coefficient tile of each j-tile is decoded
+// from the int8 codes into shared memory.  float32 products are accumulated in
+// float32 over one 128-sample tile and then folded into a float64 accumulator, so
+// the result is accurate to ~1e-7 relative while the inner loop is 3 FP32
+// instructions per (pair, feature).  Partials are written per (row chunk, feature)
+// and reduced in a fixed order: results are bitwise reproducible.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace fs {
+
+constexpr int kAccThreads = 128;  // features per CTA
+constexpr int kAccRows = 16;      // target rows per register block
+constexpr int kAccJT = 128;       // samples per coefficient tile
+
+__device__ __forceinline__ float term32(float a, float b, float r, bool cmp) {
+    const float t = __fmul_rn(fabsf(__fsub_rn(a, b)), r);
+    return cmp ? ((a != b) ? 1.0f : 0.0f) : t;
+}
+// SURF.py:153-158: float64 product, stored as float32
+__device__ __forceinline__ float term32(double a, double b, float r, bool cmp) {
+    const float t = (float)__dmul_rn(fabs(__dsub_rn(a, b)), (double)r);
+    return cmp ? ((a != b) ? 1.0f : 0.0f) : t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kAccThreads)
+accum_general_kernel(const T *__restrict__ xg, int64_t n, int64_t ld, const float *__restrict__ recip,
+                     const uint8_t *__restrict__ ctype, const T *__restrict__ xa, const int8_t *__restrict__ sel,
+                     int64_t ldn, const RowInfo *__restrict__ rinfo, int64_t R, int64_t rows_per_cta,
+                     double *__restrict__ partial) {
+    constexpr int FT = kChunkBytes / sizeof(T);
+    __shared__ __align__(16) float scoef[kAccJT][kAccRows];
+    __shared__ float stab[kAccRows][5];
+
+    const int tid = threadIdx.x;
+    const int64_t f = (int64_t)blockIdx.y * kAccThreads + tid;   // blockIdx.x = row chunk (fastest)
+    const bool live = f < ld;
+    const int64_t fc = live ? f : ld - 1;
+    const float r = recip[fc];
+    const bool cmp = ctype[fc / FT] == kChunkCompare;
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r_end = r_begin + rows_per_cta < R ? r_begin + rows_per_cta : R;
+
+    double total = 0.0;
+    for (int64_t rb = r_begin; rb < r_end; rb += kAccRows) {
+        const int nr = (int)(r_end - rb < kAccRows ? r_end - rb : kAccRows);
+        T xi[kAccRows];
+#pragma unroll
+        for (int a = 0; a < kAccRows; ++a) xi[a] = xa[(rb + (a < nr ? a : nr - 1)) * ld + fc];
+        __syncthreads();
+        if (tid < kAccRows * 5) {
+            const int a = tid / 5, q = tid % 5;
+            stab[a][q] = a < nr ? (float)rinfo[rb + a].coef[q] : 0.0f;
+        }
+        for (int64_t j0 = 0; j0 < n; j0 += kAccJT) {
+            const int nj = (int)(n - j0 < kAccJT ? n - j0 : kAccJT);
+            __syncthreads();
+            // decode the 16 x 128 coefficient tile (coalesced along j)
+            for (int e = tid; e < kAccRows * kAccJT; e += kAccThreads) {
+                const int a = e / kAccJT, jj = e % kAccJT;
+                float c = 0.0f;
+                if (a < nr && jj < nj) c = stab[a][sel[(rb + a) * ldn + j0 + jj]];
+                scoef[jj][a] = c;
+            }
+            __syncthreads();
+            float acc[kAccRows];
+#pragma unroll
+            for (int a = 0; a < kAccRows; ++a) acc[a] = 0.0f;
+#pragma unroll 4
+            for (int jj = 0; jj < nj; ++jj) {
+                const T xj = xg[(j0 + jj) * ld + fc];
+                const float4 *cp = reinterpret_cast<const float4 *>(scoef[jj]);
+                float c[kAccRows];
+#pragma unroll
+                for (int q = 0; q < kAccRows / 4; ++q) {
+                    const float4 v = cp[q];
+                    c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int a = 0; a < kAccRows; ++a) acc[a] = fmaf(c[a], term32(xi[a], xj, r, cmp), acc[a]);
+            }
+#pragma unroll
+            for (int a = 0; a < kAccRows; ++a) total += (double)acc[a];
+        }
+    }
+    if (live) partial[(int64_t)blockIdx.x * ld + f] = total;
+}
+
+// ReliefF: per target row at most C*k neighbours; one thread per feature gathers
+// the neighbour rows (coalesced) -- HBM/L2-bound: n*k*C*p*sizeof(T) bytes.
+template <typename T>
+__global__ void __launch_bounds__(kAccThreads)
+relieff_gather_kernel(const T *__restrict__ xg, int64_t ld, const float *__restrict__ recip,
+                      const uint8_t *__restrict__ ctype, const T *__restrict__ xa,
+                      const int32_t *__restrict__ nbr_idx, const double *__restrict__ nbr_w,
+                      const int32_t *__restrict__ nbr_cnt, int nbr_cap, int64_t R, int64_t rows_per_cta,
+                      double *__restrict__ partial) {
+    constexpr int FT = kChunkBytes / sizeof(T);
+    __shared__ int32_t sidx[256];
+    __shared__ double sw[256];
+    const int tid = threadIdx.x;
+    const int64_t f = (int64_t)blockIdx.y * kAccThreads + tid;
+    const bool live = f < ld;
+    const int64_t fc = live ? f : ld - 1;
+    const float r = recip[fc];
+    const bool cmp = ctype[fc / FT] == kChunkCompare;
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r_end = r_begin + rows_per_cta < R ? r_begin + rows_per_cta : R;
+    double total = 0.0;
+    for (int64_t row = r_begin; row < r_end; ++row) {
+        const T xi = xa[row * ld + fc];
+        const int cnt = nbr_cnt[row];
+        for (int s0 = 0; s0 < cnt; s0 += 256) {
+            const int m = cnt - s0 < 256 ? cnt - s0 : 256;
+            __syncthreads();
+            for (int e = tid; e < m; e += kAccThreads) {
+                sidx[e] = nbr_idx[row * nbr_cap + s0 + e];
+                sw[e] = nbr_w[row * nbr_cap + s0 + e];
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int e = 0; e < m; ++e) {
+                const T xj = xg[(int64_t)sidx[e] * ld + fc];
+                // ReliefF.py:151-154: float32 term, accumulated in float64
+                double t;
+                if (cmp) t = (xi != xj) ? 1.0 : 0.0;
+                else if (sizeof(T) == 4) t = (double)__fmul_rn(fabsf(__fsub_rn((float)xi, (float)xj)), r);
+                else t = __dmul_rn(fabs(__dsub_rn((double)xi, (double)xj)), (double)r);
+                total = __fma_rn(sw[e], t, total);
+            }
+        }
+    }
+    if (live) partial[(int64_t)blockIdx.x * ld + f] = total;
+}
+
+// rows per CTA such that the grid is ~8 CTAs per SM and a multiple of kAccRows
+static int64_t rows_per_cta_for(int64_t R, int64_t ld) {
+    const int64_t ftiles = ceil_div(ld, kAccThreads);
+    int64_t want_chunks = std::max<int64_t>(1, ceil_div(148 * 8, ftiles));
+    int64_t rows = std::max<int64_t>(kAccRows, round_up(ceil_div(R, want_chunks), kAccRows));
+    return rows;
+}
+
+int64_t accum_general_partials(const WorkSet &ws, int64_t R) {
+    if (ws.pg == 0 || R == 0) return 0;
+    return ceil_div(R, rows_per_cta_for(R, ws.ldg));
+}
+
+void launch_accum_general(const WorkSet &ws, int64_t n, const void *xa, const int8_t *sel, int64_t ldn,
+                          const RowInfo *rinfo, int64_t R, double *partial, int64_t n_part, cudaStream_t st,
+                          int *launches) {
+    if (ws.pg == 0 || R == 0) return;
+    const int64_t rows = rows_per_cta_for(R, ws.ldg);
+    dim3 grid((unsigned)n_part, (unsigned)ceil_div(ws.ldg, kAccThreads));
+    if (ws.elem == 4)
+        accum_general_kernel<float><<<grid, kAccThreads, 0, st>>>(
+            reinterpret_cast<const float *>(ws.xg.ptr), n, ws.ldg, ws.rg.ptr, ws.ctype.ptr,
+            static_cast<const float *>(xa), sel, ldn, rinfo, R, rows, partial);
+    else
+        accum_general_kernel<double><<<grid, kAccThreads, 0, st>>>(
+            reinterpret_cast<const double *>(ws.xg.ptr), n, ws.ldg, ws.rg.ptr, ws.ctype.ptr,
+            static_cast<const double *>(xa), sel, ldn, rinfo, R, rows, partial);
+    FS_CUDA(cudaGetLastError());
+    ++*launches;
+}
+
+void launch_relieff_gather(const WorkSet &ws, int64_t n, const void *xa, const int32_t *nbr_idx,
+                           const double *nbr_w, const int32_t *nbr_cnt, int32_t nbr_cap, int64_t R,
+                           double *partial, int64_t n_part, cudaStream_t st, int *launches) {
+    (void)n;
+    if (ws.pg == 0 || R == 0) return;
+    const int64_t rows = rows_per_cta_for(R, ws.ldg);
+    dim3 grid((unsigned)n_part, (unsigned)ceil_div(ws.ldg, kAccThreads));
+    if (ws.elem == 4)
+        relieff_gather_kernel<float><<<grid, kAccThreads, 0, st>>>(
+            reinterpret_cast<const float *>(ws.xg.ptr), ws.ldg, ws.rg.ptr, ws.ctype.ptr,
+            static_cast<const float *>(xa), nbr_idx, nbr_w, nbr_cnt, nbr_cap, R, rows, partial);
+    else
+        relieff_gather_kernel<double><<<grid, kAccThreads, 0, st>>>(
+            reinterpret_cast<const double *>(ws.xg.ptr), ws.ldg, ws.rg.ptr, ws.ctype.ptr,
+            static_cast<const double *>(xa), nbr_idx, nbr_w, nbr_cnt, nbr_cap, R, rows, partial);
+    FS_CUDA(cudaGetLastError());
+    ++*launches;
+}
+
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double *__restrict__ partial, int64_t n_part,
+                                                              int64_t ld, const int64_t *__restrict__ gout,
+                                                              int64_t pg, double *__restrict__ wsum) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= pg) return;
+    const int64_t o = gout[c];
+    if (o < 0) return;
+    double s = 0.0;
+    for (int64_t q = 0; q < n_part; ++q) s += partial[q * ld + c];
+    wsum[o] += s;
+}
+
+void launch_reduce_partials(const WorkSet &ws, const double *partial, int64_t n_part, double *wsum,
+                            cudaStream_t st, int *launches) {
+    if (ws.pg == 0 || n_part == 0) return;
+    reduce_partials_kernel<<<(unsigned)ceil_div(ws.pg, 256), 256, 0, st>>>(partial, n_part, ws.ldg, ws.gout.ptr,
+                                                                          ws.pg, wsum);
+    FS_CUDA(cudaGetLastError());
+    ++*launches;
+}
+
+}  // namespace fs

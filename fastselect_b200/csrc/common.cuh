@@ -1,0 +1,193 @@
+// common.cuh -- shared declarations of libfastselect_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../../include/fastselect_b200.h"
+
+namespace fs {
+
+// ---------------------------------------------------------------------------
+// errors: thread-local message + status codes (no exceptions cross the C ABI)
+// ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+const char *get_error();
+
+struct Fail {
+    int code;
+};
+
+#define FS_CUDA(expr)                                                                       \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            fs::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,              \
+                          cudaGetErrorString(_e));                                          \
+            throw fs::Fail{_e == cudaErrorMemoryAllocation ? FS_ERR_OOM : FS_ERR_CUDA};     \
+        }                                                                                   \
+    } while (0)
+
+#define FS_REQUIRE(cond, code, ...)          \
+    do {                                     \
+        if (!(cond)) {                       \
+            fs::set_error(__VA_ARGS__);      \
+            throw fs::Fail{code};            \
+        }                                    \
+    } while (0)
+
+// Device buffer with RAII; never copies.
+template <typename T>
+struct DevBuf {
+    T *ptr = nullptr;
+    size_t count = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        count = 0;
+    }
+    void alloc(size_t n) {
+        release();
+        if (n == 0) return;
+        FS_CUDA(cudaMalloc(reinterpret_cast<void **>(&ptr), n * sizeof(T)));
+        count = n;
+    }
+    // grow-only (keeps the allocation when large enough)
+    void reserve(size_t n) {
+        if (n > count) alloc(n);
+    }
+};
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Feature chunk of the CUDA-core ("general") path: 128 bytes of one sample's
+// features, i.e. 32 float32 or 16 float64 columns.  A chunk is either all
+// continuous (type 0) or all "compare" columns (type 1: term = [a != b]).
+constexpr int kChunkBytes = 128;
+enum : uint8_t { kChunkContinuous = 0, kChunkCompare = 1 };
+
+// Per-target-row result of the neighbour selection, consumed by the
+// accumulation kernels.  coef[code] is the coefficient of a pair with
+// neighbour code `code` (FS_MASK_*), already carrying the sign and the
+// per-row 1/|H_i|, 1/|M_i| normalisation (MultiSURF.py:245-251).
+struct RowInfo {
+    double thresh;
+    double coef[5];
+    int32_t n_hit, n_miss, n_far, pad;
+};
+
+// Working set of one fs_score call: the active columns split by path.
+struct WorkSet {
+    // general (CUDA-core) path
+    int64_t pg = 0;        // active general columns
+    int64_t ldg = 0;       // padded column count (multiple of the chunk)
+    int elem = 4;          // sizeof(T): 4 (FS_ARITH_F32) or 8 (FS_ARITH_F64)
+    DevBuf<char> xg;       // [n, ldg] of T, internal row order
+    DevBuf<float> rg;      // [ldg] recip (0 in padding)
+    DevBuf<uint8_t> ctype; // [ldg / chunk]
+    DevBuf<int64_t> gcol;  // [pg] original column of each general column
+    DevBuf<int64_t> gout;  // [pg] position in the caller's feat_idx list
+    std::vector<int64_t> h_gcol, h_gout;
+    int64_t n_cont = 0, n_cmp = 0;
+    // one-hot tensor-core path (filled by onehot.cu)
+    int64_t pt = 0;                 // active tensor-path columns
+    int64_t K = 0;                  // sum of V_f, padded to 128
+    std::vector<int64_t> h_tcol, h_tout, h_toff;
+    DevBuf<int64_t> tcol, tout;     // [pt]
+    DevBuf<int32_t> toff;           // [pt+1] first one-hot row of each column
+    DevBuf<int32_t> krow_col;       // [K] tensor column of each one-hot row (-1 = padding)
+    DevBuf<int8_t> A;               // [n_pad, K]   sample-major one-hot (K-major)
+    DevBuf<int8_t> At;              // [K, n_pad]   feature-major one-hot (sample-major)
+    int64_t n_pad = 0;
+    // cache key
+    std::vector<int64_t> key;
+    bool valid = false;
+};
+
+}  // namespace fs
+
+struct fs_dataset {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t n = 0, p = 0;
+    int dtype = FS_F32;
+    int n_classes = 0;
+    // raw matrix on the device, original row order
+    const void *x = nullptr;
+    int64_t ldx = 0;
+    fs::DevBuf<char> x_owned;
+    // class-sorted internal order
+    std::vector<int64_t> perm, inv_perm;     // perm[r] = original index of internal row r
+    std::vector<int32_t> y_sorted;           // class of internal row r
+    std::vector<int64_t> cls_start;          // [C+1] internal row range of each class
+    fs::DevBuf<int64_t> d_perm;
+    fs::DevBuf<int32_t> d_y;
+    fs::DevBuf<int64_t> d_cls_start;
+    // column scan
+    fs::DevBuf<double> d_cmin, d_cmax, d_vals;  // d_vals: [p, FS_DISTINCT_CAP]
+    fs::DevBuf<int32_t> d_cnt;
+    std::vector<double> cmin, cmax;
+    std::vector<int32_t> cnt;
+    // typing
+    bool have_features = false;
+    int arith = FS_ARITH_F32;
+    std::vector<uint8_t> is_discrete;
+    std::vector<float> recip;
+    // per-call scratch, kept between calls (TuRF re-scores the same data set)
+    fs::WorkSet ws;
+    fs::DevBuf<double> Dc;        // [R, ldn] continuous/general distance part
+    fs::DevBuf<int32_t> Dd;       // [R, ldn] one-hot mismatch counts
+    fs::DevBuf<int8_t> sel;       // [R, ldn] neighbour codes
+    fs::DevBuf<fs::RowInfo> rinfo;
+    fs::DevBuf<int64_t> row_ids;
+    fs::DevBuf<double> partial;   // accumulation partials
+    fs::DevBuf<double> wsum;      // [n_kept]
+    fs::DevBuf<int32_t> nbr_idx;  // ReliefF neighbour lists
+    fs::DevBuf<double> nbr_w;
+    fs::DevBuf<int32_t> nbr_cnt;
+    fs::DevBuf<float> d_class_probs;
+    fs::DevBuf<char> xa_gather;   // gathered target rows (fs_debug_rows)
+    fs::DevBuf<double> tpartial;  // tensor-path accumulation partials
+    fs::DevBuf<int8_t> maskH, maskM;
+    fs::DevBuf<unsigned long long> counters;
+};
+
+namespace fs {
+
+// dataset.cu
+void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool allow_tensor, int *launches);
+
+// dist_general.cu: D[r, j] = sum over general columns of the per-feature term
+// between target row r (rows of xa) and sample j (rows of xb).
+void launch_dist_general(const WorkSet &ws, const void *xa, int64_t na, const void *xb, int64_t nb,
+                         double *D, int64_t ldd, cudaStream_t st, int *launches);
+
+// select.cu
+void launch_select(fs_dataset *ds, int algo, int use_star, int32_t k, const int64_t *row_ids, int64_t R,
+                   const double *Dc, const int32_t *Dd, int64_t ldn, int8_t *sel, RowInfo *rinfo,
+                   int32_t *nbr_idx, double *nbr_w, int32_t *nbr_cnt, int32_t nbr_cap,
+                   const float *class_probs, cudaStream_t st, int *launches);
+
+// accum_general.cu
+int64_t accum_general_partials(const WorkSet &ws, int64_t R);
+void launch_accum_general(const WorkSet &ws, int64_t n, const void *xa, const int8_t *sel, int64_t ldn,
+                          const RowInfo *rinfo, int64_t R, double *partial, int64_t n_part,
+                          cudaStream_t st, int *launches);
+void launch_relieff_gather(const WorkSet &ws, int64_t n, const void *xa, const int32_t *nbr_idx,
+                           const double *nbr_w, const int32_t *nbr_cnt, int32_t nbr_cap, int64_t R,
+                           double *partial, int64_t n_part, cudaStream_t st, int *launches);
+// wsum[gout[c]] += sum_q partial[q, c]  (fixed order => bitwise reproducible)
+void launch_reduce_partials(const WorkSet &ws, const double *partial, int64_t n_part, double *wsum,
+                            cudaStream_t st, int *launches);
+
+}  // namespace fs

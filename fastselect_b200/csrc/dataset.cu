@@ -1,0 +1,395 @@
+// dataset.cu -- device-resident data set: upload, per-column scan (min / max /
+// distinct values), class-sorted row order, and the per-call working set of
+// active columns.  Replaces cuda.to_device(x) and the host np.unique / range pass
+// of the reference's fit (MultiSURF.py:409-425, SURF.py:347-365, ReliefF.py:366-391)
+// and TuRF's X[:, active] copy (TuRF.py:110).
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace fs {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char *get_error() { return g_err; }
+
+// ---------------------------------------------------------------------------
+// column scan: one thread per column, rows streamed coalesced across columns.
+// HBM-bound: reads n*p*sizeof(T) once.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) column_scan_kernel(const T *__restrict__ x, int64_t n, int64_t p,
+                                                          int64_t ldx, double *__restrict__ cmin,
+                                                          double *__restrict__ cmax, int32_t *__restrict__ cnt,
+                                                          double *__restrict__ vals) {
+    int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= p) return;
+    T set[FS_DISTINCT_CAP];
+    int c = 0;
+    bool over = false;
+    T mn = x[f], mx = x[f];
+    for (int64_t i = 0; i < n; ++i) {
+        T v = x[i * ldx + f];
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+        if (!over) {
+            bool found = false;
+#pragma unroll
+            for (int q = 0; q < FS_DISTINCT_CAP; ++q) found |= (q < c) && (set[q] == v);
+            if (!found) {
+                if (c < FS_DISTINCT_CAP) {
+#pragma unroll
+                    for (int q = 0; q < FS_DISTINCT_CAP; ++q)
+                        if (q == c) set[q] = v;
+                    ++c;
+                } else {
+                    over = true;
+                }
+            }
+        }
+    }
+    cmin[f] = (double)mn;
+    cmax[f] = (double)mx;
+    cnt[f] = over ? FS_DISTINCT_CAP + 1 : c;
+#pragma unroll
+    for (int q = 0; q < FS_DISTINCT_CAP; ++q) vals[f * FS_DISTINCT_CAP + q] = q < c ? (double)set[q] : 0.0;
+}
+
+template <typename T>
+static void run_scan(fs_dataset *ds) {
+    int64_t p = ds->p;
+    dim3 grid((unsigned)ceil_div(p, 128));
+    column_scan_kernel<T><<<grid, 128, 0, ds->stream>>>(static_cast<const T *>(ds->x), ds->n, p, ds->ldx,
+                                                         ds->d_cmin.ptr, ds->d_cmax.ptr, ds->d_cnt.ptr,
+                                                         ds->d_vals.ptr);
+    FS_CUDA(cudaGetLastError());
+}
+
+static size_t dtype_size(int dtype) {
+    switch (dtype) {
+        case FS_U8:
+        case FS_I8: return 1;
+        case FS_F32: return 4;
+        case FS_F64: return 8;
+    }
+    return 0;
+}
+
+static void finish_create(fs_dataset *ds, const int32_t *y_enc) {
+    const int64_t n = ds->n, p = ds->p;
+    // stable class sort of the samples: hits of a target are one contiguous row
+    // range, each miss class another (used by ReliefF's per-class selection).
+    ds->perm.resize(n);
+    std::iota(ds->perm.begin(), ds->perm.end(), (int64_t)0);
+    std::stable_sort(ds->perm.begin(), ds->perm.end(),
+                     [&](int64_t a, int64_t b) { return y_enc[a] < y_enc[b]; });
+    ds->inv_perm.resize(n);
+    ds->y_sorted.resize(n);
+    ds->cls_start.assign(ds->n_classes + 1, 0);
+    for (int64_t r = 0; r < n; ++r) {
+        ds->inv_perm[ds->perm[r]] = r;
+        ds->y_sorted[r] = y_enc[ds->perm[r]];
+        ds->cls_start[ds->y_sorted[r] + 1]++;
+    }
+    for (int c = 0; c < ds->n_classes; ++c) ds->cls_start[c + 1] += ds->cls_start[c];
+    ds->d_perm.alloc(n);
+    ds->d_y.alloc(n);
+    ds->d_cls_start.alloc(ds->n_classes + 1);
+    FS_CUDA(cudaMemcpyAsync(ds->d_perm.ptr, ds->perm.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ds->stream));
+    FS_CUDA(cudaMemcpyAsync(ds->d_y.ptr, ds->y_sorted.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, ds->stream));
+    FS_CUDA(cudaMemcpyAsync(ds->d_cls_start.ptr, ds->cls_start.data(), (ds->n_classes + 1) * sizeof(int64_t),
+                            cudaMemcpyHostToDevice, ds->stream));
+    // column scan
+    ds->d_cmin.alloc(p);
+    ds->d_cmax.alloc(p);
+    ds->d_cnt.alloc(p);
+    ds->d_vals.alloc((size_t)p * FS_DISTINCT_CAP);
+    switch (ds->dtype) {
+        case FS_U8: run_scan<uint8_t>(ds); break;
+        case FS_I8: run_scan<int8_t>(ds); break;
+        case FS_F32: run_scan<float>(ds); break;
+        case FS_F64: run_scan<double>(ds); break;
+    }
+    ds->cmin.resize(p);
+    ds->cmax.resize(p);
+    ds->cnt.resize(p);
+    FS_CUDA(cudaMemcpyAsync(ds->cmin.data(), ds->d_cmin.ptr, p * sizeof(double), cudaMemcpyDeviceToHost, ds->stream));
+    FS_CUDA(cudaMemcpyAsync(ds->cmax.data(), ds->d_cmax.ptr, p * sizeof(double), cudaMemcpyDeviceToHost, ds->stream));
+    FS_CUDA(cudaMemcpyAsync(ds->cnt.data(), ds->d_cnt.ptr, p * sizeof(int32_t), cudaMemcpyDeviceToHost, ds->stream));
+    FS_CUDA(cudaStreamSynchronize(ds->stream));
+}
+
+static int usable_devices() {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int d = 0; d < count; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+static fs_dataset *create_common(int dtype, int64_t n, int64_t p, int64_t ld, const int32_t *y_enc,
+                                 int32_t n_classes, int32_t device, void *stream) {
+    FS_REQUIRE(n >= 2 && p >= 1, FS_ERR_INVALID, "fs_dataset_create: need n >= 2 and p >= 1 (got n=%lld p=%lld)",
+               (long long)n, (long long)p);
+    FS_REQUIRE(n < (1LL << 31) - 256, FS_ERR_INVALID, "fs_dataset_create: n too large");
+    FS_REQUIRE(dtype_size(dtype) != 0, FS_ERR_INVALID, "fs_dataset_create: unknown dtype %d", dtype);
+    FS_REQUIRE(ld >= p, FS_ERR_INVALID, "fs_dataset_create: row stride %lld < p %lld", (long long)ld, (long long)p);
+    FS_REQUIRE(y_enc != nullptr && n_classes >= 1, FS_ERR_INVALID, "fs_dataset_create: y_enc / n_classes missing");
+    for (int64_t i = 0; i < n; ++i)
+        FS_REQUIRE(y_enc[i] >= 0 && y_enc[i] < n_classes, FS_ERR_INVALID,
+                   "fs_dataset_create: y_enc[%lld]=%d outside [0,%d)", (long long)i, y_enc[i], n_classes);
+    FS_REQUIRE(usable_devices() > 0, FS_ERR_NO_DEVICE,
+               "no usable NVIDIA sm_100 (B200) GPU: this library has no CPU fallback");
+    int major = 0;
+    FS_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    FS_REQUIRE(major == 10, FS_ERR_NO_DEVICE, "device %d is not sm_100 (compute capability major %d)", device, major);
+    FS_CUDA(cudaSetDevice(device));
+    fs_dataset *ds = new fs_dataset();
+    ds->device = device;
+    ds->stream = static_cast<cudaStream_t>(stream);
+    ds->n = n;
+    ds->p = p;
+    ds->dtype = dtype;
+    ds->n_classes = n_classes;
+    return ds;
+}
+
+// ---------------------------------------------------------------------------
+// working set: gather the active general-path columns, internal row order
+// ---------------------------------------------------------------------------
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256) gather_general_kernel(const Tin *__restrict__ x, int64_t ldx,
+                                                             const int64_t *__restrict__ perm,
+                                                             const int64_t *__restrict__ col, int64_t pg,
+                                                             int64_t n, int64_t ldg, Tout *__restrict__ out) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t r = blockIdx.y;
+    if (c >= ldg) return;
+    for (; r < n; r += gridDim.y) {
+        Tout v = (Tout)0;
+        if (c < pg) {
+            int64_t src = col[c];
+            if (src >= 0) v = (Tout)x[perm[r] * ldx + src];
+        }
+        out[r * ldg + c] = v;
+    }
+}
+
+template <typename Tin>
+static void run_gather(fs_dataset *ds, WorkSet &ws, int *launches) {
+    dim3 grid((unsigned)ceil_div(ws.ldg, 256), (unsigned)std::min<int64_t>(ds->n, 4096));
+    if (ws.elem == 4)
+        gather_general_kernel<Tin, float><<<grid, 256, 0, ds->stream>>>(
+            static_cast<const Tin *>(ds->x), ds->ldx, ds->d_perm.ptr, ws.gcol.ptr, ws.pg, ds->n, ws.ldg,
+            reinterpret_cast<float *>(ws.xg.ptr));
+    else
+        gather_general_kernel<Tin, double><<<grid, 256, 0, ds->stream>>>(
+            static_cast<const Tin *>(ds->x), ds->ldx, ds->d_perm.ptr, ws.gcol.ptr, ws.pg, ds->n, ws.ldg,
+            reinterpret_cast<double *>(ws.xg.ptr));
+    FS_CUDA(cudaGetLastError());
+    ++*launches;
+}
+
+void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches);  // onehot.cu
+
+void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool allow_tensor, int *launches) {
+    WorkSet &ws = ds->ws;
+    std::vector<int64_t> key(n_kept + 2);
+    key[0] = allow_tensor ? 1 : 0;
+    key[1] = ds->arith;
+    for (int64_t c = 0; c < n_kept; ++c) key[c + 2] = feat_idx ? feat_idx[c] : c;
+    if (ws.valid && ws.key == key) return;
+    ws.valid = false;
+    const int chunk = kChunkBytes / (ds->arith == FS_ARITH_F64 ? 8 : 4);
+    ws.elem = ds->arith == FS_ARITH_F64 ? 8 : 4;
+
+    // split the active columns: one-hot tensor path (discrete, V <= FS_DISTINCT_CAP),
+    // continuous, and wide discrete ("compare") columns
+    std::vector<int64_t> cont_col, cont_out, cmp_col, cmp_out;
+    ws.h_tcol.clear();
+    ws.h_tout.clear();
+    for (int64_t c = 0; c < n_kept; ++c) {
+        int64_t f = key[c + 2];
+        FS_REQUIRE(f >= 0 && f < ds->p, FS_ERR_INVALID, "feat_idx[%lld]=%lld outside [0,%lld)", (long long)c,
+                   (long long)f, (long long)ds->p);
+        if (ds->is_discrete[f]) {
+            if (allow_tensor && ds->cnt[f] <= FS_DISTINCT_CAP) {
+                ws.h_tcol.push_back(f);
+                ws.h_tout.push_back(c);
+            } else {
+                cmp_col.push_back(f);
+                cmp_out.push_back(c);
+            }
+        } else {
+            cont_col.push_back(f);
+            cont_out.push_back(c);
+        }
+    }
+    ws.pt = (int64_t)ws.h_tcol.size();
+    ws.n_cont = (int64_t)cont_col.size();
+    ws.n_cmp = (int64_t)cmp_col.size();
+
+    // general path layout: [continuous | pad to chunk | compare | pad to chunk]
+    ws.h_gcol.clear();
+    ws.h_gout.clear();
+    std::vector<uint8_t> ctype;
+    std::vector<float> rg;
+    auto append = [&](const std::vector<int64_t> &cols, const std::vector<int64_t> &outs, uint8_t type) {
+        if (cols.empty()) return;
+        for (size_t q = 0; q < cols.size(); ++q) {
+            ws.h_gcol.push_back(cols[q]);
+            ws.h_gout.push_back(outs[q]);
+            rg.push_back(type == kChunkContinuous ? ds->recip[cols[q]] : 0.0f);
+        }
+        while (ws.h_gcol.size() % chunk) {
+            ws.h_gcol.push_back(-1);
+            ws.h_gout.push_back(-1);
+            rg.push_back(0.0f);
+        }
+        ctype.resize(ws.h_gcol.size() / chunk, type);
+    };
+    append(cont_col, cont_out, kChunkContinuous);
+    append(cmp_col, cmp_out, kChunkCompare);
+    ws.pg = (int64_t)ws.h_gcol.size();
+    ws.ldg = ws.pg;
+    if (ws.pg > 0) {
+        ws.xg.reserve((size_t)ds->n * ws.ldg * ws.elem);
+        ws.rg.reserve(ws.ldg);
+        ws.ctype.reserve(ctype.size());
+        ws.gcol.reserve(ws.pg);
+        ws.gout.reserve(ws.pg);
+        FS_CUDA(cudaMemcpyAsync(ws.rg.ptr, rg.data(), rg.size() * sizeof(float), cudaMemcpyHostToDevice, ds->stream));
+        FS_CUDA(cudaMemcpyAsync(ws.ctype.ptr, ctype.data(), ctype.size(), cudaMemcpyHostToDevice, ds->stream));
+        FS_CUDA(cudaMemcpyAsync(ws.gcol.ptr, ws.h_gcol.data(), ws.pg * sizeof(int64_t), cudaMemcpyHostToDevice, ds->stream));
+        FS_CUDA(cudaMemcpyAsync(ws.gout.ptr, ws.h_gout.data(), ws.pg * sizeof(int64_t), cudaMemcpyHostToDevice, ds->stream));
+        switch (ds->dtype) {
+            case FS_U8: run_gather<uint8_t>(ds, ws, launches); break;
+            case FS_I8: run_gather<int8_t>(ds, ws, launches); break;
+            case FS_F32: run_gather<float>(ds, ws, launches); break;
+            case FS_F64: run_gather<double>(ds, ws, launches); break;
+        }
+        // the staging vectors must outlive the async copies
+        FS_CUDA(cudaStreamSynchronize(ds->stream));
+    }
+    ws.K = 0;
+    if (ws.pt > 0) build_onehot(ds, ws, launches);
+    ws.key = std::move(key);
+    ws.valid = true;
+}
+
+}  // namespace fs
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+using namespace fs;
+
+extern "C" {
+
+int fs_device_count(void) { return usable_devices(); }
+const char *fs_last_error(void) { return get_error(); }
+int fs_abi_version(void) { return FS_ABI_VERSION; }
+
+int fs_dataset_create(fs_dataset **out, const void *x, int dtype, int64_t n, int64_t p, int64_t row_stride_elems,
+                      const int32_t *y_enc, int32_t n_classes, int32_t device, void *stream) {
+    fs_dataset *ds = nullptr;
+    try {
+        FS_REQUIRE(out && x, FS_ERR_INVALID, "fs_dataset_create: null pointer");
+        ds = create_common(dtype, n, p, row_stride_elems, y_enc, n_classes, device, stream);
+        size_t es = dtype_size(dtype);
+        ds->ldx = round_up(p, 16 / (int64_t)es > 0 ? 16 / (int64_t)es : 1);
+        ds->x_owned.alloc((size_t)n * ds->ldx * es);
+        ds->x = ds->x_owned.ptr;
+        FS_CUDA(cudaMemcpy2DAsync(ds->x_owned.ptr, ds->ldx * es, x, row_stride_elems * es, p * es, n,
+                                  cudaMemcpyHostToDevice, ds->stream));
+        finish_create(ds, y_enc);
+        *out = ds;
+        return FS_OK;
+    } catch (const Fail &f) {
+        delete ds;
+        return f.code;
+    } catch (const std::exception &e) {
+        set_error("fs_dataset_create: %s", e.what());
+        delete ds;
+        return FS_ERR_OOM;
+    }
+}
+
+int fs_dataset_create_device(fs_dataset **out, const void *x_dev, int dtype, int64_t n, int64_t p,
+                             int64_t row_stride_elems, const int32_t *y_enc, int32_t n_classes, int32_t device,
+                             void *stream) {
+    fs_dataset *ds = nullptr;
+    try {
+        FS_REQUIRE(out && x_dev, FS_ERR_INVALID, "fs_dataset_create_device: null pointer");
+        ds = create_common(dtype, n, p, row_stride_elems, y_enc, n_classes, device, stream);
+        ds->x = x_dev;
+        ds->ldx = row_stride_elems;
+        finish_create(ds, y_enc);
+        *out = ds;
+        return FS_OK;
+    } catch (const Fail &f) {
+        delete ds;
+        return f.code;
+    } catch (const std::exception &e) {
+        set_error("fs_dataset_create_device: %s", e.what());
+        delete ds;
+        return FS_ERR_OOM;
+    }
+}
+
+int fs_dataset_column_stats(const fs_dataset *ds, double *col_min, double *col_max, int32_t *n_distinct) {
+    if (!ds) {
+        set_error("fs_dataset_column_stats: null data set");
+        return FS_ERR_INVALID;
+    }
+    if (col_min) memcpy(col_min, ds->cmin.data(), ds->p * sizeof(double));
+    if (col_max) memcpy(col_max, ds->cmax.data(), ds->p * sizeof(double));
+    if (n_distinct) memcpy(n_distinct, ds->cnt.data(), ds->p * sizeof(int32_t));
+    return FS_OK;
+}
+
+int fs_dataset_set_features(fs_dataset *ds, const uint8_t *is_discrete, const float *recip, int arith) {
+    if (!ds || !is_discrete || !recip || (arith != FS_ARITH_F32 && arith != FS_ARITH_F64)) {
+        set_error("fs_dataset_set_features: invalid argument");
+        return FS_ERR_INVALID;
+    }
+    ds->is_discrete.assign(is_discrete, is_discrete + ds->p);
+    ds->recip.assign(recip, recip + ds->p);
+    ds->arith = arith;
+    ds->have_features = true;
+    ds->ws.valid = false;
+    return FS_OK;
+}
+
+int fs_dataset_row_order(const fs_dataset *ds, int64_t *perm_out) {
+    if (!ds || !perm_out) {
+        set_error("fs_dataset_row_order: invalid argument");
+        return FS_ERR_INVALID;
+    }
+    memcpy(perm_out, ds->perm.data(), ds->n * sizeof(int64_t));
+    return FS_OK;
+}
+
+int fs_dataset_destroy(fs_dataset *ds) {
+    if (!ds) return FS_OK;
+    cudaSetDevice(ds->device);
+    cudaStreamSynchronize(ds->stream);
+    delete ds;
+    return FS_OK;
+}
+
+}  // extern "C"

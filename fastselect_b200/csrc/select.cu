@@ -1,0 +1,283 @@
+// select.cu -- per-target-row neighbour selection (one CTA per target row).
+//
+// Replaces, for each target i:
+//   MultiSURF: mu_i, sigma_i, T_i = mu_i - sigma_i/2 and the near/far test d_ij < T_i
+//              (MultiSURF.py:175-196, :216-243);
+//   SURF:      the float32 mean distance and d_ij < mean (SURF.py:146-163, :175-190);
+//   ReliefF:   k nearest hits and k nearest misses of every other class
+//              (ReliefF.py:144-175) with per-neighbour weights (ReliefF.py:177-216).
+// Output: one int8 neighbour code per pair (FS_MASK_*), a RowInfo per target with
+// the per-code coefficients, and for ReliefF a compact neighbour list.
+// HBM/L2-bound: each kernel streams its distance row twice (the row is L2-resident).
+#include "common.cuh"
+
+namespace fs {
+
+__device__ __forceinline__ double load_d(const double *Dc, const int32_t *Dd, int64_t off) {
+    double d = Dc ? Dc[off] : 0.0;
+    if (Dd) d += (double)Dd[off];
+    return d;
+}
+
+// deterministic block sum (fixed order): warp shuffles, then warp partials in order
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T *scratch /*[8]*/) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T s = scratch[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s += scratch[w];
+    return s;
+}
+
+template <int ALGO>
+__global__ void __launch_bounds__(256) select_threshold_kernel(const double *__restrict__ Dc,
+                                                               const int32_t *__restrict__ Dd, int64_t ldn,
+                                                               int64_t n, const int64_t *__restrict__ row_ids,
+                                                               const int32_t *__restrict__ y, int use_star,
+                                                               int8_t *__restrict__ sel,
+                                                               RowInfo *__restrict__ rinfo) {
+    __shared__ double sd[8];
+    __shared__ int si[8];
+    __shared__ double s_thresh;
+    const int64_t r = blockIdx.x;
+    const int64_t self = row_ids[r];
+    const int64_t base = r * ldn;
+    const int tid = threadIdx.x;
+    const double inv = 1.0 / (double)(n - 1);
+
+    if (ALGO == FS_MULTISURF) {
+        // pass 1: sum d, sum d^2 over j != i (MultiSURF.py:175-191)
+        double s1 = 0.0, s2 = 0.0;
+        for (int64_t j = tid; j < n; j += 256) {
+            if (j == self) continue;
+            double d = load_d(Dc, Dd, base + j);
+            s1 += d;
+            s2 = __fma_rn(d, d, s2);
+        }
+        s1 = block_sum(s1, sd);
+        s2 = block_sum(s2, sd);
+        if (tid == 0) {
+            // MultiSURF.py:193-196 with the roundings of the reference's JIT'd code
+            // (multiply by 1/(n-1); fused sum_d2*inv - mu*mu); see oracle/fs_oracle.c
+            double mu = __dmul_rn(s1, inv);
+            double var = __fma_rn(s2, inv, -__dmul_rn(mu, mu));
+            var = var > 0.0 ? var : 0.0;
+            s_thresh = __dsub_rn(mu, __dmul_rn(0.5, __dsqrt_rn(var)));
+        }
+    } else {
+        // SURF.py:146-163: distances rounded to float32, d_ii = 0 included in the sum,
+        // float32 sum (taken in float64 and rounded once), times 1/(n-1) in float64
+        double s = 0.0;
+        for (int64_t j = tid; j < n; j += 256) {
+            if (j == self) continue;
+            s += (double)(float)load_d(Dc, Dd, base + j);
+        }
+        s = block_sum(s, sd);
+        if (tid == 0) s_thresh = __dmul_rn((double)(float)s, inv);
+    }
+    __syncthreads();
+    const double thresh = s_thresh;
+    const int32_t yi = y[self];
+    int nh = 0, nm = 0, nf = 0;
+    for (int64_t j = tid; j < n; j += 256) {
+        int code = FS_MASK_NONE;
+        if (j != self) {
+            double d = load_d(Dc, Dd, base + j);
+            if (ALGO == FS_SURF) d = (double)(float)d;
+            const bool hit = (y[j] == yi);
+            if (d < thresh) {
+                code = hit ? FS_MASK_NEAR_HIT : FS_MASK_NEAR_MISS;
+            } else if (use_star) {
+                if (!hit) code = FS_MASK_FAR_MISS;
+                else if (ALGO == FS_SURF) code = FS_MASK_FAR_HIT;
+            }
+        }
+        sel[base + j] = (int8_t)code;
+        nh += (code == FS_MASK_NEAR_HIT);
+        nm += (code == FS_MASK_NEAR_MISS);
+        nf += (code == FS_MASK_FAR_MISS) + (code == FS_MASK_FAR_HIT);
+    }
+    nh = block_sum(nh, si);
+    nm = block_sum(nm, si);
+    nf = block_sum(nf, si);
+    if (tid == 0) {
+        RowInfo ri;
+        ri.thresh = thresh;
+        ri.n_hit = nh;
+        ri.n_miss = nm;
+        ri.n_far = nf;
+        ri.pad = 0;
+        ri.coef[0] = 0.0;
+        if (ALGO == FS_MULTISURF) {
+            // MultiSURF.py:245-251: divide by the counts unless they are zero;
+            // the far-miss term shares the near-miss normalisation
+            const double sh = nh > 0 ? 1.0 / (double)nh : 1.0;
+            const double sm = nm > 0 ? 1.0 / (double)nm : 1.0;
+            ri.coef[FS_MASK_NEAR_HIT] = -sh;
+            ri.coef[FS_MASK_NEAR_MISS] = sm;
+            ri.coef[FS_MASK_FAR_MISS] = -sm;
+            ri.coef[FS_MASK_FAR_HIT] = 0.0;
+        } else {
+            // SURF.py:191-193: near_miss - near_hit (+ far_hit - far_miss), no normalisation
+            ri.coef[FS_MASK_NEAR_HIT] = -1.0;
+            ri.coef[FS_MASK_NEAR_MISS] = 1.0;
+            ri.coef[FS_MASK_FAR_MISS] = -1.0;
+            ri.coef[FS_MASK_FAR_HIT] = 1.0;
+        }
+        rinfo[r] = ri;
+    }
+}
+
+// exclusive rank of `flag` within the CTA (thread order) and the CTA total
+__device__ __forceinline__ int block_rank(bool flag, int *warp_tot /*[8]*/, int &total) {
+    const unsigned b = __ballot_sync(0xffffffffu, flag);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r = __popc(b & ((1u << lane) - 1u));
+    __syncthreads();
+    if (lane == 0) warp_tot[w] = __popc(b);
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int t = warp_tot[q];
+        off += (q < w) ? t : 0;
+        tot += t;
+    }
+    total = tot;
+    return off + r;
+}
+
+__global__ void __launch_bounds__(256) relieff_select_kernel(
+    const double *__restrict__ Dc, const int32_t *__restrict__ Dd, int64_t ldn, int64_t n,
+    const int64_t *__restrict__ row_ids, const int32_t *__restrict__ y, const int64_t *__restrict__ cls_start,
+    int n_classes, int k, const float *__restrict__ class_probs, int8_t *__restrict__ sel,
+    RowInfo *__restrict__ rinfo, int32_t *__restrict__ nbr_idx, double *__restrict__ nbr_w,
+    int32_t *__restrict__ nbr_cnt, int nbr_cap) {
+    __shared__ int hist[256];
+    __shared__ int warp_tot[8];
+    __shared__ unsigned s_prefix;
+    __shared__ int s_remaining;
+    const int64_t r = blockIdx.x;
+    const int64_t self = row_ids[r];
+    const int64_t base = r * ldn;
+    const int tid = threadIdx.x;
+    const int ci = y[self];
+
+    for (int64_t j = tid; j < n; j += 256) sel[base + j] = FS_MASK_NONE;
+    // ReliefF.py:177-179
+    double denom = 1.0 - (double)class_probs[ci];
+    if (denom == 0.0) denom = 1.0;
+
+    auto key_of = [&](int64_t j) -> unsigned {
+        // ReliefF.py:144-155: float32 distances, inf on the diagonal (the target itself
+        // stays a candidate of its own class and is taken last)
+        return j == self ? 0x7f800000u : __float_as_uint((float)load_d(Dc, Dd, base + j));
+    };
+
+    int slot_base = 0, n_hit = 0, n_miss = 0;
+    for (int c = 0; c < n_classes; ++c) {
+        const int64_t s0 = cls_start[c], s1 = cls_start[c + 1];
+        const int64_t len = s1 - s0;
+        const int kk = (int)(len < (int64_t)k ? len : (int64_t)k);
+        if (kk == 0) continue;
+        // ReliefF.py:181-216: -1/h_found per hit; P(c)/(1-P(c_i))/k per miss of class c
+        const double w = (c == ci) ? -1.0 / (double)kk : ((double)class_probs[c] / denom) / (double)k;
+        const int8_t code = (c == ci) ? FS_MASK_NEAR_HIT : FS_MASK_NEAR_MISS;
+        unsigned kth = 0xffffffffu;
+        int need_eq = 0;
+        if (kk < len) {
+            // radix select of the kk-th smallest key, 8 bits per pass, MSB first
+            __syncthreads();
+            if (tid == 0) { s_prefix = 0u; s_remaining = kk; }
+            unsigned mask = 0u;
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                hist[tid] = 0;
+                __syncthreads();
+                const unsigned prefix = s_prefix;
+                for (int64_t j = s0 + tid; j < s1; j += 256) {
+                    const unsigned key = key_of(j);
+                    if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int rem = s_remaining, cum = 0, b = 0;
+                    for (; b < 256; ++b) {
+                        if (cum + hist[b] >= rem) break;
+                        cum += hist[b];
+                    }
+                    s_remaining = rem - cum;
+                    s_prefix = prefix | ((unsigned)b << shift);
+                }
+                mask |= 255u << shift;
+                __syncthreads();
+            }
+            kth = s_prefix;
+            need_eq = s_remaining;
+        }
+        // ordered pass: ties at the k-th distance are taken in sample order
+        int eq_taken = 0, slot = slot_base;
+        for (int64_t b0 = s0; b0 < s1; b0 += 256) {
+            const int64_t j = b0 + tid;
+            const bool valid = j < s1;
+            bool take = valid;
+            if (kk < len) {
+                const unsigned key = valid ? key_of(j) : 0xffffffffu;
+                const bool eq = valid && key == kth;
+                int tot_eq;
+                const int rk = block_rank(eq, warp_tot, tot_eq);
+                take = valid && (key < kth || (eq && eq_taken + rk < need_eq));
+                eq_taken += tot_eq;
+            }
+            int tot_take;
+            const int rk2 = block_rank(take, warp_tot, tot_take);
+            if (take) {
+                const int sidx = slot + rk2;
+                sel[base + j] = code;
+                if (sidx < nbr_cap) {
+                    nbr_idx[r * nbr_cap + sidx] = (int32_t)j;
+                    nbr_w[r * nbr_cap + sidx] = w;
+                }
+            }
+            slot += tot_take;
+        }
+        if (c == ci) n_hit += slot - slot_base; else n_miss += slot - slot_base;
+        slot_base = slot;
+    }
+    if (tid == 0) {
+        nbr_cnt[r] = slot_base < nbr_cap ? slot_base : nbr_cap;
+        RowInfo ri;
+        ri.thresh = 0.0;
+        for (int q = 0; q < 5; ++q) ri.coef[q] = 0.0;
+        ri.n_hit = n_hit;
+        ri.n_miss = n_miss;
+        ri.n_far = 0;
+        ri.pad = 0;
+        rinfo[r] = ri;
+    }
+}
+
+void launch_select(fs_dataset *ds, int algo, int use_star, int32_t k, const int64_t *row_ids, int64_t R,
+                   const double *Dc, const int32_t *Dd, int64_t ldn, int8_t *sel, RowInfo *rinfo,
+                   int32_t *nbr_idx, double *nbr_w, int32_t *nbr_cnt, int32_t nbr_cap, const float *class_probs,
+                   cudaStream_t st, int *launches) {
+    if (R == 0) return;
+    dim3 grid((unsigned)R);
+    if (algo == FS_MULTISURF)
+        select_threshold_kernel<FS_MULTISURF><<<grid, 256, 0, st>>>(Dc, Dd, ldn, ds->n, row_ids, ds->d_y.ptr,
+                                                                    use_star, sel, rinfo);
+    else if (algo == FS_SURF)
+        select_threshold_kernel<FS_SURF><<<grid, 256, 0, st>>>(Dc, Dd, ldn, ds->n, row_ids, ds->d_y.ptr, use_star,
+                                                               sel, rinfo);
+    else
+        relieff_select_kernel<<<grid, 256, 0, st>>>(Dc, Dd, ldn, ds->n, row_ids, ds->d_y.ptr, ds->d_cls_start.ptr,
+                                                    ds->n_classes, k, class_probs, sel, rinfo, nbr_idx, nbr_w,
+                                                    nbr_cnt, nbr_cap);
+    FS_CUDA(cudaGetLastError());
+    ++*launches;
+}
+
+}  // namespace fs

@@ -1,0 +1,151 @@
+/*
+ * fastselect_b200.h -- C ABI of libfastselect_b200.so
+ *
+ * B200-native (sm_100a) replacement for the Relief-family scoring hot path of
+ * GavinLynch04/FastSelect: the n x n sample-pair distance computation, the
+ * per-instance neighbour selection and the per-feature hit/miss weight
+ * accumulation behind ReliefF, SURF, SURF*, MultiSURF, MultiSURF* (and TuRF,
+ * which re-scores column subsets of one resident data set).
+ *
+ * Each entry point names the reference interface it replaces; citations are
+ * file:line into the reference's src/fast_select/.
+ *
+ * Conventions: every function returns 0 on success and a negative fs_status on
+ * failure; fs_last_error() returns a thread-local message for the last failure.
+ * All output buffers are caller-allocated.  The library never keeps or frees
+ * caller memory.  Calls on one fs_dataset must not overlap; different data sets
+ * may be used from different threads.  There is NO CPU fallback: every compute
+ * entry point fails with FS_ERR_NO_DEVICE when no sm_100 GPU is usable.
+ */
+#ifndef FASTSELECT_B200_H
+#define FASTSELECT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FS_API __attribute__((visibility("default")))
+#else
+#define FS_API
+#endif
+
+#define FS_ABI_VERSION 1
+/* distinct values tracked per column by fs_dataset_create; a column with more
+ * distinct values reports FS_DISTINCT_CAP + 1 */
+#define FS_DISTINCT_CAP 16
+
+typedef struct fs_dataset fs_dataset; /* opaque; device-resident */
+
+typedef enum { FS_RELIEFF = 0, FS_SURF = 1, FS_MULTISURF = 2 } fs_algo;
+typedef enum { FS_U8 = 0, FS_I8 = 1, FS_F32 = 2, FS_F64 = 3 } fs_dtype;
+/* arithmetic of the continuous per-feature term:
+ *   FS_ARITH_F32: fl32(fl32(|a-b|) * r)  -- MultiSURF.py:184-188, ReliefF.py:151-154
+ *   FS_ARITH_F64: |a-b| * (double)r       -- SURF.py:153-156 (X stays float64) */
+typedef enum { FS_ARITH_F32 = 0, FS_ARITH_F64 = 1 } fs_arith;
+
+typedef enum {
+    FS_OK = 0,
+    FS_ERR_INVALID = -1,    /* bad argument */
+    FS_ERR_NO_DEVICE = -2,  /* no usable sm_100 GPU / driver */
+    FS_ERR_CUDA = -3,       /* CUDA runtime error (message has the detail) */
+    FS_ERR_OOM = -4,        /* device or host allocation failed */
+    FS_ERR_STATE = -5       /* call order violated (e.g. score before set_features) */
+} fs_status;
+
+/* neighbour codes in fs_debug_rows' mask_out (same values as the oracle's) */
+enum { FS_MASK_NONE = 0, FS_MASK_NEAR_HIT = 1, FS_MASK_NEAR_MISS = 2, FS_MASK_FAR_MISS = 3, FS_MASK_FAR_HIT = 4 };
+
+/* Per-call timings (CUDA events on the call's stream) and work counters. */
+typedef struct fs_stats {
+    float ms_total;          /* whole fs_score call on the device */
+    float ms_gather;         /* column compaction / one-hot encode of the active columns */
+    float ms_dist_tensor;    /* one-hot int8 tcgen05 distance kernel(s) */
+    float ms_dist_general;   /* CUDA-core distance kernel(s) (continuous / wide discrete) */
+    float ms_select;         /* row statistics, thresholds / top-k, neighbour masks */
+    float ms_accum_tensor;   /* mask x one-hot tcgen05 accumulation kernel(s) */
+    float ms_accum_general;  /* CUDA-core accumulation / ReliefF gather kernel(s) */
+    float ms_reduce;         /* final per-feature reduction */
+    int32_t launches;        /* kernels launched by this call */
+    int32_t n_chunks;        /* target-row chunks processed */
+    int64_t n_tensor_cols;   /* active columns on the one-hot tensor-core path */
+    int64_t n_general_cols;  /* active columns on the CUDA-core path */
+    int64_t onehot_k;        /* contraction length of the one-hot operands (sum of V_f, padded) */
+    int64_t pairs_selected;  /* neighbour pairs with a non-zero coefficient */
+} fs_stats;
+
+/* Number of usable sm_100 devices (0 when there is no driver/GPU).  Replaces
+ * numba.cuda.is_available() in MultiSURF.py:393-406, SURF.py:338-343, ReliefF.py:382-385. */
+FS_API int fs_device_count(void);
+FS_API const char *fs_last_error(void);
+FS_API int fs_abi_version(void);
+
+/*
+ * Upload X (host pointer, row-major, row stride in elements) to `device` and scan
+ * every column once on the GPU: min, max and the set of distinct values (up to
+ * FS_DISTINCT_CAP).  Replaces cuda.to_device(x) and the per-column np.unique /
+ * range pass of fit (MultiSURF.py:409-425, SURF.py:347-365, ReliefF.py:366-391).
+ * y_enc: class index 0..n_classes-1 per sample (labels are only compared for
+ * equality: MultiSURF.py:216, SURF.py:175, ReliefF.py:166).
+ * stream: a cudaStream_t (NULL = the legacy default stream); all later work on
+ * this data set is issued on it.
+ */
+FS_API int fs_dataset_create(fs_dataset **out, const void *x, int dtype, int64_t n, int64_t p,
+                      int64_t row_stride_elems, const int32_t *y_enc, int32_t n_classes,
+                      int32_t device, void *stream);
+
+/* Same, for a matrix that is already on `device` (row-major device pointer). */
+FS_API int fs_dataset_create_device(fs_dataset **out, const void *x_dev, int dtype, int64_t n, int64_t p,
+                             int64_t row_stride_elems, const int32_t *y_enc, int32_t n_classes,
+                             int32_t device, void *stream);
+
+/* Column scan results, each [p]: exact min / max as doubles, and the distinct-value
+ * count (FS_DISTINCT_CAP + 1 means "more than FS_DISTINCT_CAP").  Any may be NULL. */
+FS_API int fs_dataset_column_stats(const fs_dataset *ds, double *col_min, double *col_max,
+                            int32_t *n_distinct);
+
+/* Per-column typing chosen by the caller exactly as the reference's fit does:
+ * is_discrete[p] (np.unique(col).size <= discrete_limit) and recip[p] = 1/range as
+ * float32 (MultiSURF.py:409-420; SURF.py:347-355; ReliefF.py:366-380). */
+FS_API int fs_dataset_set_features(fs_dataset *ds, const uint8_t *is_discrete, const float *recip, int arith);
+
+FS_API int fs_dataset_destroy(fs_dataset *ds);
+
+/*
+ * Score the columns feat_idx[0..n_kept) (NULL = all p) for the target rows
+ * [row_begin, row_end) of the data set's internal sample order (a fixed
+ * permutation of the samples; any partition of [0, n) covers every sample once,
+ * which is how target rows are sharded across GPUs).  Writes
+ *     wsum_out[c] = sum over those targets i of W_i[feat_idx[c]]     (float64)
+ * i.e. the reference host callers' result before the final "/ n_samples"
+ * (_multisurf_gpu_host_caller MultiSURF.py:147-162, _surf_gpu_host_caller
+ * SURF.py:117-128, _relieff_gpu_host_caller ReliefF.py:127-134).  A multi-GPU
+ * caller sums the partial vectors (one allreduce) and divides by n.
+ * k and class_probs[n_classes] are used by FS_RELIEFF only.
+ * out_on_device != 0: wsum_out is a device pointer on the data set's device.
+ */
+FS_API int fs_score(fs_dataset *ds, int algo, int use_star, int32_t k, const float *class_probs,
+             const int64_t *feat_idx, int64_t n_kept, int64_t row_begin, int64_t row_end,
+             double *wsum_out, int out_on_device, fs_stats *stats);
+
+/*
+ * Parity/debug view of the same kernels for nt target samples given by ORIGINAL
+ * sample index: the distance row (float64, original sample order, 0 at the target
+ * itself), the neighbour threshold (MultiSURF: T_i; SURF: mean distance; ReliefF: 0)
+ * and the neighbour code of every sample (FS_MASK_*).  Outputs are host pointers,
+ * [nt*n], [nt], [nt*n]; any may be NULL.  wsum_out[n_kept] (host, may be NULL)
+ * receives the sum of the targets' contributions, as fs_score does for a row range.
+ */
+FS_API int fs_debug_rows(fs_dataset *ds, int algo, int use_star, int32_t k, const float *class_probs,
+                  const int64_t *feat_idx, int64_t n_kept, const int64_t *targets, int64_t nt,
+                  double *dist_out, double *thresh_out, int8_t *mask_out, double *wsum_out);
+
+/* Internal order: perm_out[r] = original index of internal row r ([n]). */
+FS_API int fs_dataset_row_order(const fs_dataset *ds, int64_t *perm_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTSELECT_B200_H */

@@ -33,8 +33,8 @@ def fixture_a():
 
 
 def fixture_b():
-    x = np.array([[0.1, 0.5, 1, 5], [0.2, 0.4, 1, 5], [0.3, 0.6, 1, 5],
-                  [0.8, 0.5, 2, 5], [0.9, 0.4, 2, 5], [1.0, 0.6, 2, 5]], dtype=np.float64)
+    x = np.array([[0.1, 5.0, 10, 3.0], [0.2, 4.0, 10, 3.0], [0.3, 6.0, 10, 3.0],
+                  [10.8, 5.0, 20, 3.0], [10.9, 4.0, 20, 3.0], [11.0, 6.0, 20, 3.0]], dtype=np.float32)
     y = np.array([0, 0, 0, 1, 1, 1], dtype=np.int32)
     return x, y
 

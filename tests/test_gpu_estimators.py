@@ -1,0 +1,165 @@
+"""GPU: the estimator API end to end against the reference's own outputs (golden vectors)
+and the behavioural contract of the reference's tests (tests/test_multisurf.py,
+test_surf.py, test_relieff.py, test_turf.py)."""
+import pickle
+
+import numpy as np
+import pytest
+
+import fastselect_b200 as fsb
+from oracle import ref_oracle as R
+
+pytestmark = pytest.mark.gpu
+
+CLS = {"MultiSURF": fsb.MultiSURF, "SURF": fsb.SURF, "ReliefF": fsb.ReliefF}
+
+
+def _tied_relieff(m):
+    """ReliefF on data with distance ties depends on numba's quicksort order (oracle
+    tie_mode 0); the GPU path breaks ties by sample index.  Those cases are compared
+    with the oracle under the same tie rule instead of with the reference vector."""
+    return m["algo"] == "ReliefF" and (m["data"].startswith("geno") or m["data"] in ("A", "B")
+                                       or m["data"].startswith("mixed"))
+
+
+def test_estimators_match_reference_vectors(native, golden):
+    arrays, meta = golden
+    checked = 0
+    for m in meta:
+        if m["idx"] < 0 or m["algo"].startswith("TuRF"):
+            continue
+        x, y = arrays[f"X_{m['data']}"], arrays[f"y_{m['data']}"]
+        ref = arrays[f"scores_{m['idx']}"]
+        est = CLS[m["algo"]](n_features_to_select=min(3, x.shape[1]), backend="gpu", **m["params"]).fit(x, y)
+        assert est.effective_backend_ == "gpu"
+        assert np.array_equal(est.is_discrete_, arrays[f"isd_{m['idx']}"]), m
+        assert est.feature_importances_.dtype == np.float32
+        if _tied_relieff(m):
+            P = m["params"]
+            ref = R.fit_relieff(x, y, P.get("discrete_limit", 10), P["n_neighbors"], tie_mode=1)[0]
+        scale = max(1.0, float(np.abs(ref).max()))
+        np.testing.assert_allclose(est.feature_importances_, ref, rtol=1e-5, atol=2e-6 * scale, err_msg=str(m))
+        top = np.argsort(ref)[::-1][:len(est.top_features_)]
+        if not np.array_equal(est.top_features_, top):
+            gaps = np.abs(np.diff(np.sort(ref)[::-1][: len(top) + 1]))
+            assert gaps.min() < 2e-6 * scale, m
+        checked += 1
+    assert checked >= 70
+
+
+def test_readme_quickstart_top15(native, golden):
+    from sklearn.datasets import make_classification
+
+    arrays, _ = golden
+    x, y = make_classification(n_samples=500, n_features=1000, n_informative=20, n_redundant=100, random_state=42)
+    if not np.allclose([x.sum(), np.abs(x).sum(), float(y.sum())], arrays["readme_xsum"]):
+        pytest.skip("make_classification stream differs")
+    est = fsb.MultiSURF(n_features_to_select=15, backend="gpu").fit(x, y)
+    np.testing.assert_allclose(est.feature_importances_, arrays["readme_scores"], rtol=1e-5,
+                               atol=2e-6 * np.abs(arrays["readme_scores"]).max())
+    assert np.array_equal(est.top_features_, arrays["readme_top"])
+    assert est.transform(x).shape == (500, 15)
+
+
+def test_turf_matches_reference(native, golden):
+    arrays, meta = golden
+    for m in meta:
+        if not m["algo"].startswith("TuRF"):
+            continue
+        base = m["algo"].split(":")[1]
+        if base == "ReliefF" and not m["data"].startswith("gauss"):
+            continue
+        x, y = arrays[f"X_{m['data']}"], arrays[f"y_{m['data']}"]
+        t = fsb.TuRF(CLS[base](n_features_to_select=5, backend="gpu", **m["params"]),
+                     n_features_to_select=m["turf"]["n"], pct_remove=m["turf"]["pct"]).fit(x, y)
+        ref = arrays[f"scores_{m['idx']}"]
+        np.testing.assert_allclose(t.feature_importances_, ref, rtol=1e-5, atol=2e-6 * np.abs(ref).max())
+        assert np.array_equal(t.top_features_, arrays[f"top_{m['idx']}"]), m
+
+
+def test_turf_resident_path_equals_refit_path(native):
+    """TuRF's device-resident column-subset scoring gives the scores a from-scratch fit of
+    X[:, active] gives (TuRF.py:110-111)."""
+    from datasets import mixed
+
+    x, y = mixed(51, 120, 40, 2)
+    t = fsb.TuRF(fsb.MultiSURF(backend="gpu"), n_features_to_select=6, pct_remove=0.25).fit(x, y)
+
+    class Refit(fsb.MultiSURF):      # same estimator, but not recognised as resident-capable
+        pass
+
+    active = np.arange(40)
+    scores = fsb.MultiSURF(backend="gpu", n_features_to_select=1).fit(x, y).feature_importances_
+    while len(active) > 6:
+        k = max(1, int(len(active) * 0.25))
+        if len(active) - k < 6:
+            k = len(active) - 6
+        active = np.delete(active, np.argsort(scores)[:k])
+        scores = fsb.MultiSURF(backend="gpu", n_features_to_select=1).fit(x[:, active], y).feature_importances_
+    assert np.array_equal(t.top_features_, np.sort(active))
+
+
+def test_int8_genotypes_equal_float_input(native):
+    from datasets import epistatic_genotypes
+
+    x, y = epistatic_genotypes(7, 300, 500)
+    a = fsb.MultiSURF(n_features_to_select=5, backend="gpu").fit(x, y)
+    b = fsb.MultiSURF(n_features_to_select=5, backend="gpu").fit(x.astype(np.float64), y)
+    assert np.array_equal(a.feature_importances_, b.feature_importances_)
+    assert a.is_discrete_.all()
+    c = fsb.SURF(n_features_to_select=5, backend="gpu", use_star=True).fit(x, y)
+    d = fsb.SURF(n_features_to_select=5, backend="gpu", use_star=True).fit(x.astype(np.float64), y)
+    assert np.array_equal(c.feature_importances_, d.feature_importances_)
+
+
+def test_behavioural_contract(native, capsys):
+    x = np.array([[1.1, 5.0, 10, 3.0], [1.2, 4.0, 10, 3.0], [2.3, 6.0, 10, 3.0], [2.5, 5.5, 10, 3.0],
+                  [1.5, 4.5, 20, 3.0], [8.8, 5.0, 20, 3.0], [8.9, 4.0, 20, 3.0], [9.5, 6.0, 20, 3.0],
+                  [10.5, 4.5, 20, 3.0], [10.5, 4.5, 10, 3.0]], dtype=np.float32)
+    y = np.array([0] * 5 + [1] * 5, dtype=np.int32)
+    m = fsb.MultiSURF(n_features_to_select=1, backend="gpu", discrete_limit=4).fit(x, y)
+    assert set(m.top_features_) == {0} and abs(m.feature_importances_[3]) < 1e-7   # test_multisurf.py:36-45
+    assert fsb.MultiSURF(n_features_to_select=3, backend="gpu").fit_transform(x, y).shape == (10, 3)
+    fsb.MultiSURF(n_features_to_select=2, backend="gpu", use_star=True, verbose=True).fit(x, y)
+    assert "Running MultiSURF*" in capsys.readouterr().out
+    fsb.SURF(n_features_to_select=2, backend="gpu", verbose=True).fit(x, y)
+    out = capsys.readouterr().out
+    assert "Running SURF on the GPU now..." in out and "Feature scoring completed." in out
+    # single-class y: all scores <= 0 (test_multisurf.py:193-205); ReliefF returns zeros
+    s = fsb.MultiSURF(n_features_to_select=2, backend="gpu").fit(x, np.zeros(10)).feature_importances_
+    assert (s <= 0).all()
+    r = fsb.ReliefF(n_features_to_select=2, backend="gpu").fit(x, np.zeros(10))
+    assert not r.feature_importances_.any() and r.top_features_.tolist() == [0, 1]
+    with pytest.warns(UserWarning, match="smallest class size"):
+        fsb.ReliefF(n_features_to_select=2, n_neighbors=5, backend="gpu").fit(x, y)
+    # discrete_limit (test_multisurf.py:96-110)
+    xd = np.array([[i, i % 3] for i in range(11)] * 2, dtype=np.float32)
+    yd = np.array([0] * 11 + [1] * 11, dtype=np.int32)
+    assert fsb.MultiSURF(discrete_limit=10, backend="gpu", n_features_to_select=2).fit(xd, yd).is_discrete_.tolist() == [False, True]
+    assert fsb.MultiSURF(discrete_limit=12, backend="gpu", n_features_to_select=2).fit(xd, yd).is_discrete_.tolist() == [True, True]
+    # wide discrete columns (more distinct values than the device scan tracks)
+    xw = np.array([[i % 20, i % 3, (i * 7) % 19] for i in range(60)], dtype=np.float64)
+    yw = (np.arange(60) % 2).astype(np.int64)
+    est = fsb.SURF(discrete_limit=25, backend="gpu", n_features_to_select=2).fit(xw, yw)
+    assert est.is_discrete_.all()
+    want = R.fit_surf(xw, yw, 25, False, 1)[0]
+    np.testing.assert_allclose(est.feature_importances_, want, rtol=1e-5, atol=1e-7)
+    # fitted estimators pickle and refit identically
+    m2 = pickle.loads(pickle.dumps(m))
+    assert np.array_equal(m2.feature_importances_, m.feature_importances_)
+    assert np.array_equal(m2.fit(x, y).feature_importances_, m.feature_importances_)
+
+
+@pytest.mark.parametrize("cls", [fsb.MultiSURF, fsb.SURF, fsb.ReliefF])
+def test_sklearn_estimator_checks(native, cls):
+    """The reference runs sklearn's check_estimator with the default backend='auto'
+    (tests/test_multisurf.py:78-83), i.e. through the GPU path on a GPU box."""
+    from sklearn.utils.estimator_checks import check_estimator
+
+    check_estimator(cls())
+
+
+def test_sklearn_estimator_checks_turf(native):
+    from sklearn.utils.estimator_checks import check_estimator
+
+    check_estimator(fsb.TuRF(fsb.MultiSURF()))

@@ -1,0 +1,215 @@
+"""CPU: host-side logic of the package -- parameter validation and error behaviour of the
+estimator mirror, TuRF's pruning schedule (ports of the behaviours in the reference's
+tests/test_turf.py, tests/test_multisurf.py:121-178), the C ABI surface, and the
+multi-process row sharding (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+from sklearn.base import BaseEstimator
+from sklearn.exceptions import NotFittedError
+
+import fastselect_b200 as fsb
+from fastselect_b200 import _native
+from fastselect_b200._shard import shard_rows
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAVE_GPU = _native.device_count() > 0
+
+X = np.random.RandomState(0).rand(12, 5)
+Y = np.arange(12) % 2
+
+
+@pytest.mark.parametrize("cls", [fsb.MultiSURF, fsb.SURF, fsb.ReliefF])
+def test_parameter_validation_messages(cls):
+    for bad in (-1, 0, 100):
+        with pytest.raises(ValueError, match="must be > 0 and <= n_features"):
+            cls(n_features_to_select=bad, backend="gpu").fit(X, Y)
+    with pytest.raises(ValueError, match="must be in"):
+        cls(n_features_to_select=1.1, backend="gpu").fit(X, Y)
+    with pytest.raises(TypeError, match="must be an int or a float"):
+        cls(n_features_to_select="hi", backend="gpu").fit(X, Y)
+    with pytest.raises(ValueError, match="backend must be one of"):
+        cls(backend="tpu").fit(X, Y)
+    with pytest.raises(ValueError, match="contains NaN"):
+        xn = X.copy()
+        xn[0, 0] = np.nan
+        cls(backend="gpu").fit(xn, Y)
+    with pytest.raises(NotFittedError):
+        cls().transform(X)
+    with pytest.raises(NotImplementedError, match="only the GPU backend"):
+        cls(n_features_to_select=2, backend="cpu").fit(X, Y)
+
+
+def test_relieff_n_neighbors_validation():
+    for k in (0, 12, 50):
+        with pytest.raises(ValueError, match="n_neighbors"):
+            fsb.ReliefF(n_neighbors=k, backend="gpu").fit(X, Y)
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="needs a box WITHOUT a GPU")
+def test_gpu_backend_fails_loudly_without_a_gpu():
+    """No silent CPU fallback: MultiSURF.py:399-403 / SURF.py:341-342 messages."""
+    with pytest.raises(RuntimeError, match="no compatible NVIDIA GPU"):
+        fsb.MultiSURF(backend="gpu").fit(X, Y)
+    with pytest.raises(RuntimeError, match="no CUDA-enabled GPU is available"):
+        fsb.SURF(backend="gpu").fit(X, Y)
+    with pytest.raises(RuntimeError):
+        fsb.ReliefF(backend="auto").fit(X, Y)
+    with pytest.raises(RuntimeError):
+        fsb.MultiSURF(backend="auto").fit(X, Y)          # 'auto' does not fall back either
+    with pytest.raises(RuntimeError, match="no usable NVIDIA sm_100"):
+        _native.Dataset(X, Y.astype(np.int32), 2)
+
+
+def test_relieff_single_class_early_return_needs_no_gpu():
+    r = fsb.ReliefF(n_features_to_select=2).fit(X, np.zeros(12))
+    assert not r.feature_importances_.any() and r.top_features_.tolist() == [0, 1]
+
+
+def test_c_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "fastselect_b200.h")).read()
+    declared = set(re.findall(r"FS_API\s+[\w\s\*]+?\b(fs_\w+)\s*\(", header))
+    assert {"fs_score", "fs_dataset_create", "fs_debug_rows", "fs_device_count"} <= declared
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.fs_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", _native.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert declared <= exported
+    assert not [s for s in exported if "fso_" in s], "the oracle must not be linked into the product"
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fastselect_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                hits = re.findall(r"(?:from|import)\s+oracle|libfs_oracle|fso_\w+\s*\(|#include[^\n]*oracle|ref_oracle", src)
+                assert not hits, (os.path.join(dirpath, f), hits)
+
+
+# ---------------------------------------------------------------------------
+# TuRF (behaviours of the reference's tests/test_turf.py with the same mock)
+# ---------------------------------------------------------------------------
+class MockReliefEstimator(BaseEstimator):
+    def __init__(self):
+        pass
+
+    def fit(self, X, y):
+        self.n_features_in_ = X.shape[1]
+        self.feature_importances_ = np.linspace(1.0, 0.0, self.n_features_in_)
+        return self
+
+
+def _data(n=50, p=100):
+    rs = np.random.RandomState(0)
+    return rs.rand(n, p), rs.randint(0, 2, n)
+
+
+def test_turf_selects_the_requested_number_sorted():
+    x, y = _data()
+    t = fsb.TuRF(MockReliefEstimator(), n_features_to_select=10, pct_remove=0.1).fit(x, y)
+    assert len(t.top_features_) == 10
+    assert np.array_equal(t.top_features_, np.arange(10))          # sorted surviving indices
+    assert t.feature_importances_.shape == (100,)
+    assert t.transform(x).shape == (50, 10)
+    assert t.fit_transform(x, y).shape == (50, 10)
+
+
+def test_turf_never_overshoots_and_honours_n_iterations():
+    x, y = _data(p=23)
+    t = fsb.TuRF(MockReliefEstimator(), n_features_to_select=7, pct_remove=0.5).fit(x, y)
+    assert len(t.top_features_) == 7
+    t = fsb.TuRF(MockReliefEstimator(), n_features_to_select=2, pct_remove=0.1, n_iterations=3).fit(x, y)
+    assert len(t.top_features_) == 23 - 2 - 2 - 1                   # max(1, int(len * 0.1)) per iteration
+    t = fsb.TuRF(MockReliefEstimator(), n_features_to_select=30).fit(x, y)
+    assert len(t.top_features_) == 23                               # nothing to remove
+
+
+def test_turf_schedule_of_config_c5():
+    """p = 500 000, pct 0.1 -> 10 features: 109 fits, sum of p_t = 5 000 376."""
+    t = fsb.TuRF(MockReliefEstimator(), n_features_to_select=10, pct_remove=0.1)
+    n_active, fits, total = 500_000, 1, 500_000
+    while n_active > 10:
+        n_active -= t._n_to_remove(n_active)
+        fits += 1
+        total += n_active
+    assert (fits, total) == (109, 5_000_376)
+
+
+def test_turf_errors_and_verbose(capsys):
+    x, y = _data(p=12)
+    for pct in (0.0, 1.0, -0.5, 1.5):
+        with pytest.raises(ValueError, match="pct_remove must be between 0 and 1"):
+            fsb.TuRF(MockReliefEstimator(), pct_remove=pct).fit(x, y)
+    with pytest.raises(NotFittedError):
+        fsb.TuRF(MockReliefEstimator()).transform(x)
+    fsb.TuRF(MockReliefEstimator(), n_features_to_select=10, pct_remove=0.1, verbose=True).fit(x, y)
+    assert "Iteration 0: 11 features remaining." in capsys.readouterr().out
+
+
+# ---------------------------------------------------------------------------
+# row sharding
+# ---------------------------------------------------------------------------
+def test_shard_rows_partitions_every_row_once():
+    for n in (2, 7, 100, 4000, 20001):
+        for w in (1, 2, 3, 8):
+            parts = [shard_rows(n, w, r) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_rows(10, 2, 2)
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, {root!r})
+from fastselect_b200._shard import score_sharded, shard_rows, dist_info
+from oracle import ref_oracle as R
+from datasets import mixed
+
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+x, y = mixed(3, 61, 18, 3)
+x32, recip, isd = R.multisurf_prep(x, 10)
+yc = np.unique(y, return_inverse=True)[1].astype(np.int64)
+calls = []
+def score_rows(lo, hi, out_ptr):          # the oracle stands in for the GPU kernel in this CPU test
+    assert out_ptr is None
+    calls.append((lo, hi))
+    return R.multisurf_targets(x32, yc, recip, isd, True, np.arange(lo, hi), False, False)["wsum"]
+total = score_sharded(61, 18, score_rows, device_buffers=False)
+full = R.multisurf_targets(x32, yc, recip, isd, True, np.arange(61), False, False)["wsum"]
+assert calls == [shard_rows(61, 2, dist.get_rank())], calls
+np.testing.assert_allclose(total, full, rtol=1e-12, atol=1e-12)
+print("rank", dist.get_rank(), "ok", calls)
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_sharding_matches_single_process(tmp_path):
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "tests")]))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], env=env, stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    assert "rank 0 ok [(0, 31)]" in outs[0] and "rank 1 ok [(31, 61)]" in outs[1]
