@@ -83,7 +83,7 @@ enum : uint8_t { kChunkContinuous = 0, kChunkCompare = 1 };
 struct RowInfo {
     double thresh;
     double coef[5];
-    int32_t n_hit, n_miss, n_far, pad;
+    int32_t n_hit, n_miss, n_far_hit, n_far_miss;   // near hits, near misses, far hits, far misses
 };
 
 // Working set of one fs_score call: the active columns split by path.
@@ -105,10 +105,11 @@ struct WorkSet {
     std::vector<int64_t> h_tcol, h_tout, h_toff;
     DevBuf<int64_t> tcol, tout;     // [pt]
     DevBuf<int32_t> toff;           // [pt+1] first one-hot row of each column
-    DevBuf<int32_t> krow_col;       // [K] tensor column of each one-hot row (-1 = padding)
-    DevBuf<int8_t> A;               // [n_pad, K]   sample-major one-hot (K-major)
-    DevBuf<int8_t> At;              // [K, n_pad]   feature-major one-hot (sample-major)
-    int64_t n_pad = 0;
+    DevBuf<int8_t> A;               // [n, K]    sample-major one-hot (K = one-hot row, contiguous)
+    DevBuf<int8_t> At;              // [K, ldt]  feature-major one-hot (sample index contiguous)
+    DevBuf<uint8_t> codes;          // [n, ldc]  value codes of the tensor columns (ReliefF gather)
+    int64_t ldt = 0, ldc = 0;
+    int64_t K_used = 0;             // sum of V_f (one-hot rows in use); K is K_used padded to 128
     // cache key
     std::vector<int64_t> key;
     bool valid = false;
@@ -159,6 +160,7 @@ struct fs_dataset {
     fs::DevBuf<char> xa_gather;   // gathered target rows (fs_debug_rows)
     fs::DevBuf<double> tpartial;  // tensor-path accumulation partials
     fs::DevBuf<int8_t> maskH, maskM;
+    fs::DevBuf<int8_t> a_gather;  // gathered one-hot target rows (fs_debug_rows)
     fs::DevBuf<unsigned long long> counters;
 };
 
@@ -174,7 +176,8 @@ void launch_dist_general(const WorkSet &ws, const void *xa, int64_t na, const vo
 
 // select.cu
 void launch_select(fs_dataset *ds, int algo, int use_star, int32_t k, const int64_t *row_ids, int64_t R,
-                   const double *Dc, const int32_t *Dd, int64_t ldn, int8_t *sel, RowInfo *rinfo,
+                   const double *Dc, const int32_t *Dd, int64_t ldn, int8_t *sel, int8_t *mask_h, int8_t *mask_m,
+                   RowInfo *rinfo,
                    int32_t *nbr_idx, double *nbr_w, int32_t *nbr_cnt, int32_t nbr_cap,
                    const float *class_probs, cudaStream_t st, int *launches);
 

@@ -84,7 +84,7 @@ struct DebugOut {
 __global__ void count_selected_kernel(const RowInfo *rinfo, int64_t R, unsigned long long *out) {
     unsigned long long s = 0;
     for (int64_t r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (int64_t)gridDim.x * blockDim.x)
-        s += (unsigned long long)(rinfo[r].n_hit + rinfo[r].n_miss + rinfo[r].n_far);
+        s += (unsigned long long)(rinfo[r].n_hit + rinfo[r].n_miss + rinfo[r].n_far_hit + rinfo[r].n_far_miss);
     atomicAdd(out, s);
 }
 
@@ -126,6 +126,11 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
     if (ws.pg > 0) ds->Dc.reserve((size_t)Rmax * ldn);
     if (ws.pt > 0) ds->Dd.reserve((size_t)Rmax * ldn);
     ds->sel.reserve((size_t)Rmax * ldn);
+    const bool use_masks = ws.pt > 0 && algo != FS_RELIEFF;
+    if (use_masks) {
+        ds->maskH.reserve((size_t)Rmax * ldn);
+        ds->maskM.reserve((size_t)Rmax * ldn);
+    }
     ds->rinfo.reserve(Rmax);
     ds->row_ids.reserve(Rmax);
     int32_t nbr_cap = 0;
@@ -177,7 +182,8 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
         // ---- neighbour selection
         timer.begin(PH_SELECT);
         launch_select(ds, algo, use_star, k, ds->row_ids.ptr, R, ws.pg > 0 ? ds->Dc.ptr : nullptr,
-                      ws.pt > 0 ? ds->Dd.ptr : nullptr, ldn, ds->sel.ptr, ds->rinfo.ptr, ds->nbr_idx.ptr,
+                      ws.pt > 0 ? ds->Dd.ptr : nullptr, ldn, ds->sel.ptr, use_masks ? ds->maskH.ptr : nullptr,
+                      use_masks ? ds->maskM.ptr : nullptr, ds->rinfo.ptr, ds->nbr_idx.ptr,
                       ds->nbr_w.ptr, ds->nbr_cnt.ptr, nbr_cap, ds->d_class_probs.ptr, st, &launches);
         if (stats) {
             count_selected_kernel<<<32, 256, 0, st>>>(ds->rinfo.ptr, R, ds->counters.ptr);

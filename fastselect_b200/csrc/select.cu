@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(const double *__r
                                                                int64_t n, const int64_t *__restrict__ row_ids,
                                                                const int32_t *__restrict__ y, int use_star,
                                                                int8_t *__restrict__ sel,
+                                                               int8_t *__restrict__ mask_h,
+                                                               int8_t *__restrict__ mask_m,
                                                                RowInfo *__restrict__ rinfo) {
     __shared__ double sd[8];
     __shared__ int si[8];
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(const double *__r
     __syncthreads();
     const double thresh = s_thresh;
     const int32_t yi = y[self];
-    int nh = 0, nm = 0, nf = 0;
+    int nh = 0, nm = 0, nfh = 0, nfm = 0;
     for (int64_t j = tid; j < n; j += 256) {
         int code = FS_MASK_NONE;
         if (j != self) {
@@ -97,20 +99,27 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(const double *__r
             }
         }
         sel[base + j] = (int8_t)code;
+        if (mask_h) {
+            // signed masks of the tensor-core accumulation: c_ij = -aH*mH + aM*mM
+            mask_h[base + j] = (int8_t)((code == FS_MASK_NEAR_HIT) - (code == FS_MASK_FAR_HIT));
+            mask_m[base + j] = (int8_t)((code == FS_MASK_NEAR_MISS) - (code == FS_MASK_FAR_MISS));
+        }
         nh += (code == FS_MASK_NEAR_HIT);
         nm += (code == FS_MASK_NEAR_MISS);
-        nf += (code == FS_MASK_FAR_MISS) + (code == FS_MASK_FAR_HIT);
+        nfm += (code == FS_MASK_FAR_MISS);
+        nfh += (code == FS_MASK_FAR_HIT);
     }
     nh = block_sum(nh, si);
     nm = block_sum(nm, si);
-    nf = block_sum(nf, si);
+    nfh = block_sum(nfh, si);
+    nfm = block_sum(nfm, si);
     if (tid == 0) {
         RowInfo ri;
         ri.thresh = thresh;
         ri.n_hit = nh;
         ri.n_miss = nm;
-        ri.n_far = nf;
-        ri.pad = 0;
+        ri.n_far_hit = nfh;
+        ri.n_far_miss = nfm;
         ri.coef[0] = 0.0;
         if (ALGO == FS_MULTISURF) {
             // MultiSURF.py:245-251: divide by the counts unless they are zero;
@@ -254,24 +263,24 @@ __global__ void __launch_bounds__(256) relieff_select_kernel(
         for (int q = 0; q < 5; ++q) ri.coef[q] = 0.0;
         ri.n_hit = n_hit;
         ri.n_miss = n_miss;
-        ri.n_far = 0;
-        ri.pad = 0;
+        ri.n_far_hit = 0;
+        ri.n_far_miss = 0;
         rinfo[r] = ri;
     }
 }
 
 void launch_select(fs_dataset *ds, int algo, int use_star, int32_t k, const int64_t *row_ids, int64_t R,
-                   const double *Dc, const int32_t *Dd, int64_t ldn, int8_t *sel, RowInfo *rinfo,
-                   int32_t *nbr_idx, double *nbr_w, int32_t *nbr_cnt, int32_t nbr_cap, const float *class_probs,
+                   const double *Dc, const int32_t *Dd, int64_t ldn, int8_t *sel, int8_t *mask_h, int8_t *mask_m,
+                   RowInfo *rinfo, int32_t *nbr_idx, double *nbr_w, int32_t *nbr_cnt, int32_t nbr_cap, const float *class_probs,
                    cudaStream_t st, int *launches) {
     if (R == 0) return;
     dim3 grid((unsigned)R);
     if (algo == FS_MULTISURF)
         select_threshold_kernel<FS_MULTISURF><<<grid, 256, 0, st>>>(Dc, Dd, ldn, ds->n, row_ids, ds->d_y.ptr,
-                                                                    use_star, sel, rinfo);
+                                                                    use_star, sel, mask_h, mask_m, rinfo);
     else if (algo == FS_SURF)
         select_threshold_kernel<FS_SURF><<<grid, 256, 0, st>>>(Dc, Dd, ldn, ds->n, row_ids, ds->d_y.ptr, use_star,
-                                                               sel, rinfo);
+                                                               sel, mask_h, mask_m, rinfo);
     else
         relieff_select_kernel<<<grid, 256, 0, st>>>(Dc, Dd, ldn, ds->n, row_ids, ds->d_y.ptr, ds->d_cls_start.ptr,
                                                     ds->n_classes, k, class_probs, sel, rinfo, nbr_idx, nbr_w,

@@ -1,0 +1,145 @@
+// tc_dist.cu -- genotype / discrete mismatch distance on the 5th-gen tensor cores.
+//
+// Replaces the discrete branch of the reference's distance loops
+// (MultiSURF.py:184-185, SURF.py:153-154, ReliefF.py:151-152):
+//     d_ij = sum_f [x_if != x_jf] = p_disc - sum_k A[i,k] * A[j,k],
+// where A is the one-hot image of the discrete columns (one int8 column per
+// (feature, value); K = sum_f V_f).  The contraction is an int8 GEMM A * A^T with
+// int32 accumulation, so the distances are exact integers.
+//
+// Kernel: one CTA per 128 x 256 tile of D.  Warp 0 streams 128-byte-wide K slabs of
+// both operands with TMA (128B swizzle) through a 4-stage mbarrier ring; one elected
+// thread of warp 1 issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=256, K=32) into
+// a 256-column TMEM accumulator; warps 2-5 read the accumulator back with
+// tcgen05.ld (32 lanes x 32 columns per instruction), form p_disc - acc and store
+// int32 rows (each thread writes whole 128-byte lines).  Tensor-pipe bound:
+// 6 int-ops per (sample pair, feature) for 3-valued genotypes.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace fs {
+
+namespace {
+constexpr int BM = 128;        // target rows per tile   (UMMA M)
+constexpr int BN = 256;        // sample columns per tile (UMMA N)
+constexpr int BK = 128;        // bytes of K per stage (one swizzle atom)
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK;   // 16 KB
+constexpr int B_BYTES = BN * BK;   // 32 KB
+constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int THREADS = 192;
+}  // namespace
+
+__global__ void __launch_bounds__(THREADS, 1)
+tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               int num_k_blocks, int32_t p_disc, int64_t R, int64_t n, int32_t *__restrict__ Dd, int64_t ldd) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *smem_a = smem;
+    unsigned char *smem_b = smem + STAGES * A_BYTES;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * (A_BYTES + B_BYTES));
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *accum_bar = empty_bar + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_a);
+        tc::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        tc::mbar_init(accum_bar, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc<BN>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                tc::mbar_wait(&empty_bar[s], ph ^ 1);
+                tc::mbar_arrive_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+                tc::tma_load_2d(smem_a + s * A_BYTES, &tmap_a, &full_bar[s], kb * BK, m0);
+                tc::tma_load_2d(smem_b + s * B_BYTES, &tmap_b, &full_bar[s], kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::make_idesc_i8(BM, BN);
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                tc::mbar_wait(&full_bar[s], ph);
+                tc::tc_fence_after();
+                const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem_a + s * A_BYTES));
+                const uint64_t db = tc::make_smem_desc_sw128(tc::smem_u32(smem_b + s * B_BYTES));
+#pragma unroll
+                for (int k = 0; k < BK / 32; ++k)   // +32 bytes of K = +2 in the (addr >> 4) field
+                    tc::mma_i8(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                tc::tc_commit(&empty_bar[s]);       // frees the smem stage when these MMAs retire
+            }
+            tc::tc_commit(accum_bar);               // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +32 =====
+        const int q = warp & 3;
+        tc::mbar_wait(accum_bar, 0);
+        tc::tc_fence_after();
+        const int64_t row = (int64_t)m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tc::tmem_ld_wait();
+            const int64_t col = (int64_t)n0 + c0;
+            if (row < R && col < n) {
+                int32_t *dst = Dd + row * ldd + col;       // ldd is a multiple of 128: 16-byte aligned
+                if (col + 32 <= ldd) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4) {
+                        int4 o;
+                        o.x = p_disc - (int32_t)v[e];
+                        o.y = p_disc - (int32_t)v[e + 1];
+                        o.z = p_disc - (int32_t)v[e + 2];
+                        o.w = p_disc - (int32_t)v[e + 3];
+                        *reinterpret_cast<int4 *>(dst + e) = o;
+                    }
+                } else {
+                    for (int e = 0; e < 32 && col + e < ldd; ++e) dst[e] = p_disc - (int32_t)v[e];
+                }
+            }
+        }
+        tc::tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc<BN>(tmem_base);
+    }
+}
+
+void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_t K, int32_t p_disc, int64_t R,
+                    int64_t n, int32_t *Dd, int64_t ldd, cudaStream_t st, int *launches) {
+    static bool configured = false;
+    if (!configured) {
+        FS_CUDA(cudaFuncSetAttribute(tc_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid((unsigned)ceil_div(n, BN), (unsigned)ceil_div(R, BM));
+    tc_dist_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmap_a, tmap_b, (int)(K / BK), p_disc, R, n, Dd, ldd);
+    FS_CUDA(cudaGetLastError());
+    ++*launches;
+}
+
+}  // namespace fs
