@@ -65,6 +65,14 @@ CUtensorMap make_tmap_u8_sw128(const void *base, uint64_t row_bytes, uint64_t ro
 // ---------------------------------------------------------------------------
 // encode
 // ---------------------------------------------------------------------------
+// Tile: 128 samples x 64 columns per CTA.  Step 1 reads x coalesced along the column
+// index and keeps the value codes in shared memory (both orientations); step 2 emits the
+// A rows (one-hot index contiguous) and step 3 the At rows (sample index contiguous) as
+// packed 32-bit stores -- every byte of the tile's A / At footprint is written exactly
+// once, so no memset of the operands is needed.
+constexpr int ENC_ROWS = 128;
+constexpr int ENC_COLS = 64;
+
 template <typename Tin>
 __global__ void __launch_bounds__(256) onehot_encode_kernel(const Tin *__restrict__ x, int64_t ldx,
                                                             const int64_t *__restrict__ perm,
@@ -74,27 +82,38 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(const Tin *__restric
                                                             int64_t pt, int64_t K, int64_t ldt, int64_t ldc,
                                                             int8_t *__restrict__ A, int8_t *__restrict__ At,
                                                             uint8_t *__restrict__ codes) {
-    __shared__ uint8_t tile[32][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
-    // phase 1: column index fastest (coalesced reads of x, near-contiguous writes of A)
+    __shared__ __align__(16) uint8_t code_rc[ENC_ROWS][ENC_COLS];       // [sample][column]
+    __shared__ __align__(16) uint8_t code_cr[ENC_COLS][ENC_ROWS];       // [column][sample]
+    __shared__ uint8_t kcol[ENC_COLS * FS_DISTINCT_CAP];                // one-hot index -> column in tile
+    __shared__ uint8_t kval[ENC_COLS * FS_DISTINCT_CAP];                // one-hot index -> value code
+    const int tid = threadIdx.x;
+    const int64_t c0 = (int64_t)blockIdx.x * ENC_COLS, r0 = (int64_t)blockIdx.y * ENC_ROWS;
+    const int ncols = (int)(pt - c0 < ENC_COLS ? pt - c0 : ENC_COLS);
+    const int nrows = (int)(n - r0 < ENC_ROWS ? n - r0 : ENC_ROWS);
+    const int k0 = toff[c0], k1 = toff[c0 + ncols];
+
+    // ---- step 1: value codes
     {
-        const int64_t c = c0 + tx;
+        const int c = tid & (ENC_COLS - 1);
         int64_t f = 0;
         int off = 0, V = 0;
         double v[FS_DISTINCT_CAP];
-        if (c < pt) {
-            f = tcol[c];
-            off = toff[c];
-            V = toff[c + 1] - off;
+        if (c < ncols) {
+            f = tcol[c0 + c];
+            off = toff[c0 + c];
+            V = toff[c0 + c + 1] - off;
 #pragma unroll
             for (int q = 0; q < FS_DISTINCT_CAP; ++q) v[q] = vals[f * FS_DISTINCT_CAP + q];
+            if (tid < ENC_COLS)
+                for (int q = 0; q < V; ++q) {
+                    kcol[off - k0 + q] = (uint8_t)c;
+                    kval[off - k0 + q] = (uint8_t)q;
+                }
         }
-        for (int rr = ty; rr < 32; rr += 8) {
-            const int64_t r = r0 + rr;
+        for (int rr = tid >> 6; rr < ENC_ROWS; rr += 4) {
             uint8_t code = 0;
-            if (c < pt && r < n) {
-                const double xv = (double)x[perm[r] * ldx + f];
+            if (c < ncols && rr < nrows) {
+                const double xv = (double)x[perm[r0 + rr] * ldx + f];
                 int found = 0;
 #pragma unroll
                 for (int q = FS_DISTINCT_CAP - 1; q >= 0; --q) {
@@ -102,20 +121,62 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(const Tin *__restric
                     if (q < V && eq) found = q;      // lowest matching index wins
                 }
                 code = (uint8_t)found;
-                codes[r * ldc + c] = code;
-                for (int q = 0; q < V; ++q) A[r * K + off + q] = (int8_t)(q == found);
+                codes[(r0 + rr) * ldc + c0 + c] = code;
             }
-            tile[rr][tx] = code;
+            code_rc[rr][c] = code;
+            code_cr[c][rr] = code;
         }
     }
     __syncthreads();
-    // phase 2: sample index fastest (coalesced writes of At)
-    for (int cc = ty; cc < 32; cc += 8) {
-        const int64_t c = c0 + cc, r = r0 + tx;
-        if (c < pt && r < n) {
-            const int off = toff[c], V = toff[c + 1] - off;
-            const int code = tile[tx][cc];
-            for (int q = 0; q < V; ++q) At[(int64_t)(off + q) * ldt + r] = (int8_t)(q == code);
+
+    // ---- step 2: A[r, k0..k1): 32-bit words where the whole word belongs to this tile,
+    // single bytes at the unaligned edges (a neighbouring tile owns the rest of that word)
+    {
+        const int w0 = k0 >> 2, w1 = (k1 + 3) >> 2;               // word range covering [k0, k1)
+        const int nw = w1 - w0;
+        for (int e = tid; e < nrows * nw; e += 256) {
+            const int rr = e / nw, w = w0 + e % nw;
+            uint32_t word = 0;
+            bool full = true;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int k = 4 * w + b;
+                if (k >= k0 && k < k1) {
+                    const uint32_t on = code_rc[rr][kcol[k - k0]] == kval[k - k0] ? 1u : 0u;
+                    word |= on << (8 * b);
+                } else {
+                    full = false;
+                }
+            }
+            int8_t *dst = A + (r0 + rr) * K + 4 * (int64_t)w;
+            if (full) {
+                *reinterpret_cast<uint32_t *>(dst) = word;
+            } else {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int k = 4 * w + b;
+                    if (k >= k0 && k < k1) dst[b] = (int8_t)((word >> (8 * b)) & 0xffu);
+                }
+            }
+        }
+    }
+    // ---- step 3: At[k, r0..r0+128): one warp instruction writes one 128-byte row segment
+    {
+        const int lane4 = (tid & 31) * 4;
+        for (int k = k0 + (tid >> 5); k < k1; k += 8) {
+            const uint32_t cw = *reinterpret_cast<const uint32_t *>(&code_cr[kcol[k - k0]][lane4]);
+            const uint32_t val = kval[k - k0];
+            uint32_t word = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) word |= (((cw >> (8 * b)) & 0xffu) == val ? 1u : 0u) << (8 * b);
+            int8_t *dst = At + (int64_t)k * ldt + r0 + lane4;       // r0, ldt multiples of 128: aligned
+            if (lane4 + 4 <= nrows) {
+                *reinterpret_cast<uint32_t *>(dst) = word;
+            } else {
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (lane4 + b < nrows) dst[b] = (int8_t)((word >> (8 * b)) & 0xffu);
+            }
         }
     }
 }
@@ -140,10 +201,14 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     FS_CUDA(cudaMemcpyAsync(ws.tcol.ptr, ws.h_tcol.data(), pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     FS_CUDA(cudaMemcpyAsync(ws.tout.ptr, ws.h_tout.data(), pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     FS_CUDA(cudaMemcpyAsync(ws.toff.ptr, toff32.data(), (pt + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    FS_CUDA(cudaMemsetAsync(ws.A.ptr, 0, (size_t)n * ws.K, st));
-    FS_CUDA(cudaMemsetAsync(ws.At.ptr, 0, (size_t)ws.K * ws.ldt, st));
-    FS_CUDA(cudaMemsetAsync(ws.codes.ptr, 0, (size_t)n * ws.ldc, st));
-    dim3 grid((unsigned)ceil_div(pt, 32), (unsigned)ceil_div(n, 32));
+    // the encode kernel writes every used byte of A, At and codes exactly once; only the K
+    // padding (one-hot indices K_used..K) has to be cleared.  Sample padding of At rows
+    // (columns n..ldt) and code padding are never read (the TMA maps are n bytes wide).
+    if (ws.K > ws.K_used) {
+        FS_CUDA(cudaMemset2DAsync(ws.A.ptr + ws.K_used, (size_t)ws.K, 0, (size_t)(ws.K - ws.K_used), (size_t)n, st));
+        FS_CUDA(cudaMemsetAsync(ws.At.ptr + (size_t)ws.K_used * ws.ldt, 0, (size_t)(ws.K - ws.K_used) * ws.ldt, st));
+    }
+    dim3 grid((unsigned)ceil_div(pt, ENC_COLS), (unsigned)ceil_div(n, ENC_ROWS));
     const int as_f32 = (ds->arith == FS_ARITH_F32 && ds->dtype == FS_F64) ? 1 : 0;
 #define FS_ENCODE(T)                                                                                              \
     onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,        \
@@ -271,8 +336,8 @@ void launch_accum_tensor(fs_dataset *ds, const WorkSet &ws, int algo, const int6
     ds->tpartial.reserve((size_t)groups * ws.K_used);
     // K of this GEMM is the sample index: rows of At and of the masks are n bytes long
     const CUtensorMap tat = make_tmap_u8_sw128(ws.At.ptr, (uint64_t)n, (uint64_t)ws.K, (uint64_t)ws.ldt, 128);
-    const CUtensorMap tmh = make_tmap_u8_sw128(ds->maskH.ptr, (uint64_t)n, (uint64_t)R, (uint64_t)ldn, 128);
-    const CUtensorMap tmm = make_tmap_u8_sw128(ds->maskM.ptr, (uint64_t)n, (uint64_t)R, (uint64_t)ldn, 128);
+    const CUtensorMap tmh = make_tmap_u8_sw128(ds->maskH.ptr, (uint64_t)n, (uint64_t)R, (uint64_t)ldn, 256);
+    const CUtensorMap tmm = make_tmap_u8_sw128(ds->maskM.ptr, (uint64_t)n, (uint64_t)R, (uint64_t)ldn, 256);
     launch_tc_accum(tat, tmh, tmm, n, R, d_row_ids, contiguous, ds->d_y.ptr, ds->d_cls_start.ptr, rinfo, ws.At.ptr,
                     ws.ldt, ws.K_used, ds->tpartial.ptr, st, launches);
     reduce_tensor_partials_kernel<<<(unsigned)ceil_div(ws.pt, 256), 256, 0, st>>>(ds->tpartial.ptr, groups, ws.K_used,

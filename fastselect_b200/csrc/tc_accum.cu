@@ -13,18 +13,19 @@
 // rsH_i / rsM_i being the row sums of the masks.  All counts are exact integers; the
 // per-target scaling and the reduction over targets are done in float64.
 //
-// Kernel: a CTA owns 128 one-hot rows (UMMA M = TMEM lanes) and a group of up to 8
-// tiles of 128 target rows (UMMA N).  Warp 0: TMA producer (At tile + the mask tiles a
-// K block needs); warp 1: one thread issues tcgen05.mma kind::i8 into the hit and miss
-// accumulators (2 x 128 TMEM columns, double-buffered across target tiles); warps 2-5:
-// epilogue -- tcgen05.ld both accumulators, pick the plane the target itself carries
-// (the one-hot byte At[(f,v), i]), scale, and add into one float64 register per one-hot
-// row; the reduction over a tile's targets is a loop over TMEM columns inside one
-// thread.  Samples are class-sorted, so for a class-homogeneous target tile the hit
-// mask is non-zero only in the K blocks of the tile's own class and the miss mask only
-// outside: the other K blocks are skipped, which keeps the MMA work at 3 MAC per
-// (pair, feature).  Partials are written per (tile group, one-hot row) and reduced in
-// a fixed order.
+// Kernel: a CTA owns 128 one-hot rows (UMMA M = TMEM lanes) and a group of up to 4
+// tiles of 256 target rows (UMMA N).  Each tile is processed as two work items, "hit"
+// and "miss", one mask and one 256-column TMEM accumulator each (double-buffered, so the
+// epilogue of one item overlaps the MMAs of the next).  Warp 0: TMA producer (At tile +
+// mask tile per K block of 128 samples, 128B swizzle, 4-stage mbarrier ring); warp 1:
+// one thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=256, K=32); warps 2-5:
+// epilogue -- tcgen05.ld the accumulator, pick the plane the target itself carries (the
+// one-hot byte At[(f,v), i]), scale, and add into one float64 register per one-hot row;
+// the reduction over a tile's targets is a loop over TMEM columns inside one thread.
+// Samples are class-sorted, so for a class-homogeneous target tile the hit mask is
+// non-zero only in the K blocks of the tile's own class and the miss mask only outside:
+// the other K blocks are skipped, which keeps the MMA work at 3 MAC per (pair, feature).
+// Partials are written per (tile group, one-hot row) and reduced in a fixed order.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -32,15 +33,17 @@ namespace fs {
 
 namespace {
 constexpr int BM = 128;   // one-hot rows per CTA
-constexpr int BN = 128;   // target rows per tile
+constexpr int BN = 256;   // target rows per tile
 constexpr int BK = 128;   // samples (bytes) per K block
 constexpr int STAGES = 4;
-constexpr int TILE_BYTES = 128 * BK;              // 16 KB (A, mH and mM tiles alike)
-constexpr int STAGE_BYTES = 3 * TILE_BYTES;       // 48 KB
-constexpr int GROUP = 8;                          // target tiles per CTA
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + 2 * BN * 24;
+constexpr int A_BYTES = BM * BK;                  // 16 KB
+constexpr int B_BYTES = BN * BK;                  // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 48 KB
+constexpr int GROUP = 4;                          // target tiles per CTA
+constexpr int CONST_BYTES = 2 * BN * 16;          // [2][BN] x {double c; int rs; int pad}
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + CONST_BYTES;
 constexpr int THREADS = 192;
-constexpr int TMEM_COLS = 512;                    // 2 buffers x (hit, miss) x 128 columns
+constexpr int TMEM_COLS = 512;                    // 2 accumulator buffers x 256 columns
 
 struct TileFlags {
     int64_t hs, he;   // sample range that can hold hits of this target tile
@@ -64,13 +67,16 @@ __device__ __forceinline__ TileFlags tile_flags(const int64_t *ids, int64_t R, i
     f.mixed = c_lo != c_hi;
     return f;
 }
-__device__ __forceinline__ bool need_hit(const TileFlags &f, int kb) {
+// does work item (tile, phase) need K block kb?  phase 0 = hit mask, 1 = miss mask
+__device__ __forceinline__ bool need_block(const TileFlags &f, int phase, int kb) {
     const int64_t k0 = (int64_t)kb * BK;
-    return k0 < f.he && k0 + BK > f.hs;
-}
-__device__ __forceinline__ bool need_miss(const TileFlags &f, int kb) {
-    const int64_t k0 = (int64_t)kb * BK;
+    if (phase == 0) return k0 < f.he && k0 + BK > f.hs;
     return f.mixed || !(k0 >= f.hs && k0 + BK <= f.he);
+}
+__device__ __forceinline__ int count_blocks(const TileFlags &f, int phase, int num_k_blocks) {
+    int c = 0;
+    for (int kb = 0; kb < num_k_blocks; ++kb) c += need_block(f, phase, kb) ? 1 : 0;
+    return c;
 }
 }  // namespace
 
@@ -87,9 +93,8 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
     uint64_t *tfull_bar = empty_bar + STAGES;     // [2] accumulator buffer ready
     uint64_t *tempty_bar = tfull_bar + 2;         // [2] accumulator buffer drained
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
-    // per-target constants of the tile being drained: [2][BN] x {cH, cM (double), rsH, rsM (int)}
-    double *s_c = reinterpret_cast<double *>(smem + STAGES * STAGE_BYTES + 512);
-    int32_t *s_rs = reinterpret_cast<int32_t *>(s_c + 2 * BN * 2);
+    // per-target constants of the work item being drained: [2][BN] x {double c; int rs}
+    unsigned char *s_const = smem + STAGES * STAGE_BYTES + 512;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM;                       // first one-hot row of this CTA
@@ -122,18 +127,19 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
             int it = 0;
             for (int t = tile_begin; t < tile_end; ++t) {
                 const TileFlags tf = tile_flags(ids, R, t, contiguous != 0, y, cls_start, n);
-                for (int kb = 0; kb < num_k_blocks; ++kb) {
-                    const bool nh = need_hit(tf, kb), nm = need_miss(tf, kb);
-                    if (!nh && !nm) continue;
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    ++it;
-                    tc::mbar_wait(&empty_bar[s], ph ^ 1);
-                    unsigned char *st = smem + s * STAGE_BYTES;
-                    tc::mbar_arrive_expect_tx(&full_bar[s], TILE_BYTES * (1 + (nh ? 1 : 0) + (nm ? 1 : 0)));
-                    tc::tma_load_2d(st, &tmap_at, &full_bar[s], kb * BK, m0);
-                    if (nh) tc::tma_load_2d(st + TILE_BYTES, &tmap_mh, &full_bar[s], kb * BK, t * BN);
-                    if (nm) tc::tma_load_2d(st + 2 * TILE_BYTES, &tmap_mm, &full_bar[s], kb * BK, t * BN);
+                for (int phase = 0; phase < 2; ++phase) {
+                    const CUtensorMap *tm = phase == 0 ? &tmap_mh : &tmap_mm;
+                    for (int kb = 0; kb < num_k_blocks; ++kb) {
+                        if (!need_block(tf, phase, kb)) continue;
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        ++it;
+                        tc::mbar_wait(&empty_bar[s], ph ^ 1);
+                        unsigned char *st = smem + s * STAGE_BYTES;
+                        tc::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                        tc::tma_load_2d(st, &tmap_at, &full_bar[s], kb * BK, m0);
+                        tc::tma_load_2d(st + A_BYTES, tm, &full_bar[s], kb * BK, t * BN);
+                    }
                 }
             }
         }
@@ -141,36 +147,37 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = tc::make_idesc_i8(BM, BN);
-            int it = 0;
+            int it = 0, item = 0;
             for (int t = tile_begin; t < tile_end; ++t) {
-                const int buf = (t - tile_begin) & 1;
-                const uint32_t tph = ((t - tile_begin) >> 1) & 1;
                 const TileFlags tf = tile_flags(ids, R, t, contiguous != 0, y, cls_start, n);
-                tc::mbar_wait(&tempty_bar[buf], tph ^ 1);     // epilogue has drained this buffer
-                tc::tc_fence_after();
-                const uint32_t acc_h = tmem_base + (uint32_t)(buf * 2 * BN);
-                const uint32_t acc_m = acc_h + BN;
-                uint32_t have_h = 0, have_m = 0;
-                for (int kb = 0; kb < num_k_blocks; ++kb) {
-                    const bool nh = need_hit(tf, kb), nm = need_miss(tf, kb);
-                    if (!nh && !nm) continue;
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    ++it;
-                    tc::mbar_wait(&full_bar[s], ph);
+                for (int phase = 0; phase < 2; ++phase) {
+                    if (count_blocks(tf, phase, num_k_blocks) == 0) continue;   // mask is all zero: nothing to add
+                    const int buf = item & 1;
+                    const uint32_t tph = (item >> 1) & 1;
+                    ++item;
+                    tc::mbar_wait(&tempty_bar[buf], tph ^ 1);     // epilogue has drained this buffer
                     tc::tc_fence_after();
-                    const uint32_t sa = tc::smem_u32(smem + s * STAGE_BYTES);
-                    const uint64_t da = tc::make_smem_desc_sw128(sa);
-                    const uint64_t dh = tc::make_smem_desc_sw128(sa + TILE_BYTES);
-                    const uint64_t dm = tc::make_smem_desc_sw128(sa + 2 * TILE_BYTES);
+                    const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+                    uint32_t have = 0;
+                    for (int kb = 0; kb < num_k_blocks; ++kb) {
+                        if (!need_block(tf, phase, kb)) continue;
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        ++it;
+                        tc::mbar_wait(&full_bar[s], ph);
+                        tc::tc_fence_after();
+                        const uint32_t sa = tc::smem_u32(smem + s * STAGE_BYTES);
+                        const uint64_t da = tc::make_smem_desc_sw128(sa);
+                        const uint64_t db = tc::make_smem_desc_sw128(sa + A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 32; ++k) {
-                        if (nh) { tc::mma_i8(acc_h, da + (uint64_t)(2 * k), dh + (uint64_t)(2 * k), idesc, have_h); have_h = 1; }
-                        if (nm) { tc::mma_i8(acc_m, da + (uint64_t)(2 * k), dm + (uint64_t)(2 * k), idesc, have_m); have_m = 1; }
+                        for (int k = 0; k < BK / 32; ++k) {
+                            tc::mma_i8(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, have);
+                            have = 1;
+                        }
+                        tc::tc_commit(&empty_bar[s]);
                     }
-                    tc::tc_commit(&empty_bar[s]);
+                    tc::tc_commit(&tfull_bar[buf]);
                 }
-                tc::tc_commit(&tfull_bar[buf]);
             }
         }
     } else {
@@ -181,84 +188,71 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
         const bool row_live = mrow < K_rows;
         const int8_t *at_row = At + (row_live ? mrow : 0) * ldt;
         double acc = 0.0;
+        int item = 0;
         for (int t = tile_begin; t < tile_end; ++t) {
-            const int buf = (t - tile_begin) & 1;
-            const uint32_t tph = ((t - tile_begin) >> 1) & 1;
             const TileFlags tf = tile_flags(ids, R, t, contiguous != 0, y, cls_start, n);
-            // does either accumulator receive no MMA at all for this tile?
-            bool any_h = false, any_m = false;
-            for (int kb = 0; kb < num_k_blocks; ++kb) { any_h |= need_hit(tf, kb); any_m |= need_miss(tf, kb); }
-            // per-target constants (one target per epilogue thread)
-            {
-                const int64_t r = (int64_t)t * BN + et;
-                double ch = 0.0, cm = 0.0;
-                int rh = 0, rm = 0;
-                if (r < R) {
-                    const RowInfo ri = rinfo[r];
-                    ch = ri.coef[FS_MASK_NEAR_HIT];           // -aH
-                    cm = ri.coef[FS_MASK_NEAR_MISS];          // +aM
-                    rh = ri.n_hit - ri.n_far_hit;
-                    rm = ri.n_miss - ri.n_far_miss;
+            for (int phase = 0; phase < 2; ++phase) {
+                if (count_blocks(tf, phase, num_k_blocks) == 0) continue;
+                const int buf = item & 1;
+                const uint32_t tph = (item >> 1) & 1;
+                ++item;
+                // per-target constants: c = -aH (hit phase) or +aM (miss phase); rs = mask row sum
+                double *s_c = reinterpret_cast<double *>(s_const + buf * BN * 16);
+                int32_t *s_rs = reinterpret_cast<int32_t *>(s_const + buf * BN * 16 + BN * 8);
+                for (int e = et; e < BN; e += 128) {
+                    const int64_t r = (int64_t)t * BN + e;
+                    double c = 0.0;
+                    int rs = 0;
+                    if (r < R) {
+                        const RowInfo ri = rinfo[r];
+                        c = phase == 0 ? ri.coef[FS_MASK_NEAR_HIT] : ri.coef[FS_MASK_NEAR_MISS];
+                        rs = phase == 0 ? ri.n_hit - ri.n_far_hit : ri.n_miss - ri.n_far_miss;
+                    }
+                    s_c[e] = c;
+                    s_rs[e] = rs;
                 }
-                s_c[(buf * BN + et) * 2] = ch;
-                s_c[(buf * BN + et) * 2 + 1] = cm;
-                s_rs[(buf * BN + et) * 2] = rh;
-                s_rs[(buf * BN + et) * 2 + 1] = rm;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            tc::mbar_wait(&tfull_bar[buf], tph);
-            tc::tc_fence_after();
-            const uint32_t acc_h = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN);
-            const uint32_t acc_m = acc_h + BN;
-            const int64_t id0 = contiguous ? ids[0] + (int64_t)t * BN : 0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                tc::mbar_wait(&tfull_bar[buf], tph);
+                tc::tc_fence_after();
+                const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+                const int64_t id0 = contiguous ? ids[0] + (int64_t)t * BN : 0;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t vh[32], vm[32];
-                if (any_h) tc::tmem_ld_32x32(acc_h + c0, vh);
-                if (any_m) tc::tmem_ld_32x32(acc_m + c0, vm);
-                // one-hot bytes of the 32 targets at this one-hot row
-                uint32_t oh[8];
-                if (contiguous) {
-                    // ids are contiguous and tile-aligned to 128 relative to ids[0]; ids[0] may be unaligned
-                    const int8_t *src = at_row + id0 + c0;
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    tc::tmem_ld_32x32(tacc + c0, v);
+                    // one-hot bytes of the 32 targets at this one-hot row
+                    uint32_t oh[8];
+                    const int64_t rbase = (int64_t)t * BN + c0;
+                    if (contiguous && rbase + 32 <= R && ((id0 + c0) & 15) == 0) {
+                        const uint4 *src = reinterpret_cast<const uint4 *>(at_row + id0 + c0);
+                        const uint4 a = src[0], b = src[1];
+                        oh[0] = a.x; oh[1] = a.y; oh[2] = a.z; oh[3] = a.w;
+                        oh[4] = b.x; oh[5] = b.y; oh[6] = b.z; oh[7] = b.w;
+                    } else {
 #pragma unroll
-                    for (int w = 0; w < 8; ++w) {
-                        uint32_t x = 0;
+                        for (int w = 0; w < 8; ++w) {
+                            uint32_t x = 0;
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const int64_t r = (int64_t)t * BN + c0 + w * 4 + b;
-                            const uint32_t byte = (r < R) ? (uint32_t)(uint8_t)src[w * 4 + b] : 0u;
-                            x |= byte << (8 * b);
+                            for (int b = 0; b < 4; ++b) {
+                                const int64_t r = rbase + w * 4 + b;
+                                uint32_t byte = 0u;
+                                if (r < R) byte = (uint32_t)(uint8_t)(contiguous ? at_row[id0 + c0 + w * 4 + b] : at_row[ids[r]]);
+                                x |= byte << (8 * b);
+                            }
+                            oh[w] = x;
                         }
-                        oh[w] = x;
                     }
-                } else {
+                    tc::tmem_ld_wait();
 #pragma unroll
-                    for (int w = 0; w < 8; ++w) {
-                        uint32_t x = 0;
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const int64_t r = (int64_t)t * BN + c0 + w * 4 + b;
-                            const uint32_t byte = (r < R) ? (uint32_t)(uint8_t)at_row[ids[r]] : 0u;
-                            x |= byte << (8 * b);
-                        }
-                        oh[w] = x;
+                    for (int e = 0; e < 32; ++e) {
+                        const bool on = ((oh[e >> 2] >> (8 * (e & 3))) & 0xffu) != 0u;
+                        const double term = s_c[c0 + e] * (double)(s_rs[c0 + e] - (int)v[e]);
+                        acc += on ? term : 0.0;
                     }
                 }
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const bool on = ((oh[e >> 2] >> (8 * (e & 3))) & 0xffu) != 0u;
-                    const int c = c0 + e;
-                    const double ch = s_c[(buf * BN + c) * 2], cm = s_c[(buf * BN + c) * 2 + 1];
-                    const int gh = any_h ? (int)vh[e] : 0, gm = any_m ? (int)vm[e] : 0;
-                    const double term = ch * (double)(s_rs[(buf * BN + c) * 2] - gh) +
-                                        cm * (double)(s_rs[(buf * BN + c) * 2 + 1] - gm);
-                    acc += on ? term : 0.0;
-                }
+                tc::tc_fence_before();
+                tc::mbar_arrive(&tempty_bar[buf]);
             }
-            tc::tc_fence_before();
-            tc::mbar_arrive(&tempty_bar[buf]);
         }
         if (row_live) tpartial[(int64_t)blockIdx.x * K_rows + mrow] = acc;
     }
