@@ -41,24 +41,33 @@ struct Fail {
         }                                    \
     } while (0)
 
-// Device buffer with RAII; never copies.
+// Stream used by DevBuf allocations of the current API call (set at every C-ABI entry).
+cudaStream_t &alloc_stream();
+void configure_pool(int device);
+
+// Device buffer with RAII; never copies.  Memory comes from the device's stream-ordered
+// pool (cudaMallocAsync) whose release threshold is raised so that freed blocks stay
+// cached: a fit re-uses the previous fit's allocations instead of paying cudaMalloc /
+// cudaFree for gigabyte-sized operands.
 template <typename T>
 struct DevBuf {
     T *ptr = nullptr;
     size_t count = 0;
+    cudaStream_t st = nullptr;
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (ptr) cudaFree(ptr);
+        if (ptr) cudaFreeAsync(ptr, st);
         ptr = nullptr;
         count = 0;
     }
     void alloc(size_t n) {
         release();
         if (n == 0) return;
-        FS_CUDA(cudaMalloc(reinterpret_cast<void **>(&ptr), n * sizeof(T)));
+        st = alloc_stream();
+        FS_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ptr), n * sizeof(T), st));
         count = n;
     }
     // grow-only (keeps the allocation when large enough)

@@ -21,6 +21,24 @@ void set_error(const char *fmt, ...) {
 }
 const char *get_error() { return g_err; }
 
+cudaStream_t &alloc_stream() {
+    static thread_local cudaStream_t s = nullptr;
+    return s;
+}
+
+// keep freed blocks in the device's default memory pool (no trimming at synchronisation)
+void configure_pool(int device) {
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thresh = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+    cudaGetLastError();
+    done[device] = true;
+}
+
 // ---------------------------------------------------------------------------
 // column scan: one thread per column, rows streamed coalesced across columns.
 // HBM-bound: reads n*p*sizeof(T) once.
@@ -158,6 +176,8 @@ static fs_dataset *create_common(int dtype, int64_t n, int64_t p, int64_t ld, co
     FS_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
     FS_REQUIRE(major == 10, FS_ERR_NO_DEVICE, "device %d is not sm_100 (compute capability major %d)", device, major);
     FS_CUDA(cudaSetDevice(device));
+    configure_pool(device);
+    alloc_stream() = static_cast<cudaStream_t>(stream);
     fs_dataset *ds = new fs_dataset();
     ds->device = device;
     ds->stream = static_cast<cudaStream_t>(stream);
@@ -388,6 +408,7 @@ int fs_dataset_destroy(fs_dataset *ds) {
     if (!ds) return FS_OK;
     cudaSetDevice(ds->device);
     cudaStreamSynchronize(ds->stream);
+    alloc_stream() = ds->stream;
     delete ds;
     return FS_OK;
 }

@@ -110,6 +110,7 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
     }
     FS_CUDA(cudaSetDevice(ds->device));
     cudaStream_t st = ds->stream;
+    alloc_stream() = st;
     const int64_t n = ds->n;
     int launches = 0;
     Timer timer(stats != nullptr, st);
@@ -278,6 +279,7 @@ int fs_score(fs_dataset *ds, int algo, int use_star, int32_t k, const float *cla
                    "fs_score: bad row range [%lld, %lld) for n=%lld", (long long)row_begin, (long long)row_end,
                    (long long)ds->n);
         FS_CUDA(cudaSetDevice(ds->device));
+        alloc_stream() = ds->stream;
         std::vector<int64_t> targets(row_end - row_begin);
         for (int64_t r = row_begin; r < row_end; ++r) targets[r - row_begin] = r;
         double *d_out = wsum_out;
@@ -311,6 +313,7 @@ int fs_debug_rows(fs_dataset *ds, int algo, int use_star, int32_t k, const float
         FS_REQUIRE(ds && targets && nt >= 1, FS_ERR_INVALID, "fs_debug_rows: invalid argument");
         if (!feat_idx) n_kept = ds->p;
         FS_CUDA(cudaSetDevice(ds->device));
+        alloc_stream() = ds->stream;
         std::vector<int64_t> ids(nt);
         for (int64_t t = 0; t < nt; ++t) {
             FS_REQUIRE(targets[t] >= 0 && targets[t] < ds->n, FS_ERR_INVALID, "fs_debug_rows: target %lld out of range",

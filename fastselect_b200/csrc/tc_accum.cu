@@ -18,8 +18,8 @@
 // and "miss", one mask and one 256-column TMEM accumulator each (double-buffered, so the
 // epilogue of one item overlaps the MMAs of the next).  Warp 0: TMA producer (At tile +
 // mask tile per K block of 128 samples, 128B swizzle, 4-stage mbarrier ring); warp 1:
-// one thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=256, K=32); warps 2-5:
-// epilogue -- tcgen05.ld the accumulator, pick the plane the target itself carries (the
+// one thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=256, K=32); warps 2-9
+// (lane quarter x column half): epilogue -- tcgen05.ld the accumulator, pick the plane the target itself carries (the
 // one-hot byte At[(f,v), i]), scale, and add into one float64 register per one-hot row;
 // the reduction over a tile's targets is a loop over TMEM columns inside one thread.
 // Samples are class-sorted, so for a class-homogeneous target tile the hit mask is
@@ -42,7 +42,8 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 48 KB
 constexpr int GROUP = 4;                          // target tiles per CTA
 constexpr int CONST_BYTES = 2 * BN * 16;          // [2][BN] x {double c; int rs; int pad}
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + CONST_BYTES;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;              // TMA warp, MMA warp, 8 epilogue warps
+constexpr int HALF = BN / 2;              // target columns per epilogue thread
 constexpr int TMEM_COLS = 512;                    // 2 accumulator buffers x 256 columns
 
 struct TileFlags {
@@ -111,7 +112,7 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
         }
         for (int b = 0; b < 2; ++b) {
             tc::mbar_init(&tfull_bar[b], 1);
-            tc::mbar_init(&tempty_bar[b], 128);           // all epilogue threads arrive
+            tc::mbar_init(&tempty_bar[b], 256);           // all epilogue threads arrive
         }
         tc::fence_barrier_init();
     }
@@ -181,16 +182,47 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
             }
         }
     } else {
-        // ===== epilogue (warps 2..5, 128 threads, thread = one-hot row) =====
+        // ===== epilogue (warps 2..9: lane quarter = warp % 4, column half = (warp - 2) / 4) =====
+        // thread = one-hot row (TMEM lane) x half of the work item's 256 target columns
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int et = q * 32 + lane;                         // 0..127: TMEM lane / local one-hot row
+        const int ethread = (warp - 2) * 32 + lane;           // 0..255
         const int64_t mrow = (int64_t)m0 + et;
         const bool row_live = mrow < K_rows;
         const int8_t *at_row = At + (row_live ? mrow : 0) * ldt;
-        double acc = 0.0;
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
         int item = 0;
         for (int t = tile_begin; t < tile_end; ++t) {
             const TileFlags tf = tile_flags(ids, R, t, contiguous != 0, y, cls_start, n);
+            // one-hot bytes of this thread's 128 targets at its one-hot row (issued before the
+            // accumulator wait so the loads overlap the MMAs); shared by both phases
+            uint32_t oh[HALF / 4];
+            {
+                const int64_t rbase = (int64_t)t * BN + half * HALF;
+                const int64_t id0 = contiguous ? ids[0] + rbase : 0;
+                if (contiguous && rbase + HALF <= R && (id0 & 15) == 0) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(at_row + id0);
+#pragma unroll
+                    for (int w = 0; w < HALF / 16; ++w) {
+                        const uint4 a = src[w];
+                        oh[4 * w] = a.x; oh[4 * w + 1] = a.y; oh[4 * w + 2] = a.z; oh[4 * w + 3] = a.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < HALF / 4; ++w) {
+                        uint32_t x = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const int64_t r = rbase + w * 4 + b;
+                            uint32_t byte = 0u;
+                            if (r < R) byte = (uint32_t)(uint8_t)(contiguous ? at_row[id0 + w * 4 + b] : at_row[ids[r]]);
+                            x |= byte << (8 * b);
+                        }
+                        oh[w] = x;
+                    }
+                }
+            }
             for (int phase = 0; phase < 2; ++phase) {
                 if (count_blocks(tf, phase, num_k_blocks) == 0) continue;
                 const int buf = item & 1;
@@ -199,8 +231,8 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                 // per-target constants: c = -aH (hit phase) or +aM (miss phase); rs = mask row sum
                 double *s_c = reinterpret_cast<double *>(s_const + buf * BN * 16);
                 int32_t *s_rs = reinterpret_cast<int32_t *>(s_const + buf * BN * 16 + BN * 8);
-                for (int e = et; e < BN; e += 128) {
-                    const int64_t r = (int64_t)t * BN + e;
+                {
+                    const int64_t r = (int64_t)t * BN + ethread;
                     double c = 0.0;
                     int rs = 0;
                     if (r < R) {
@@ -208,53 +240,41 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                         c = phase == 0 ? ri.coef[FS_MASK_NEAR_HIT] : ri.coef[FS_MASK_NEAR_MISS];
                         rs = phase == 0 ? ri.n_hit - ri.n_far_hit : ri.n_miss - ri.n_far_miss;
                     }
-                    s_c[e] = c;
-                    s_rs[e] = rs;
+                    s_c[ethread] = c;
+                    s_rs[ethread] = rs;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 tc::mbar_wait(&tfull_bar[buf], tph);
                 tc::tc_fence_after();
-                const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-                const int64_t id0 = contiguous ? ids[0] + (int64_t)t * BN : 0;
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * HALF);
+#pragma unroll
+                for (int c0 = 0; c0 < HALF; c0 += 32) {
                     uint32_t v[32];
                     tc::tmem_ld_32x32(tacc + c0, v);
-                    // one-hot bytes of the 32 targets at this one-hot row
-                    uint32_t oh[8];
-                    const int64_t rbase = (int64_t)t * BN + c0;
-                    if (contiguous && rbase + 32 <= R && ((id0 + c0) & 15) == 0) {
-                        const uint4 *src = reinterpret_cast<const uint4 *>(at_row + id0 + c0);
-                        const uint4 a = src[0], b = src[1];
-                        oh[0] = a.x; oh[1] = a.y; oh[2] = a.z; oh[3] = a.w;
-                        oh[4] = b.x; oh[5] = b.y; oh[6] = b.z; oh[7] = b.w;
-                    } else {
-#pragma unroll
-                        for (int w = 0; w < 8; ++w) {
-                            uint32_t x = 0;
-#pragma unroll
-                            for (int b = 0; b < 4; ++b) {
-                                const int64_t r = rbase + w * 4 + b;
-                                uint32_t byte = 0u;
-                                if (r < R) byte = (uint32_t)(uint8_t)(contiguous ? at_row[id0 + c0 + w * 4 + b] : at_row[ids[r]]);
-                                x |= byte << (8 * b);
-                            }
-                            oh[w] = x;
-                        }
-                    }
                     tc::tmem_ld_wait();
+                    const double *cc = s_c + half * HALF + c0;
+                    const int32_t *rr = s_rs + half * HALF + c0;
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const bool on = ((oh[e >> 2] >> (8 * (e & 3))) & 0xffu) != 0u;
-                        const double term = s_c[c0 + e] * (double)(s_rs[c0 + e] - (int)v[e]);
-                        acc += on ? term : 0.0;
+                    for (int e = 0; e < 32; e += 4) {
+                        const uint32_t w = oh[(c0 + e) >> 2];
+                        // term = on ? c * (rs - G) : 0, four independent float64 chains
+                        const double t0 = (double)(rr[e] - (int)v[e]);
+                        const double t1 = (double)(rr[e + 1] - (int)v[e + 1]);
+                        const double t2 = (double)(rr[e + 2] - (int)v[e + 2]);
+                        const double t3 = (double)(rr[e + 3] - (int)v[e + 3]);
+                        acc0 = fma((w & 0x000000ffu) ? cc[e] : 0.0, t0, acc0);
+                        acc1 = fma((w & 0x0000ff00u) ? cc[e + 1] : 0.0, t1, acc1);
+                        acc2 = fma((w & 0x00ff0000u) ? cc[e + 2] : 0.0, t2, acc2);
+                        acc3 = fma((w & 0xff000000u) ? cc[e + 3] : 0.0, t3, acc3);
                     }
                 }
                 tc::tc_fence_before();
                 tc::mbar_arrive(&tempty_bar[buf]);
             }
         }
-        if (row_live) tpartial[(int64_t)blockIdx.x * K_rows + mrow] = acc;
+        // two column halves per one-hot row: partial layout [group][half][row]
+        if (row_live)
+            tpartial[((int64_t)blockIdx.x * 2 + half) * K_rows + mrow] = (acc0 + acc1) + (acc2 + acc3);
     }
     __syncthreads();
     if (warp == 1) {
@@ -263,7 +283,8 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
     }
 }
 
-int tc_accum_groups(int64_t R) { return (int)ceil_div(ceil_div(R, BN), GROUP); }
+// partial vectors written per launch: (tile groups) x (2 column halves)
+int tc_accum_groups(int64_t R) { return 2 * (int)ceil_div(ceil_div(R, BN), GROUP); }
 
 void launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
                      int64_t R, const int64_t *d_ids, bool contiguous, const int32_t *d_y,
@@ -271,7 +292,7 @@ void launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, con
                      double *tpartial, cudaStream_t st, int *launches) {
     FS_CUDA(cudaFuncSetAttribute(tc_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     const int num_tiles = (int)ceil_div(R, BN);
-    dim3 grid((unsigned)tc_accum_groups(R), (unsigned)ceil_div(K_rows, BM));
+    dim3 grid((unsigned)(tc_accum_groups(R) / 2), (unsigned)ceil_div(K_rows, BM));
     tc_accum_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmap_at, tmap_mh, tmap_mm, (int)ceil_div(n, BK), n, R, num_tiles,
                                                        d_ids, contiguous ? 1 : 0, d_y, d_cls_start, rinfo, At, ldt,
                                                        K_rows, tpartial);
