@@ -152,6 +152,7 @@ def run_cpu_port(w, xs, ys):
 def cpu_baseline(w):
     from oracle import ref_oracle as R
 
+    R.set_threads(os.cpu_count() or 1)
     xs, ys, n_s, p_s = cpu_sample(w)
     dt = run_cpu_port(w, xs, ys)
     return {"value": n_s * n_s * p_s / dt, "unit": UNIT, "cores": R.max_threads(), "kind": "port",
@@ -167,6 +168,7 @@ def reference_arm(args):
     from oracle import ref_oracle as R
 
     R.build()
+    R.set_threads(os.cpu_count() or 1)
     w = make_workload(args.workload, 1, "weak", args.n, args.p)
     xs, ys, n_s, p_s = cpu_sample(w)
     for _ in range(args.warmup):
@@ -315,7 +317,8 @@ def own_arm(args):
                 "peak_source": "measured copy (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
                 "note": "issue-bound CUDA-core kernel; HBM fraction is low by construction"}
 
-    cpu = cpu_baseline(w)
+    # the CPU baseline is reported at N = 1 only (rank 0)
+    cpu = cpu_baseline(w) if world == 1 else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": "u8 one-hot / int32 accum (genotype), f32 terms + f64 accum (continuous)",

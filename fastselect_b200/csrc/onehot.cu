@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(const Tin *__restric
                                                             int8_t *__restrict__ A, int8_t *__restrict__ At,
                                                             uint8_t *__restrict__ codes) {
     __shared__ __align__(16) uint8_t code_rc[ENC_ROWS][ENC_COLS];       // [sample][column]
-    __shared__ __align__(16) uint8_t code_cr[ENC_COLS][ENC_ROWS];       // [column][sample]
+    __shared__ __align__(16) uint8_t code_cr[ENC_COLS][ENC_ROWS + 4];   // [column][sample], padded: conflict-free transposed stores
     __shared__ uint8_t kcol[ENC_COLS * FS_DISTINCT_CAP];                // one-hot index -> column in tile
     __shared__ uint8_t kval[ENC_COLS * FS_DISTINCT_CAP];                // one-hot index -> value code
     const int tid = threadIdx.x;
@@ -97,13 +97,21 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(const Tin *__restric
         const int c = tid & (ENC_COLS - 1);
         int64_t f = 0;
         int off = 0, V = 0;
-        double v[FS_DISTINCT_CAP];
+        // code table of this thread's column in the input's own type (values came from the
+        // data, so the conversion back is exact); float64 input scored in float32 arithmetic
+        // is compared after narrowing, as the reference compares x.astype(float32)
+        Tin v[FS_DISTINCT_CAP];
+        float vf[FS_DISTINCT_CAP];
         if (c < ncols) {
             f = tcol[c0 + c];
             off = toff[c0 + c];
             V = toff[c0 + c + 1] - off;
 #pragma unroll
-            for (int q = 0; q < FS_DISTINCT_CAP; ++q) v[q] = vals[f * FS_DISTINCT_CAP + q];
+            for (int q = 0; q < FS_DISTINCT_CAP; ++q) {
+                const double d = vals[f * FS_DISTINCT_CAP + q];
+                v[q] = (Tin)d;
+                vf[q] = (float)d;
+            }
             if (tid < ENC_COLS)
                 for (int q = 0; q < V; ++q) {
                     kcol[off - k0 + q] = (uint8_t)c;
@@ -113,11 +121,11 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(const Tin *__restric
         for (int rr = tid >> 6; rr < ENC_ROWS; rr += 4) {
             uint8_t code = 0;
             if (c < ncols && rr < nrows) {
-                const double xv = (double)x[perm[r0 + rr] * ldx + f];
+                const Tin xv = x[perm[r0 + rr] * ldx + f];
                 int found = 0;
 #pragma unroll
                 for (int q = FS_DISTINCT_CAP - 1; q >= 0; --q) {
-                    const bool eq = as_f32 ? ((float)xv == (float)v[q]) : (xv == v[q]);
+                    const bool eq = as_f32 ? ((float)xv == vf[q]) : (xv == v[q]);
                     if (q < V && eq) found = q;      // lowest matching index wins
                 }
                 code = (uint8_t)found;

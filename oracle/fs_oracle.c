@@ -34,6 +34,14 @@
 /* mask codes written to mask_out (one int8 per (target, j)) */
 enum { FSO_NONE = 0, FSO_NEAR_HIT = 1, FSO_NEAR_MISS = 2, FSO_FAR_MISS = 3, FSO_FAR_HIT = 4 };
 
+FSO_API void fso_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 FSO_API int fso_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

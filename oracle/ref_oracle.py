@@ -47,6 +47,11 @@ def max_threads() -> int:
     return int(lib().fso_max_threads())
 
 
+def set_threads(n: int) -> None:
+    """OpenMP threads used by the oracle (torchrun exports OMP_NUM_THREADS=1)."""
+    lib().fso_set_threads(C.c_int(int(n)))
+
+
 # --------------------------------------------------------------------------- #
 # preprocessing restated (a10)
 # --------------------------------------------------------------------------- #
