@@ -241,9 +241,9 @@ class ReliefF(_ReliefBase):
     """ReliefF on B200 (drop-in for ``fast_select.ReliefF``, GPU backend; ReliefF.py:239-407).
 
     Follows the reference's CPU semantics (k hits + k misses of every other class,
-    prior-weighted), any ``n_neighbors`` and any number of classes.  Ties at the k-th
-    distance are broken by sample index (the reference's order is that of numba's
-    quicksort)."""
+    prior-weighted), any ``n_neighbors`` and any number of classes.  Candidates tied at the
+    k-th distance are taken in the order the reference takes them (numba's quicksort order,
+    replayed on the GPU); ``FS_B200_RELIEFF_TIES=index`` switches to sample-index order."""
 
     _algo_label = "ReliefF"
 

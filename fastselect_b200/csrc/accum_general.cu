@@ -26,14 +26,12 @@ constexpr int kAccThreads = 128;  // features per CTA
 constexpr int kAccRows = 16;      // target rows per register block
 constexpr int kAccJT = 128;       // samples per coefficient tile
 
-__device__ __forceinline__ float term32(float a, float b, float r, bool cmp) {
-    const float t = __fmul_rn(fabsf(__fsub_rn(a, b)), r);
-    return cmp ? ((a != b) ? 1.0f : 0.0f) : t;
+__device__ __forceinline__ float term_cont32(float a, float b, float r) {
+    return __fmul_rn(fabsf(__fsub_rn(a, b)), r);
 }
 // SURF.py:153-158: float64 product, stored as float32
-__device__ __forceinline__ float term32(double a, double b, float r, bool cmp) {
-    const float t = (float)__dmul_rn(fabs(__dsub_rn(a, b)), (double)r);
-    return cmp ? ((a != b) ? 1.0f : 0.0f) : t;
+__device__ __forceinline__ float term_cont32(double a, double b, float r) {
+    return (float)__dmul_rn(fabs(__dsub_rn(a, b)), (double)r);
 }
 
 template <typename T>
@@ -80,18 +78,34 @@ accum_general_kernel(const T *__restrict__ xg, int64_t n, int64_t ld, const floa
             float acc[kAccRows];
 #pragma unroll
             for (int a = 0; a < kAccRows; ++a) acc[a] = 0.0f;
-#pragma unroll 4
-            for (int jj = 0; jj < nj; ++jj) {
-                const T xj = xg[(j0 + jj) * ld + fc];
-                const float4 *cp = reinterpret_cast<const float4 *>(scoef[jj]);
-                float c[kAccRows];
+            // the chunk type is uniform per warp (float32: 32 columns per chunk), so the branch
+            // below does not diverge; sample values are fetched 8 rows ahead of their use
+            constexpr int kAhead = 8;
+            for (int jb = 0; jb < nj; jb += kAhead) {
+                T xj[kAhead];
 #pragma unroll
-                for (int q = 0; q < kAccRows / 4; ++q) {
-                    const float4 v = cp[q];
-                    c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+                for (int u = 0; u < kAhead; ++u) {
+                    const int jj = jb + u < nj ? jb + u : nj - 1;
+                    xj[u] = xg[(j0 + jj) * ld + fc];
                 }
 #pragma unroll
-                for (int a = 0; a < kAccRows; ++a) acc[a] = fmaf(c[a], term32(xi[a], xj, r, cmp), acc[a]);
+                for (int u = 0; u < kAhead; ++u) {
+                    if (jb + u >= nj) break;
+                    const float4 *cp = reinterpret_cast<const float4 *>(scoef[jb + u]);
+                    float c[kAccRows];
+#pragma unroll
+                    for (int q = 0; q < kAccRows / 4; ++q) {
+                        const float4 v = cp[q];
+                        c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+                    }
+                    if (cmp) {
+#pragma unroll
+                        for (int a = 0; a < kAccRows; ++a) acc[a] += (xi[a] != xj[u]) ? c[a] : 0.0f;
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < kAccRows; ++a) acc[a] = fmaf(c[a], term_cont32(xi[a], xj[u], r), acc[a]);
+                    }
+                }
             }
 #pragma unroll
             for (int a = 0; a < kAccRows; ++a) total += (double)acc[a];
@@ -147,12 +161,14 @@ relieff_gather_kernel(const T *__restrict__ xg, int64_t ld, const float *__restr
     if (live) partial[(int64_t)blockIdx.x * ld + f] = total;
 }
 
-// rows per CTA such that the grid is ~8 CTAs per SM and a multiple of kAccRows
+// Rows per CTA.  CTAs that share a 128-column strip of X (same blockIdx.y) are launched
+// back to back (blockIdx.x fastest), so with ~128 row chunks per strip only ~8 strips are
+// in flight on the chip at a time and each strip (n x 512 B) stays L2-resident while its
+// CTAs sweep it once per 16 target rows.
 static int64_t rows_per_cta_for(int64_t R, int64_t ld) {
-    const int64_t ftiles = ceil_div(ld, kAccThreads);
-    int64_t want_chunks = std::max<int64_t>(1, ceil_div(148 * 8, ftiles));
-    int64_t rows = std::max<int64_t>(kAccRows, round_up(ceil_div(R, want_chunks), kAccRows));
-    return rows;
+    (void)ld;
+    const int64_t want_chunks = 128;
+    return std::max<int64_t>(kAccRows, round_up(ceil_div(R, want_chunks), kAccRows));
 }
 
 int64_t accum_general_partials(const WorkSet &ws, int64_t R) {

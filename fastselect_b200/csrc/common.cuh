@@ -140,7 +140,7 @@ struct fs_dataset {
     std::vector<int64_t> perm, inv_perm;     // perm[r] = original index of internal row r
     std::vector<int32_t> y_sorted;           // class of internal row r
     std::vector<int64_t> cls_start;          // [C+1] internal row range of each class
-    fs::DevBuf<int64_t> d_perm;
+    fs::DevBuf<int64_t> d_perm, d_inv_perm;
     fs::DevBuf<int32_t> d_y;
     fs::DevBuf<int64_t> d_cls_start;
     // column scan
@@ -170,6 +170,8 @@ struct fs_dataset {
     fs::DevBuf<double> tpartial;  // tensor-path accumulation partials
     fs::DevBuf<int8_t> maskH, maskM;
     fs::DevBuf<int8_t> a_gather;  // gathered one-hot target rows (fs_debug_rows)
+    fs::DevBuf<int32_t> tie_flag, tie_order;   // ReliefF reference tie order (select.cu)
+    fs::DevBuf<float> tie_keys;
     fs::DevBuf<unsigned long long> counters;
 };
 

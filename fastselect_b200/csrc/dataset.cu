@@ -119,9 +119,11 @@ static void finish_create(fs_dataset *ds, const int32_t *y_enc) {
     }
     for (int c = 0; c < ds->n_classes; ++c) ds->cls_start[c + 1] += ds->cls_start[c];
     ds->d_perm.alloc(n);
+    ds->d_inv_perm.alloc(n);
     ds->d_y.alloc(n);
     ds->d_cls_start.alloc(ds->n_classes + 1);
     FS_CUDA(cudaMemcpyAsync(ds->d_perm.ptr, ds->perm.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ds->stream));
+    FS_CUDA(cudaMemcpyAsync(ds->d_inv_perm.ptr, ds->inv_perm.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, ds->stream));
     FS_CUDA(cudaMemcpyAsync(ds->d_y.ptr, ds->y_sorted.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, ds->stream));
     FS_CUDA(cudaMemcpyAsync(ds->d_cls_start.ptr, ds->cls_start.data(), (ds->n_classes + 1) * sizeof(int64_t),
                             cudaMemcpyHostToDevice, ds->stream));

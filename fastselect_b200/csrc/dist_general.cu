@@ -44,8 +44,24 @@ __device__ __forceinline__ void unpack(const double2 &v, double (&o)[2]) {
     o[0] = v.x; o[1] = v.y;
 }
 
+// float32 term widened to float64 without the conversion unit: F2F.F64.F32 runs on the
+// XU pipe at 16 lanes/clk/SM and bounded this kernel at 92 % XU utilisation (ncu,
+// profiles/r01_ncu_general_summary.txt).  For a normal, non-negative float with bits x,
+// the float64 with bits x * 2^29 + (896 << 52) has the same value (exponent re-biased from
+// 127 to 1023, mantissa left-aligned): two integer instructions on the ALU/FMA pipes.  Zero (and denormal
+// products, < 1.2e-38) map to ~2^-127 instead; such an addend is absorbed without trace by
+// any partial sum above 2^-74, and the kernel flushes totals below 2^-100 to exactly 0, so
+// only rows whose continuous distance is itself below 1e-30 could see a difference.
+__device__ __forceinline__ double widen_f32(float t) {
+    // written as two 32-bit halves on purpose: a single 64-bit multiply-add compiles to
+    // IMAD.WIDE.U32, which stalls the FMA pipe (ncu: stall_math/dispatch on that line)
+    const uint32_t x = __float_as_uint(t);
+    const uint32_t hi = (x >> 3) + 0x38000000u;
+    const uint32_t lo = x << 29;
+    return __hiloint2double((int)hi, (int)lo);
+}
 __device__ __forceinline__ double term_cont(float a, float b, float r) {
-    return (double)__fmul_rn(fabsf(__fsub_rn(a, b)), r);
+    return widen_f32(__fmul_rn(fabsf(__fsub_rn(a, b)), r));
 }
 __device__ __forceinline__ double term_cont(double a, double b, float r) {
     return __dmul_rn(fabs(__dsub_rn(a, b)), (double)r);
@@ -55,7 +71,10 @@ template <typename T>
 __global__ void __launch_bounds__(256, 2)
 dist_general_kernel(const T *__restrict__ xa, int64_t na, const T *__restrict__ xb, int64_t nb, int64_t ld,
                     const float *__restrict__ recip, const uint8_t *__restrict__ ctype, int nchunks,
-                    double *__restrict__ D, int64_t ldd) {
+                    double *__restrict__ D, int64_t ldd, int symmetric) {
+    // symmetric: xa == xb (all samples are targets): d_ij = d_ji, so only tiles on or above
+    // the diagonal are computed and each is also stored transposed (half the arithmetic)
+    if (symmetric && blockIdx.x < blockIdx.y) return;
     using V = typename Vec<T>::type;
     constexpr int VN = Vec<T>::N;                 // features per 128-bit load
     constexpr int FT = kChunkBytes / sizeof(T);   // features per chunk
@@ -154,6 +173,10 @@ dist_general_kernel(const T *__restrict__ xa, int64_t na, const T *__restrict__ 
         __syncthreads();
     }
 #pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = acc[a][b] < 0x1p-100 ? 0.0 : acc[a][b];
+#pragma unroll
     for (int a = 0; a < 4; ++a) {
         int64_t i = i0 + ty + 16 * a;
         if (i >= na) continue;
@@ -163,22 +186,38 @@ dist_general_kernel(const T *__restrict__ xa, int64_t na, const T *__restrict__ 
             if (j < nb) D[i * ldd + j] = acc[a][b];
         }
     }
+    if (symmetric && blockIdx.x != blockIdx.y) {
+        // transposed copy through shared memory (the operand stages are free now): 64 x 64 doubles
+        double *tile = reinterpret_cast<double *>(&smem[0][0][0]);
+        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) tile[(tx + 16 * b) * kTile + (ty + 16 * a)] = acc[a][b];
+        __syncthreads();
+        for (int e = tid; e < kTile * kTile; e += 256) {
+            const int jj = e >> 6, ii = e & 63;            // row of the transposed tile, column
+            const int64_t j = j0 + jj, i = i0 + ii;
+            if (j < nb && i < na) D[j * ldd + i] = tile[jj * kTile + ii];
+        }
+    }
 }
 
 void launch_dist_general(const WorkSet &ws, const void *xa, int64_t na, const void *xb, int64_t nb, double *D,
                          int64_t ldd, cudaStream_t st, int *launches) {
     if (ws.pg == 0 || na == 0) return;
+    const int symmetric = (xa == xb && na == nb) ? 1 : 0;
     dim3 grid((unsigned)ceil_div(nb, kTile), (unsigned)ceil_div(na, kTile));
     if (ws.elem == 4) {
         int nchunks = (int)(ws.ldg / (kChunkBytes / 4));
         dist_general_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(xa), na,
                                                          static_cast<const float *>(xb), nb, ws.ldg, ws.rg.ptr,
-                                                         ws.ctype.ptr, nchunks, D, ldd);
+                                                         ws.ctype.ptr, nchunks, D, ldd, symmetric);
     } else {
         int nchunks = (int)(ws.ldg / (kChunkBytes / 8));
         dist_general_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double *>(xa), na,
                                                           static_cast<const double *>(xb), nb, ws.ldg, ws.rg.ptr,
-                                                          ws.ctype.ptr, nchunks, D, ldd);
+                                                          ws.ctype.ptr, nchunks, D, ldd, symmetric);
     }
     FS_CUDA(cudaGetLastError());
     ++*launches;

@@ -123,10 +123,18 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(const Tin *__restric
             if (c < ncols && rr < nrows) {
                 const Tin xv = x[perm[r0 + rr] * ldx + f];
                 int found = 0;
+                if (V <= 4) {                        // genotype-like columns: 4 compares, no loop
 #pragma unroll
-                for (int q = FS_DISTINCT_CAP - 1; q >= 0; --q) {
-                    const bool eq = as_f32 ? ((float)xv == vf[q]) : (xv == v[q]);
-                    if (q < V && eq) found = q;      // lowest matching index wins
+                    for (int q = 3; q >= 0; --q) {
+                        const bool eq = as_f32 ? ((float)xv == vf[q]) : (xv == v[q]);
+                        if (q < V && eq) found = q;  // lowest matching index wins
+                    }
+                } else {
+#pragma unroll
+                    for (int q = FS_DISTINCT_CAP - 1; q >= 0; --q) {
+                        const bool eq = as_f32 ? ((float)xv == vf[q]) : (xv == v[q]);
+                        if (q < V && eq) found = q;
+                    }
                 }
                 code = (uint8_t)found;
                 codes[(r0 + rr) * ldc + c0 + c] = code;
@@ -137,13 +145,30 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(const Tin *__restric
     }
     __syncthreads();
 
-    // ---- step 2: A[r, k0..k1): 32-bit words where the whole word belongs to this tile,
-    // single bytes at the unaligned edges (a neighbouring tile owns the rest of that word)
-    {
+    // ---- step 2: A[r, k0..k1)
+    // fast path (every column of the tile has 3 values and k0 is word-aligned, i.e. 0/1/2
+    // genotypes): 4 codes -> 12 one-hot bytes = three 32-bit words built with shifts
+    const bool v3 = __syncthreads_and((tid >= ncols) || (toff[c0 + (tid < ncols ? tid : 0) + 1] - toff[c0 + (tid < ncols ? tid : 0)] == 3)) &&
+                    (k0 & 3) == 0 && (ncols & 3) == 0;
+    if (v3) {
+        const int ngroups = ncols >> 2;                           // 4 columns per thread-iteration
+        for (int rr = tid >> 4; rr < nrows; rr += 16)
+            for (int g = tid & 15; g < ngroups; g += 16) {
+                const uint32_t cw = *reinterpret_cast<const uint32_t *>(&code_rc[rr][4 * g]);
+                // p_i = one-hot triple of code i as a 24-bit little-endian pattern
+                const uint32_t p0 = 1u << (8 * (cw & 0xffu)), p1 = 1u << (8 * ((cw >> 8) & 0xffu));
+                const uint32_t p2 = 1u << (8 * ((cw >> 16) & 0xffu)), p3 = 1u << (8 * (cw >> 24));
+                uint32_t *dst = reinterpret_cast<uint32_t *>(A + (r0 + rr) * K + k0 + 12 * g);
+                dst[0] = p0 | (p1 << 24);
+                dst[1] = (p1 >> 8) | (p2 << 16);
+                dst[2] = (p2 >> 16) | (p3 << 8);
+            }
+    } else {
+        // general path: 32-bit words where the whole word belongs to this tile, single bytes at
+        // the unaligned edges (a neighbouring tile owns the rest of that word)
         const int w0 = k0 >> 2, w1 = (k1 + 3) >> 2;               // word range covering [k0, k1)
-        const int nw = w1 - w0;
-        for (int e = tid; e < nrows * nw; e += 256) {
-            const int rr = e / nw, w = w0 + e % nw;
+        for (int rr = tid >> 5; rr < nrows; rr += 8)
+        for (int w = w0 + (tid & 31); w < w1; w += 32) {
             uint32_t word = 0;
             bool full = true;
 #pragma unroll
@@ -174,9 +199,7 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(const Tin *__restric
         for (int k = k0 + (tid >> 5); k < k1; k += 8) {
             const uint32_t cw = *reinterpret_cast<const uint32_t *>(&code_cr[kcol[k - k0]][lane4]);
             const uint32_t val = kval[k - k0];
-            uint32_t word = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) word |= (((cw >> (8 * b)) & 0xffu) == val ? 1u : 0u) << (8 * b);
+            const uint32_t word = __vcmpeq4(cw, val * 0x01010101u) & 0x01010101u;
             int8_t *dst = At + (int64_t)k * ldt + r0 + lane4;       // r0, ldt multiples of 128: aligned
             if (lane4 + 4 <= nrows) {
                 *reinterpret_cast<uint32_t *>(dst) = word;

@@ -88,10 +88,10 @@ __global__ void count_selected_kernel(const RowInfo *rinfo, int64_t R, unsigned 
     atomicAdd(out, s);
 }
 
-static int64_t chunk_rows(const fs_dataset *ds, const WorkSet &ws, int64_t ldn) {
+static int64_t chunk_rows(const fs_dataset *ds, const WorkSet &ws, int64_t ldn, int algo) {
     int64_t budget_mb = 6144;
     if (const char *e = getenv("FS_B200_CHUNK_MB")) budget_mb = std::max<int64_t>(16, atoll(e));
-    int64_t per_row = ldn * ((ws.pg > 0 ? 8 : 0) + (ws.pt > 0 ? 4 : 0) + 1 + (ws.pt > 0 ? 2 : 0));
+    int64_t per_row = ldn * ((ws.pg > 0 ? 8 : 0) + (ws.pt > 0 ? 4 : 0) + 1 + (ws.pt > 0 ? 2 : 0) + (algo == FS_RELIEFF ? 8 : 0));
     int64_t rows = budget_mb * (1LL << 20) / std::max<int64_t>(1, per_row);
     rows = std::max<int64_t>(128, rows / 128 * 128);
     (void)ds;
@@ -123,7 +123,7 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
     const WorkSet &ws = ds->ws;
 
     const int64_t ldn = round_up(n, 128);
-    const int64_t Rmax = std::min<int64_t>(chunk_rows(ds, ws, ldn), round_up((int64_t)targets.size(), 128));
+    const int64_t Rmax = std::min<int64_t>(chunk_rows(ds, ws, ldn, algo), round_up((int64_t)targets.size(), 128));
     if (ws.pg > 0) ds->Dc.reserve((size_t)Rmax * ldn);
     if (ws.pt > 0) ds->Dd.reserve((size_t)Rmax * ldn);
     ds->sel.reserve((size_t)Rmax * ldn);

@@ -37,7 +37,8 @@ template <int ALGO>
 __global__ void __launch_bounds__(256) select_threshold_kernel(const double *__restrict__ Dc,
                                                                const int32_t *__restrict__ Dd, int64_t ldn,
                                                                int64_t n, const int64_t *__restrict__ row_ids,
-                                                               const int32_t *__restrict__ y, int use_star,
+                                                               const int32_t *__restrict__ y,
+                                                               const int64_t *__restrict__ inv_perm, int use_star,
                                                                int8_t *__restrict__ sel,
                                                                int8_t *__restrict__ mask_h,
                                                                int8_t *__restrict__ mask_m,
@@ -71,15 +72,49 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(const double *__r
             s_thresh = __dsub_rn(mu, __dmul_rn(0.5, __dsqrt_rn(var)));
         }
     } else {
-        // SURF.py:146-163: distances rounded to float32, d_ii = 0 included in the sum,
-        // float32 sum (taken in float64 and rounded once), times 1/(n-1) in float64
-        double s = 0.0;
-        for (int64_t j = tid; j < n; j += 256) {
-            if (j == self) continue;
-            s += (double)(float)load_d(Dc, Dd, base + j);
+        // SURF.py:146-163: distances rounded to float32, d_ii = 0 included, np.sum in float32,
+        // times 1/(n-1) in float64.  The float32 sum is taken in the order the reference's
+        // JIT'd code uses on x86-64 (AVX2 width, observed with inspect_asm(); oracle
+        // sum_mode 2, pinned to the reference): 32 interleaved partial sums over the leading
+        // multiple of 32 folded 32->8->4->2->1, then a 4-wide loop seeded with that value,
+        // then a scalar tail.  One warp does it (the chain per lane is n/32 adds).
+        if (tid < 32) {
+            const unsigned full = 0xffffffffu;
+            // the sum runs over the samples in their ORIGINAL order (o -> internal row inv_perm[o])
+            auto d32 = [&](int64_t o) -> float {
+                const int64_t j = inv_perm[o];
+                return j == self ? 0.0f : (float)load_d(Dc, Dd, base + j);
+            };
+            float s = 0.0f;
+            int64_t done = 0;
+            if (n >= 32) {
+                const int64_t m = n & ~(int64_t)31;
+                float p = 0.0f;
+                for (int64_t t = 0; t < m; t += 32) p = __fadd_rn(p, d32(t + tid));
+                // q[l] = (p[l] + p[l+8]) + (p[l+24] + p[l+16]), l < 8
+                const float a = __fadd_rn(p, __shfl_down_sync(full, p, 8));
+                const float q = __fadd_rn(a, __shfl_down_sync(full, a, 16));
+                const float r4 = __fadd_rn(__shfl_down_sync(full, q, 4), q);      // r[l] = q[l+4] + q[l]
+                const float u2 = __fadd_rn(__shfl_down_sync(full, r4, 2), r4);    // u[l] = r[l+2] + r[l]
+                s = __fadd_rn(__shfl_down_sync(full, u2, 1), u2);                 // u[1] + u[0]
+                s = __shfl_sync(full, s, 0);
+                done = m;
+            }
+            if (n - done >= 4) {
+                const int64_t m = done + ((n - done) & ~(int64_t)3);
+                float v = tid == 0 ? s : 0.0f;
+                if (tid < 4)
+                    for (int64_t t = done; t < m; t += 4) v = __fadd_rn(v, d32(t + tid));
+                const float u = __fadd_rn(__shfl_down_sync(full, v, 2), v);       // v[2]+v[0], v[3]+v[1]
+                s = __fadd_rn(__shfl_down_sync(full, u, 1), u);                   // u1 + u0
+                s = __shfl_sync(full, s, 0);
+                done = m;
+            }
+            if (tid == 0) {
+                for (int64_t t = done; t < n; ++t) s = __fadd_rn(s, d32(t));
+                s_thresh = __dmul_rn((double)s, inv);
+            }
         }
-        s = block_sum(s, sd);
-        if (tid == 0) s_thresh = __dmul_rn((double)(float)s, inv);
     }
     __syncthreads();
     const double thresh = s_thresh;
@@ -165,7 +200,7 @@ __global__ void __launch_bounds__(256) relieff_select_kernel(
     const int64_t *__restrict__ row_ids, const int32_t *__restrict__ y, const int64_t *__restrict__ cls_start,
     int n_classes, int k, const float *__restrict__ class_probs, int8_t *__restrict__ sel,
     RowInfo *__restrict__ rinfo, int32_t *__restrict__ nbr_idx, double *__restrict__ nbr_w,
-    int32_t *__restrict__ nbr_cnt, int nbr_cap) {
+    int32_t *__restrict__ nbr_cnt, int nbr_cap, int32_t *__restrict__ tie_flag) {
     __shared__ int hist[256];
     __shared__ int warp_tot[8];
     __shared__ unsigned s_prefix;
@@ -188,6 +223,7 @@ __global__ void __launch_bounds__(256) relieff_select_kernel(
     };
 
     int slot_base = 0, n_hit = 0, n_miss = 0;
+    bool ambiguous = false;     // some class has more candidates tied at the k-th distance than slots
     for (int c = 0; c < n_classes; ++c) {
         const int64_t s0 = cls_start[c], s1 = cls_start[c + 1];
         const int64_t len = s1 - s0;
@@ -240,6 +276,7 @@ __global__ void __launch_bounds__(256) relieff_select_kernel(
                 const int rk = block_rank(eq, warp_tot, tot_eq);
                 take = valid && (key < kth || (eq && eq_taken + rk < need_eq));
                 eq_taken += tot_eq;
+                if (b0 + 256 >= s1 && eq_taken > need_eq) ambiguous = true;
             }
             int tot_take;
             const int rk2 = block_rank(take, warp_tot, tot_take);
@@ -257,6 +294,7 @@ __global__ void __launch_bounds__(256) relieff_select_kernel(
         slot_base = slot;
     }
     if (tid == 0) {
+        if (tie_flag) tie_flag[r] = ambiguous ? 1 : 0;
         nbr_cnt[r] = slot_base < nbr_cap ? slot_base : nbr_cap;
         RowInfo ri;
         ri.thresh = 0.0;
@@ -269,6 +307,117 @@ __global__ void __launch_bounds__(256) relieff_select_kernel(
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// ReliefF tie order of the reference.  When several candidates are tied at the k-th
+// distance (discrete data), which of them the reference takes is decided by the order
+// numba's np.argsort leaves them in (ReliefF.py:157; numba/misc/quicksort.py: median-of-
+// three partition with an explicit stack, insertion sort below 15 elements).  For the
+// target rows flagged by relieff_select_kernel this kernel replays that quicksort on the
+// float32 distance row in ORIGINAL sample order -- one thread per row, the algorithm is
+// sequential -- then scans the order exactly as ReliefF.py:164-175 does and rewrites the
+// row's neighbour codes and list.  Untied rows (all rows of continuous data) exit at once.
+// ---------------------------------------------------------------------------
+constexpr int kMaxTieClasses = 64;
+
+__device__ __forceinline__ void nbq_swap(int32_t *R, int64_t a, int64_t b) {
+    const int32_t t = R[a]; R[a] = R[b]; R[b] = t;
+}
+
+__device__ void numba_argsort_f32(const float *A, int32_t *R, int64_t n) {
+    if (n < 2) return;
+    int32_t stack_lo[100], stack_hi[100];
+    int sp = 1;
+    stack_lo[0] = 0; stack_hi[0] = (int32_t)(n - 1);
+    while (sp > 0) {
+        --sp;
+        int64_t low = stack_lo[sp], high = stack_hi[sp];
+        while (high - low >= 15) {
+            // partition around the median of {low, mid, high}
+            const int64_t mid = (low + high) >> 1;
+            if (A[R[mid]] < A[R[low]]) nbq_swap(R, low, mid);
+            if (A[R[high]] < A[R[mid]]) nbq_swap(R, high, mid);
+            if (A[R[mid]] < A[R[low]]) nbq_swap(R, low, mid);
+            const float pivot = A[R[mid]];
+            nbq_swap(R, high, mid);
+            int64_t i = low, j = high - 1;
+            for (;;) {
+                while (i < high && A[R[i]] < pivot) ++i;
+                while (j >= low && pivot < A[R[j]]) --j;
+                if (i >= j) break;
+                nbq_swap(R, i, j);
+                ++i; --j;
+            }
+            nbq_swap(R, i, high);
+            if (high - i > i - low) {
+                if (high > i) { stack_lo[sp] = (int32_t)(i + 1); stack_hi[sp] = (int32_t)high; ++sp; }
+                high = i - 1;
+            } else {
+                if (i > low) { stack_lo[sp] = (int32_t)low; stack_hi[sp] = (int32_t)(i - 1); ++sp; }
+                low = i + 1;
+            }
+        }
+        // insertion sort of [low, high]
+        for (int64_t i = low + 1; i <= high; ++i) {
+            const int32_t kk = R[i];
+            const float v = A[kk];
+            int64_t j = i;
+            while (j > low && v < A[R[j - 1]]) { R[j] = R[j - 1]; --j; }
+            R[j] = kk;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32) relieff_ties_kernel(
+    const double *__restrict__ Dc, const int32_t *__restrict__ Dd, int64_t ldn, int64_t n,
+    const int64_t *__restrict__ row_ids, const int32_t *__restrict__ y, const int64_t *__restrict__ inv_perm,
+    int n_classes, int k, const float *__restrict__ class_probs, const int32_t *__restrict__ tie_flag,
+    float *__restrict__ keys, int32_t *__restrict__ order, int8_t *__restrict__ sel,
+    int32_t *__restrict__ nbr_idx, double *__restrict__ nbr_w, int32_t *__restrict__ nbr_cnt, int nbr_cap,
+    int64_t R) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R || !tie_flag[r]) return;
+    const int64_t self = row_ids[r];
+    const int64_t base = r * ldn;
+    float *A = keys + r * n;
+    int32_t *ord = order + r * n;
+    for (int64_t o = 0; o < n; ++o) {
+        const int64_t j = inv_perm[o];
+        A[o] = j == self ? __int_as_float(0x7f800000) : (float)load_d(Dc, Dd, base + j);   // ReliefF.py:146-155
+        ord[o] = (int32_t)o;
+    }
+    numba_argsort_f32(A, ord, n);
+    const int ci = y[self];
+    double denom = 1.0 - (double)class_probs[ci];
+    if (denom == 0.0) denom = 1.0;
+    int found[kMaxTieClasses];
+    for (int c = 0; c < n_classes; ++c) found[c] = 0;
+    for (int64_t j = 0; j < n; ++j) sel[base + j] = FS_MASK_NONE;
+    // ReliefF.py:164-175 (the scan never ends early in the reference: the target's own class
+    // cannot reach k misses; stopping once every class is served selects the same samples)
+    int slot = 0, filled = 0;
+    const int64_t own_len = 0;
+    (void)own_len;
+    for (int64_t q = 0; q < n && filled < n_classes; ++q) {
+        const int64_t j = inv_perm[ord[q]];
+        const int c = y[j];
+        if (found[c] >= k) continue;
+        if (++found[c] == k) ++filled;
+        sel[base + j] = c == ci ? FS_MASK_NEAR_HIT : FS_MASK_NEAR_MISS;
+        if (slot < nbr_cap) {
+            nbr_idx[r * nbr_cap + slot] = (int32_t)j;
+            nbr_w[r * nbr_cap + slot] = c == ci ? -1.0 : ((double)class_probs[c] / denom) / (double)k;
+        }
+        ++slot;
+    }
+    // hits are normalised by the number found (ReliefF.py:211-212)
+    const double wh = found[ci] > 0 ? -1.0 / (double)found[ci] : 0.0;
+    const int m = slot < nbr_cap ? slot : nbr_cap;
+    for (int e = 0; e < m; ++e)
+        if (nbr_w[r * nbr_cap + e] == -1.0) nbr_w[r * nbr_cap + e] = wh;
+    nbr_cnt[r] = m;
+}
+
 void launch_select(fs_dataset *ds, int algo, int use_star, int32_t k, const int64_t *row_ids, int64_t R,
                    const double *Dc, const int32_t *Dd, int64_t ldn, int8_t *sel, int8_t *mask_h, int8_t *mask_m,
                    RowInfo *rinfo, int32_t *nbr_idx, double *nbr_w, int32_t *nbr_cnt, int32_t nbr_cap, const float *class_probs,
@@ -277,14 +426,29 @@ void launch_select(fs_dataset *ds, int algo, int use_star, int32_t k, const int6
     dim3 grid((unsigned)R);
     if (algo == FS_MULTISURF)
         select_threshold_kernel<FS_MULTISURF><<<grid, 256, 0, st>>>(Dc, Dd, ldn, ds->n, row_ids, ds->d_y.ptr,
-                                                                    use_star, sel, mask_h, mask_m, rinfo);
+                                                                    ds->d_inv_perm.ptr, use_star, sel, mask_h, mask_m,
+                                                                    rinfo);
     else if (algo == FS_SURF)
-        select_threshold_kernel<FS_SURF><<<grid, 256, 0, st>>>(Dc, Dd, ldn, ds->n, row_ids, ds->d_y.ptr, use_star,
-                                                               sel, mask_h, mask_m, rinfo);
-    else
+        select_threshold_kernel<FS_SURF><<<grid, 256, 0, st>>>(Dc, Dd, ldn, ds->n, row_ids, ds->d_y.ptr,
+                                                               ds->d_inv_perm.ptr, use_star, sel, mask_h, mask_m, rinfo);
+    else {
+        // reference tie order unless FS_B200_RELIEFF_TIES=index (ties then go by sample index)
+        const char *env = getenv("FS_B200_RELIEFF_TIES");
+        const bool emulate = !(env && env[0] == 'i') && ds->n_classes <= kMaxTieClasses;
+        if (emulate) ds->tie_flag.reserve(R);
         relieff_select_kernel<<<grid, 256, 0, st>>>(Dc, Dd, ldn, ds->n, row_ids, ds->d_y.ptr, ds->d_cls_start.ptr,
                                                     ds->n_classes, k, class_probs, sel, rinfo, nbr_idx, nbr_w,
-                                                    nbr_cnt, nbr_cap);
+                                                    nbr_cnt, nbr_cap, emulate ? ds->tie_flag.ptr : nullptr);
+        if (emulate) {
+            FS_CUDA(cudaGetLastError());
+            ++*launches;
+            ds->tie_keys.reserve((size_t)R * ds->n);
+            ds->tie_order.reserve((size_t)R * ds->n);
+            relieff_ties_kernel<<<(unsigned)ceil_div(R, 32), 32, 0, st>>>(
+                Dc, Dd, ldn, ds->n, row_ids, ds->d_y.ptr, ds->d_inv_perm.ptr, ds->n_classes, k, class_probs,
+                ds->tie_flag.ptr, ds->tie_keys.ptr, ds->tie_order.ptr, sel, nbr_idx, nbr_w, nbr_cnt, nbr_cap, R);
+        }
+    }
     FS_CUDA(cudaGetLastError());
     ++*launches;
 }

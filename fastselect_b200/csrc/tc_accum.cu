@@ -13,7 +13,7 @@
 // rsH_i / rsM_i being the row sums of the masks.  All counts are exact integers; the
 // per-target scaling and the reduction over targets are done in float64.
 //
-// Kernel: a CTA owns 128 one-hot rows (UMMA M = TMEM lanes) and a group of up to 4
+// Kernel: a CTA owns 128 one-hot rows (UMMA M = TMEM lanes) and a group of up to 8
 // tiles of 256 target rows (UMMA N).  Each tile is processed as two work items, "hit"
 // and "miss", one mask and one 256-column TMEM accumulator each (double-buffered, so the
 // epilogue of one item overlaps the MMAs of the next).  Warp 0: TMA producer (At tile +
@@ -39,7 +39,7 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK;                  // 16 KB
 constexpr int B_BYTES = BN * BK;                  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 48 KB
-constexpr int GROUP = 4;                          // target tiles per CTA
+constexpr int GROUP = 8;                          // target tiles per CTA
 constexpr int CONST_BYTES = 2 * BN * 16;          // [2][BN] x {double c; int rs; int pad}
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 512 + CONST_BYTES;
 constexpr int THREADS = 320;              // TMA warp, MMA warp, 8 epilogue warps

@@ -79,6 +79,9 @@ DATA = {
     "mixed3": lambda: mixed(5, 72, 36, 3),
     "mixed2_mid": lambda: mixed(6, 300, 200, 2),
     "geno2_mid": lambda: genotype(7, 256, 384, 2),
+    # SURF's float32 mean distance is summation-order sensitive here (2 neighbour pairs flip
+    # between a sequential / correctly-rounded sum and the order the reference really uses)
+    "gauss2_long": lambda: gaussian(2, 1500, 4, 2),
 }
 
 CASES = []
@@ -95,6 +98,10 @@ for d in ("geno2", "geno3", "gauss2", "gauss3", "mixed3", "mixed2_mid", "geno2_m
         CASES.append((d, "SURF", dict(use_star=star)))
     for k in (1, 5, 10):
         CASES.append((d, "ReliefF", dict(n_neighbors=k)))
+for star in (False, True):
+    CASES.append(("gauss2_long", "SURF", dict(use_star=star)))
+    CASES.append(("gauss2_long", "MultiSURF", dict(use_star=star)))
+CASES.append(("gauss2_long", "ReliefF", dict(n_neighbors=10)))
 CASES.append(("gauss2", "MultiSURF", dict(discrete_limit=100)))   # n <= limit: every column discrete
 CASES.append(("mixed3", "SURF", dict(discrete_limit=2, use_star=True)))
 

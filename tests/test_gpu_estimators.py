@@ -14,14 +14,6 @@ pytestmark = pytest.mark.gpu
 CLS = {"MultiSURF": fsb.MultiSURF, "SURF": fsb.SURF, "ReliefF": fsb.ReliefF}
 
 
-def _tied_relieff(m):
-    """ReliefF on data with distance ties depends on numba's quicksort order (oracle
-    tie_mode 0); the GPU path breaks ties by sample index.  Those cases are compared
-    with the oracle under the same tie rule instead of with the reference vector."""
-    return m["algo"] == "ReliefF" and (m["data"].startswith("geno") or m["data"] in ("A", "B")
-                                       or m["data"].startswith("mixed"))
-
-
 def test_estimators_match_reference_vectors(native, golden):
     arrays, meta = golden
     checked = 0
@@ -34,9 +26,6 @@ def test_estimators_match_reference_vectors(native, golden):
         assert est.effective_backend_ == "gpu"
         assert np.array_equal(est.is_discrete_, arrays[f"isd_{m['idx']}"]), m
         assert est.feature_importances_.dtype == np.float32
-        if _tied_relieff(m):
-            P = m["params"]
-            ref = R.fit_relieff(x, y, P.get("discrete_limit", 10), P["n_neighbors"], tie_mode=1)[0]
         scale = max(1.0, float(np.abs(ref).max()))
         np.testing.assert_allclose(est.feature_importances_, ref, rtol=1e-5, atol=2e-6 * scale, err_msg=str(m))
         top = np.argsort(ref)[::-1][:len(est.top_features_)]
@@ -67,8 +56,6 @@ def test_turf_matches_reference(native, golden):
         if not m["algo"].startswith("TuRF"):
             continue
         base = m["algo"].split(":")[1]
-        if base == "ReliefF" and not m["data"].startswith("gauss"):
-            continue
         x, y = arrays[f"X_{m['data']}"], arrays[f"y_{m['data']}"]
         t = fsb.TuRF(CLS[base](n_features_to_select=5, backend="gpu", **m["params"]),
                      n_features_to_select=m["turf"]["n"], pct_remove=m["turf"]["pct"]).fit(x, y)
@@ -142,7 +129,7 @@ def test_behavioural_contract(native, capsys):
     yw = (np.arange(60) % 2).astype(np.int64)
     est = fsb.SURF(discrete_limit=25, backend="gpu", n_features_to_select=2).fit(xw, yw)
     assert est.is_discrete_.all()
-    want = R.fit_surf(xw, yw, 25, False, 1)[0]
+    want = R.fit_surf(xw, yw, 25, False, 2)[0]
     np.testing.assert_allclose(est.feature_importances_, want, rtol=1e-5, atol=1e-7)
     # fitted estimators pickle and refit identically
     m2 = pickle.loads(pickle.dumps(m))
@@ -163,3 +150,25 @@ def test_sklearn_estimator_checks_turf(native):
     from sklearn.utils.estimator_checks import check_estimator
 
     check_estimator(fsb.TuRF(fsb.MultiSURF()))
+
+
+def test_turf_on_genotypes_matches_oracle_driven_turf(native):
+    """Config C5 geometry at reduced size: TuRF(MultiSURF, pct 0.1) on int8 genotypes with the
+    data set resident on the GPU, against the same pruning loop driven by the CPU oracle."""
+    from datasets import epistatic_genotypes
+
+    x, y = epistatic_genotypes(44, 300, 600)
+    t = fsb.TuRF(fsb.MultiSURF(backend="gpu"), n_features_to_select=10, pct_remove=0.1).fit(x, y)
+
+    xf = x.astype(np.float32)
+    active = np.arange(600)
+    scores = R.fit_multisurf(xf, y)[0]
+    first = scores.copy()
+    while len(active) > 10:
+        k = max(1, int(len(active) * 0.1))
+        if len(active) - k < 10:
+            k = len(active) - 10
+        active = np.delete(active, np.argsort(scores)[:k])
+        scores = R.fit_multisurf(xf[:, active], y)[0]
+    np.testing.assert_allclose(t.feature_importances_, first, rtol=1e-5, atol=2e-6 * np.abs(first).max())
+    assert np.array_equal(t.top_features_, np.sort(active))

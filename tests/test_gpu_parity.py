@@ -86,7 +86,7 @@ def test_surf_rows_match_oracle(native, name, star):
     with ds:
         tg = np.arange(n)
         got = ds.debug_rows(native.FS_SURF, tg, use_star=star)
-        want = R.surf_targets(*args, star, tg, sum_mode=1)
+        want = R.surf_targets(*args, star, tg, sum_mode=2)
         assert np.array_equal(got["dist"], want["dist"])          # float32-rounded distances
         np.testing.assert_allclose(got["thresh"], want["thresh"], rtol=1e-15)
         assert np.array_equal(got["mask"], want["mask"])
@@ -97,22 +97,45 @@ def test_surf_rows_match_oracle(native, name, star):
 
 @pytest.mark.parametrize("name", ["geno2", "geno3", "gauss2", "gauss4", "mixed3", "mixed2", "one_feature"])
 @pytest.mark.parametrize("k", [1, 5, 30])
-def test_relieff_rows_match_oracle(native, name, k):
+@pytest.mark.parametrize("ties", ["reference", "index"])
+def test_relieff_rows_match_oracle(native, monkeypatch, name, k, ties):
+    """ties='reference': candidates tied at the k-th distance are taken in the order numba's
+    quicksort leaves them (what the reference does; oracle tie_mode 0).  ties='index':
+    FS_B200_RELIEFF_TIES=index takes them by sample index (oracle tie_mode 1)."""
     x, y = DATA[name]()
     n = x.shape[0]
     if k >= n:
         pytest.skip("k >= n")
+    if ties == "index":
+        monkeypatch.setenv("FS_B200_RELIEFF_TIES", "index")
+    else:
+        monkeypatch.delenv("FS_B200_RELIEFF_TIES", raising=False)
     ds, args = open_relieff(native, x, y)
     x32, y_enc, recip, isd, cp = args
     with ds:
         tg = np.arange(n)
         got = ds.debug_rows(native.FS_RELIEFF, tg, k=k, class_probs=cp)
-        want = R.relieff_targets(x32, y_enc, recip, isd, k, cp, tg, tie_mode=1)
+        want = R.relieff_targets(x32, y_enc, recip, isd, k, cp, tg, tie_mode=0 if ties == "reference" else 1)
         assert np.array_equal(got["dist"], want["dist"])
-        assert np.array_equal(got["mask"], want["mask"])          # identical neighbour sets (index tie rule)
+        assert np.array_equal(got["mask"], want["mask"])          # identical neighbour sets
         np.testing.assert_allclose(got["wsum"], want["wsum"], rtol=RTOL, atol=atol_for(want["wsum"]) * n)
         full = ds.score(native.FS_RELIEFF, k=k, class_probs=cp)
         np.testing.assert_allclose(full, want["wsum"], rtol=RTOL, atol=atol_for(want["wsum"]) * n)
+
+
+def test_surf_mean_uses_the_reference_summation_order(native, golden):
+    """gauss2_long: the float32 row sum decides two neighbour pairs; only the order the
+    reference's compiled code uses (oracle sum_mode 2) reproduces the reference scores."""
+    arrays, meta = golden
+    x, y = arrays["X_gauss2_long"], arrays["y_gauss2_long"]
+    ds, args = open_surf(native, x, y)
+    with ds:
+        got = ds.debug_rows(native.FS_SURF, np.arange(x.shape[0]))
+    want = R.surf_targets(*args, False, np.arange(x.shape[0]), sum_mode=2)
+    other = R.surf_targets(*args, False, np.arange(x.shape[0]), sum_mode=1)
+    assert np.array_equal(got["thresh"], want["thresh"])
+    assert np.array_equal(got["mask"], want["mask"])
+    assert not np.array_equal(want["mask"], other["mask"])      # the case is discriminating
 
 
 def test_relieff_without_ties_matches_the_reference_order(native):

@@ -42,6 +42,16 @@ def test_oracle_matches_reference_vectors(golden, algo):
             assert gaps.min() < TOL * scale, m
 
 
+def test_surf_sum_order_is_pinned_by_a_discriminating_case(golden):
+    """On gauss2_long only the reference's real summation order (sum_mode 2) gives the
+    reference's scores; the sequential and the correctly-rounded sums flip neighbour pairs."""
+    arrays, meta = golden
+    m = next(m for m in meta if m["data"] == "gauss2_long" and m["algo"] == "SURF" and not m["params"]["use_star"])
+    x, y, ref = arrays["X_gauss2_long"], arrays["y_gauss2_long"], arrays[f"scores_{m['idx']}"]
+    err = {sm: float(np.abs(R.fit_surf(x, y, 10, False, sm)[0] - ref).max()) for sm in (0, 1, 2)}
+    assert err[2] == 0.0 and err[0] > 1e-5 and err[1] > 1e-5, err
+
+
 def test_known_answer_vectors_of_the_survey(golden):
     """vectors captured from the reference CPU path on the
     reference's own test fixtures (tests/test_multisurf.py:19-33, tests/test_surf.py:22-32)."""
