@@ -186,6 +186,17 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def load_traffic(workload):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel from the
+    committed `ncu --set full` capture of this workload (profiles/traffic.json), keyed by phase."""
+    if workload is None:
+        return {}
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload, {})
+    except Exception:
+        return {}
+
+
 # --------------------------------------------------------------------------- #
 # own arm
 # --------------------------------------------------------------------------- #
@@ -298,22 +309,37 @@ def own_arm(args):
     rows = hi - lo
     u_rank = float(rows) * n * p
     top = max(("ms_dist_tensor", "ms_dist_general", "ms_accum_tensor", "ms_accum_general"), key=lambda q: phases[q])
+    bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    int8_peak = 2.0 * bf16
+    traffic = load_traffic(args.workload if world == 1 else None)
+    kernels = {}
+    for ph, key in (("ms_dist_tensor", "ops_dist_tensor"), ("ms_accum_tensor", "ops_accum_tensor")):
+        if phases[ph] > 0:
+            # int8 operations actually issued to the tensor pipe (fs_stats), not the 6/u of SURVEY 8d:
+            # the reduced one-hot operands need 2 MAC per (pair, 3-valued feature) and symmetric tiles half of that
+            ex = agg.get(key, 0.0) / steps / (phases[ph] / 1e3) / 1e12
+            kernels[ph] = {"bound": "tensor", "achieved": ex, "peak": int8_peak, "unit": "TOP/s int8",
+                           "frac": ex / int8_peak, "survey_algorithmic_rate": 6.0 * u_rank / (phases[ph] / 1e3) / 1e12,
+                           "traffic": traffic.get(ph)}
+    if phases["ms_gather"] > 0 and agg.get("onehot_k", 0) > 0:
+        kk = agg["onehot_k"] / steps
+        pt = agg["n_tensor_cols"] / steps
+        # encode: raw columns read once; U, Wd, At (3 x n x K) and codesT (n x pt) written once
+        byts = n * pt * w["x"].itemsize + 3.0 * n * kk + n * pt
+        gbs = byts / (phases["ms_gather"] / 1e3) / 1e9
+        kernels["ms_gather"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                "traffic": traffic.get("ms_gather")}
     if top.endswith("tensor"):
-        # 3 MAC = 6 int-ops per (pair, feature) for either one-hot contraction
-        achieved = 6.0 * u_rank / (phases[top] / 1e3) / 1e12
-        bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak = 2.0 * bf16
-        roof = {"bound": "tensor", "kernel": top, "achieved": achieved, "peak": peak, "unit": "TOP/s int8",
-                "frac": achieved / peak, "traffic": None,
-                "peak_source": ("2 x measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "2 x fallback 1.4 PF")}
+        roof = dict(kernels[top], kernel=top,
+                    peak_source=("2 x measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "2 x fallback 1.4 PF"))
     else:
         # CUDA-core kernels re-use every loaded element >= 64 times: algorithmic bytes are one
         # read of both operand slabs plus the D slab write
         byts = (rows + n) * p * 4.0 + rows * n * 8.0
         achieved = byts / (phases[top] / 1e3) / 1e9
-        peak = peaks.get("hbm_gbs", 6650.0)
-        roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+        roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                "frac": achieved / hbm, "traffic": traffic.get(top),
                 "peak_source": "measured copy (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
                 "note": "issue-bound CUDA-core kernel; HBM fraction is low by construction"}
 
@@ -330,7 +356,7 @@ def own_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "seconds_per_fit": dt / e2e_steps, "matches_resident_run": same},
             "gpu_launches": int(agg.get("launches", 0)),
-            "roofline": roof, "phases_ms": phases, "cpu_baseline": cpu,
+            "roofline": roof, "kernels": kernels, "phases_ms": phases, "cpu_baseline": cpu,
             "top_features": fitted.top_features_.tolist(),
             "stats": {k_: int(agg[k_] / steps) for k_ in ("n_tensor_cols", "n_general_cols", "onehot_k",
                                                            "pairs_selected", "n_chunks") if k_ in agg}}

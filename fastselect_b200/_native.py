@@ -14,6 +14,7 @@ FS_RELIEFF, FS_SURF, FS_MULTISURF = 0, 1, 2
 FS_U8, FS_I8, FS_F32, FS_F64 = 0, 1, 2, 3
 FS_ARITH_F32, FS_ARITH_F64 = 0, 1
 FS_DISTINCT_CAP = 16
+FS_ABI_VERSION = 2
 
 _DTYPES = {np.dtype(np.uint8): FS_U8, np.dtype(np.int8): FS_I8,
            np.dtype(np.float32): FS_F32, np.dtype(np.float64): FS_F64}
@@ -27,7 +28,8 @@ class FsStats(C.Structure):
                 ("ms_dist_general", C.c_float), ("ms_select", C.c_float), ("ms_accum_tensor", C.c_float),
                 ("ms_accum_general", C.c_float), ("ms_reduce", C.c_float), ("launches", C.c_int32),
                 ("n_chunks", C.c_int32), ("n_tensor_cols", C.c_int64), ("n_general_cols", C.c_int64),
-                ("onehot_k", C.c_int64), ("pairs_selected", C.c_int64)]
+                ("onehot_k", C.c_int64), ("pairs_selected", C.c_int64),
+                ("ops_dist_tensor", C.c_double), ("ops_accum_tensor", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -58,6 +60,9 @@ def load():
     lib.fs_dataset_row_order.argtypes = [vp, vp]
     lib.fs_score.argtypes = [vp, C.c_int, C.c_int, i32, vp, vp, i64, i64, i64, vp, C.c_int, C.POINTER(FsStats)]
     lib.fs_debug_rows.argtypes = [vp, C.c_int, C.c_int, i32, vp, vp, i64, vp, i64, vp, vp, vp, vp]
+    if lib.fs_abi_version() != FS_ABI_VERSION:
+        raise RuntimeError(f"fastselect_b200: {LIB_PATH} has ABI version {lib.fs_abi_version()}, "
+                           f"this package needs {FS_ABI_VERSION}; rebuild it (make -C fastselect_b200/csrc)")
     _lib = lib
     return lib
 

@@ -108,17 +108,23 @@ struct WorkSet {
     DevBuf<int64_t> gout;  // [pg] position in the caller's feat_idx list
     std::vector<int64_t> h_gcol, h_gout;
     int64_t n_cont = 0, n_cmp = 0;
-    // one-hot tensor-core path (filled by onehot.cu)
-    int64_t pt = 0;                 // active tensor-path columns
-    int64_t K = 0;                  // sum of V_f, padded to 128
+    // one-hot tensor-core path (filled by onehot.cu).  A column with V distinct values owns
+    // V - 1 "reduced" one-hot rows (values 0..V-2); the last value is implied (see onehot.cu)
+    int64_t pt = 0;                 // active tensor-path columns (V >= 2)
+    int64_t K = 0;                  // K_used padded to 128
+    int64_t K_used = 0;             // sum of (V_f - 1): reduced one-hot rows in use
     std::vector<int64_t> h_tcol, h_tout, h_toff;
     DevBuf<int64_t> tcol, tout;     // [pt]
-    DevBuf<int32_t> toff;           // [pt+1] first one-hot row of each column
-    DevBuf<int8_t> A;               // [n, K]    sample-major one-hot (K = one-hot row, contiguous)
-    DevBuf<int8_t> At;              // [K, ldt]  feature-major one-hot (sample index contiguous)
-    DevBuf<uint8_t> codes;          // [n, ldc]  value codes of the tensor columns (ReliefF gather)
+    DevBuf<int32_t> toff;           // [pt+1] first reduced one-hot row of each column
+    DevBuf<int8_t> U;               // [n, K]    sample-major, U[i,(f,v)] = [code == v]            (target side of the distance GEMM)
+    DevBuf<int8_t> Wd;              // [n, K]    sample-major, U + [code != last]                 (sample side of the distance GEMM)
+    DevBuf<int8_t> At;              // [K, ldt]  feature-major reduced one-hot (sample index contiguous)
+    DevBuf<uint8_t> codesT;         // [pt, ldt] feature-major value codes (accumulation epilogue)
+    DevBuf<uint8_t> codes;          // [n, ldc]  sample-major value codes (ReliefF gather only)
+    DevBuf<int32_t> srow;           // [n] number of tensor columns whose code is not the last one
+    DevBuf<uint32_t> krow;          // [K] per reduced row: column | value << 24 | last << 28
     int64_t ldt = 0, ldc = 0;
-    int64_t K_used = 0;             // sum of V_f (one-hot rows in use); K is K_used padded to 128
+    bool have_codes = false;
     // cache key
     std::vector<int64_t> key;
     bool valid = false;
@@ -178,7 +184,8 @@ struct fs_dataset {
 namespace fs {
 
 // dataset.cu
-void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool allow_tensor, int *launches);
+void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool allow_tensor, bool need_codes,
+                   int *launches);
 
 // dist_general.cu: D[r, j] = sum over general columns of the per-feature term
 // between target row r (rows of xa) and sample j (rows of xb).

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128) column_scan_kernel(const T *__restrict__ 
                                                           double *__restrict__ vals) {
     int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= p) return;
-    T set[FS_DISTINCT_CAP];
+    T set[FS_DISTINCT_CAP] = {};
     int c = 0;
     bool over = false;
     T mn = x[f], mx = x[f];
@@ -72,6 +72,18 @@ __global__ void __launch_bounds__(128) column_scan_kernel(const T *__restrict__ 
                     over = true;
                 }
             }
+        }
+    }
+    // ascending value order (odd-even transposition on registers): for 0/1/2 genotypes the
+    // value code is then the value itself, which the one-hot encoder exploits
+#pragma unroll
+    for (int pass = 0; pass < FS_DISTINCT_CAP; ++pass) {
+#pragma unroll
+        for (int q = pass & 1; q + 1 < FS_DISTINCT_CAP; q += 2) {
+            const bool sw = (q + 1 < c) && (set[q + 1] < set[q]);
+            const T lo = sw ? set[q + 1] : set[q], hi = sw ? set[q] : set[q + 1];
+            set[q] = lo;
+            set[q + 1] = hi;
         }
     }
     cmin[f] = (double)mn;
@@ -228,20 +240,21 @@ static void run_gather(fs_dataset *ds, WorkSet &ws, int *launches) {
 
 void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches);  // onehot.cu
 
-void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool allow_tensor, int *launches) {
+void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool allow_tensor, bool need_codes,
+                   int *launches) {
     WorkSet &ws = ds->ws;
     std::vector<int64_t> key(n_kept + 2);
     key[0] = allow_tensor ? 1 : 0;
     key[1] = ds->arith;
     for (int64_t c = 0; c < n_kept; ++c) key[c + 2] = feat_idx ? feat_idx[c] : c;
-    if (ws.valid && ws.key == key) return;
+    if (ws.valid && ws.key == key && (ws.have_codes || !need_codes || ws.pt == 0)) return;
     ws.valid = false;
     const int chunk = kChunkBytes / (ds->arith == FS_ARITH_F64 ? 8 : 4);
     ws.elem = ds->arith == FS_ARITH_F64 ? 8 : 4;
 
     // split the active columns: one-hot tensor path (discrete, V <= FS_DISTINCT_CAP),
     // continuous, and wide discrete ("compare") columns
-    std::vector<int64_t> cont_col, cont_out, cmp_col, cmp_out;
+    std::vector<int64_t> cont_col, cont_out, cmp_col, cmp_out, const_col, const_out;
     ws.h_tcol.clear();
     ws.h_tout.clear();
     for (int64_t c = 0; c < n_kept; ++c) {
@@ -249,7 +262,12 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
         FS_REQUIRE(f >= 0 && f < ds->p, FS_ERR_INVALID, "feat_idx[%lld]=%lld outside [0,%lld)", (long long)c,
                    (long long)f, (long long)ds->p);
         if (ds->is_discrete[f]) {
-            if (allow_tensor && ds->cnt[f] <= FS_DISTINCT_CAP) {
+            if (ds->cnt[f] == 1) {
+                // a constant column: every per-feature term is 0 (MultiSURF.py:184-185), so it
+                // adds nothing to any distance and its weight stays 0 -- it takes no part
+                const_col.push_back(f);
+                const_out.push_back(c);
+            } else if (allow_tensor && ds->cnt[f] <= FS_DISTINCT_CAP) {
                 ws.h_tcol.push_back(f);
                 ws.h_tout.push_back(c);
             } else {
@@ -260,6 +278,12 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
             cont_col.push_back(f);
             cont_out.push_back(c);
         }
+    }
+    if (ws.h_tcol.empty() && cont_col.empty() && cmp_col.empty()) {
+        // nothing but constant columns: keep one on the compare path so the pipeline has a
+        // (zero) distance matrix to select on
+        cmp_col.push_back(const_col[0]);
+        cmp_out.push_back(const_out[0]);
     }
     ws.pt = (int64_t)ws.h_tcol.size();
     ws.n_cont = (int64_t)cont_col.size();
@@ -308,6 +332,7 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
         FS_CUDA(cudaStreamSynchronize(ds->stream));
     }
     ws.K = 0;
+    ws.have_codes = need_codes;
     if (ws.pt > 0) build_onehot(ds, ws, launches);
     ws.key = std::move(key);
     ws.valid = true;

@@ -1,14 +1,15 @@
 // onehot.cu -- one-hot tensor-core path: encoding of the active discrete columns, TMA
 // tensor maps, and the host side of the tcgen05 distance / accumulation kernels.
 //
-// K0 "encode" of the design: every active discrete column f with V_f <= FS_DISTINCT_CAP
-// distinct values becomes V_f one-hot int8 rows/columns (one per value; only equality
-// matters, MultiSURF.py:184-185, so any injective value coding is exact):
-//   A  [n, K]   sample-major (one-hot index contiguous)  -> operands of the distance GEMM
-//   At [K, ldt] feature-major (sample index contiguous)   -> A operand of the accumulation GEMM
-//   codes [n, ldc] the value index itself (ReliefF's sparse neighbour gather)
+// K0 "encode" of the design: every active discrete column f with 2 <= V_f <= FS_DISTINCT_CAP
+// distinct values becomes V_f - 1 reduced one-hot int8 rows/columns (only equality matters,
+// MultiSURF.py:184-185, so any injective value coding is exact):
+//   U, Wd [n, K]   sample-major (one-hot index contiguous)  -> the two operands of the distance GEMM
+//   At    [K, ldt] feature-major (sample index contiguous)   -> M operand of the accumulation GEMM
+//   codesT [pt, ldt] feature-major value codes               -> accumulation epilogue
+//   codes  [n, ldc]  sample-major value codes                -> ReliefF's sparse neighbour gather (only then)
 // Samples are in the data set's class-sorted internal order.  HBM-bound streaming kernel:
-// reads n*pt elements once, writes n*K*2 + n*pt bytes.
+// reads n*pt elements once, writes 3*n*K + n*pt bytes.
 #include <algorithm>
 
 #include <cuda.h>
@@ -18,13 +19,15 @@
 
 namespace fs {
 
-void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_t K, int32_t p_disc, int64_t R,
-                    int64_t n, int32_t *Dd, int64_t ldd, cudaStream_t st, int *launches);
+void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_t K, const int32_t *srow,
+                    const int64_t *d_ids, int64_t R, int64_t n, int32_t *Dd, int64_t ldd, bool symmetric,
+                    cudaStream_t st, int *launches, double *ops);
 int tc_accum_groups(int64_t R);
 void launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
                      int64_t R, const int64_t *d_ids, bool contiguous, const int32_t *d_y,
-                     const int64_t *d_cls_start, const RowInfo *rinfo, const int8_t *At, int64_t ldt, int64_t K_rows,
-                     double *tpartial, cudaStream_t st, int *launches);
+                     const int64_t *d_cls_start, const RowInfo *rinfo, const uint8_t *codesT, int64_t ldt,
+                     const uint32_t *krow, int64_t K_rows, double *tpartial, cudaStream_t st, int *launches,
+                     const int64_t *h_ids, const int32_t *h_y, const int64_t *h_cls_start, double *ops);
 
 bool tensor_path_available() { return true; }
 
@@ -65,38 +68,65 @@ CUtensorMap make_tmap_u8_sw128(const void *base, uint64_t row_bytes, uint64_t ro
 // ---------------------------------------------------------------------------
 // encode
 // ---------------------------------------------------------------------------
-// Tile: 128 samples x 64 columns per CTA.  Step 1 reads x coalesced along the column
-// index and keeps the value codes in shared memory (both orientations); step 2 emits the
-// A rows (one-hot index contiguous) and step 3 the At rows (sample index contiguous) as
-// packed 32-bit stores -- every byte of the tile's A / At footprint is written exactly
-// once, so no memset of the operands is needed.
+// Reduced one-hot operands.  A column with V distinct values (codes 0..V-1) owns V - 1
+// rows, one per code v < V - 1; the last code is implied because every sample carries
+// exactly one code:
+//   matches_f(i, j) = sum_v [c_i = v][c_j = v]
+//                   = 1 - [c_i != last] - [c_j != last] + sum_{v < last} [c_i = v] ([c_j = v] + [c_j != last]),
+// so with U[i,(f,v)] = [c_i = v], Wd[j,(f,v)] = [c_j = v] + [c_j != last] and
+// s_i = #{f : c_if != last_f}:   d_ij = sum_f (1 - matches_f) = s_i + s_j - (U Wd^T)_ij   -- exact integers,
+// with a contraction length of sum_f (V_f - 1) instead of sum_f V_f (2/3 of the MMA work for
+// 0/1/2 genotypes).  The accumulation GEMM contracts the same reduced rows (At) and its
+// epilogue recovers the implied plane from G_last = rowsum - sum_{v<last} G_v (tc_accum.cu).
+//
+// Tile: 128 samples x 64 columns per CTA.  Step 1 reads x and keeps the value codes in
+// shared memory in both orientations; step 2 emits the U / Wd rows (one-hot index
+// contiguous) and the per-sample counts s; step 3 the At and codesT rows (sample index
+// contiguous).  All global stores are 16-byte vectors on the 0/1/2 fast path, and every
+// byte of the tile's footprint is written exactly once (no memset of the operands).
 constexpr int ENC_ROWS = 128;
 constexpr int ENC_COLS = 64;
+constexpr int ENC_CR_LD = ENC_ROWS + 4;                       // conflict-free transposed stores
+constexpr int ENC_KMAX = ENC_COLS * (FS_DISTINCT_CAP - 1);
+
+// 4 genotype codes (one per byte, each 0/1/2) -> 8 bytes of U, 8 bytes of Wd, count of codes != 2
+__device__ __forceinline__ void expand_v3(uint32_t cw, uint32_t &u0, uint32_t &u1, uint32_t &w0, uint32_t &w1, int &cnt) {
+    const uint32_t p0 = (1u << (8 * (cw & 0xffu))) & 0xffffu, p1 = (1u << (8 * ((cw >> 8) & 0xffu))) & 0xffffu;
+    const uint32_t p2 = (1u << (8 * ((cw >> 16) & 0xffu))) & 0xffffu, p3 = (1u << (8 * (cw >> 24))) & 0xffffu;
+    const uint32_t ne = __vcmpne4(cw, 0x02020202u) & 0x01010101u;      // byte i = [code_i != last]
+    cnt += __popc(ne);
+    u0 = p0 | (p1 << 16);
+    u1 = p2 | (p3 << 16);
+    w0 = u0 + (ne & 1u) * 0x0101u + ((ne >> 8) & 1u) * 0x01010000u;
+    w1 = u1 + ((ne >> 16) & 1u) * 0x0101u + (ne >> 24) * 0x01010000u;
+}
 
 template <typename Tin>
-__global__ void __launch_bounds__(256) onehot_encode_kernel(const Tin *__restrict__ x, int64_t ldx,
-                                                            const int64_t *__restrict__ perm,
-                                                            const int64_t *__restrict__ tcol,
-                                                            const int32_t *__restrict__ toff,
-                                                            const double *__restrict__ vals, int as_f32, int64_t n,
-                                                            int64_t pt, int64_t K, int64_t ldt, int64_t ldc,
-                                                            int8_t *__restrict__ A, int8_t *__restrict__ At,
-                                                            uint8_t *__restrict__ codes) {
+__global__ void __launch_bounds__(256) onehot_encode_kernel(
+    const Tin *__restrict__ x, int64_t ldx, const int64_t *__restrict__ perm, const int64_t *__restrict__ tcol,
+    const int32_t *__restrict__ toff, const double *__restrict__ vals, int as_f32, int64_t n, int64_t pt, int64_t K,
+    int64_t ldt, int64_t ldc, int8_t *__restrict__ U, int8_t *__restrict__ Wd, int8_t *__restrict__ At,
+    uint8_t *__restrict__ codesT, uint8_t *__restrict__ codes, int32_t *__restrict__ srow,
+    uint32_t *__restrict__ krow) {
     __shared__ __align__(16) uint8_t code_rc[ENC_ROWS][ENC_COLS];       // [sample][column]
-    __shared__ __align__(16) uint8_t code_cr[ENC_COLS][ENC_ROWS + 4];   // [column][sample], padded: conflict-free transposed stores
-    __shared__ uint8_t kcol[ENC_COLS * FS_DISTINCT_CAP];                // one-hot index -> column in tile
-    __shared__ uint8_t kval[ENC_COLS * FS_DISTINCT_CAP];                // one-hot index -> value code
-    const int tid = threadIdx.x;
+    __shared__ __align__(16) uint8_t code_cr[ENC_COLS][ENC_CR_LD];      // [column][sample]
+    __shared__ uint8_t kcol[ENC_KMAX];                                  // reduced row -> column in tile
+    __shared__ uint8_t kval[ENC_KMAX];                                  // reduced row -> value code
+    __shared__ uint8_t clast[ENC_COLS];                                 // last code of each column
+    __shared__ int64_t sperm[ENC_ROWS];
+    const int tid = threadIdx.x, lane = tid & 31;
     const int64_t c0 = (int64_t)blockIdx.x * ENC_COLS, r0 = (int64_t)blockIdx.y * ENC_ROWS;
     const int ncols = (int)(pt - c0 < ENC_COLS ? pt - c0 : ENC_COLS);
     const int nrows = (int)(n - r0 < ENC_ROWS ? n - r0 : ENC_ROWS);
     const int k0 = toff[c0], k1 = toff[c0 + ncols];
+    if (tid < ENC_ROWS) sperm[tid] = tid < nrows ? perm[r0 + tid] : 0;
 
     // ---- step 1: value codes
     {
         const int c = tid & (ENC_COLS - 1);
         int64_t f = 0;
-        int off = 0, V = 0;
+        int V = 0;
+        bool ident = true;          // the code of a value is the value itself (sorted 0..V-1)
         // code table of this thread's column in the input's own type (values came from the
         // data, so the conversion back is exact); float64 input scored in float32 arithmetic
         // is compared after narrowing, as the reference compares x.astype(float32)
@@ -104,109 +134,169 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(const Tin *__restric
         float vf[FS_DISTINCT_CAP];
         if (c < ncols) {
             f = tcol[c0 + c];
-            off = toff[c0 + c];
-            V = toff[c0 + c + 1] - off;
+            const int off = toff[c0 + c];
+            V = toff[c0 + c + 1] - off + 1;
 #pragma unroll
             for (int q = 0; q < FS_DISTINCT_CAP; ++q) {
-                const double d = vals[f * FS_DISTINCT_CAP + q];
+                const double d = q < V ? vals[f * FS_DISTINCT_CAP + q] : 0.0;
                 v[q] = (Tin)d;
                 vf[q] = (float)d;
+                ident = ident && (q >= V || d == (double)q);
             }
-            if (tid < ENC_COLS)
-                for (int q = 0; q < V; ++q) {
+            if (tid < ENC_COLS) {
+                clast[c] = (uint8_t)(V - 1);
+                for (int q = 0; q < V - 1; ++q) {
                     kcol[off - k0 + q] = (uint8_t)c;
                     kval[off - k0 + q] = (uint8_t)q;
+                    if (blockIdx.y == 0)
+                        krow[off + q] = (uint32_t)(c0 + c) | ((uint32_t)q << 24) | ((uint32_t)(V - 1) << 28);
                 }
-        }
-        for (int rr = tid >> 6; rr < ENC_ROWS; rr += 4) {
-            uint8_t code = 0;
-            if (c < ncols && rr < nrows) {
-                const Tin xv = x[perm[r0 + rr] * ldx + f];
-                int found = 0;
-                if (V <= 4) {                        // genotype-like columns: 4 compares, no loop
-#pragma unroll
-                    for (int q = 3; q >= 0; --q) {
-                        const bool eq = as_f32 ? ((float)xv == vf[q]) : (xv == v[q]);
-                        if (q < V && eq) found = q;  // lowest matching index wins
-                    }
-                } else {
-#pragma unroll
-                    for (int q = FS_DISTINCT_CAP - 1; q >= 0; --q) {
-                        const bool eq = as_f32 ? ((float)xv == vf[q]) : (xv == v[q]);
-                        if (q < V && eq) found = q;
-                    }
-                }
-                code = (uint8_t)found;
-                codes[(r0 + rr) * ldc + c0 + c] = code;
             }
-            code_rc[rr][c] = code;
-            code_cr[c][rr] = code;
+        }
+        __syncthreads();            // sperm
+        // 32 samples per thread (rows tid/64 + 4i): the loads of a batch of 8 are issued before
+        // any of them is used, so 8 requests per thread are in flight
+        constexpr int kBatch = 8;
+        for (int i0 = 0; i0 < ENC_ROWS / 4; i0 += kBatch) {
+            Tin xv[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int rr = (tid >> 6) + 4 * (i0 + u);
+                xv[u] = (c < ncols && rr < nrows) ? x[sperm[rr] * ldx + f] : (Tin)0;
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int rr = (tid >> 6) + 4 * (i0 + u);
+                uint8_t code = 0;
+                if (c < ncols && rr < nrows) {
+                    int found = 0;
+                    if (ident) {
+                        found = (int)xv[u];
+                    } else if (V <= 4) {                 // genotype-like columns: 3 compares, no loop
+#pragma unroll
+                        for (int q = 3; q >= 1; --q) {
+                            const bool eq = as_f32 ? ((float)xv[u] == vf[q]) : (xv[u] == v[q]);
+                            if (q < V && eq) found = q;
+                        }
+                        if (as_f32 ? ((float)xv[u] == vf[0]) : (xv[u] == v[0])) found = 0;   // lowest match wins
+                    } else {
+#pragma unroll
+                        for (int q = FS_DISTINCT_CAP - 1; q >= 0; --q) {
+                            const bool eq = as_f32 ? ((float)xv[u] == vf[q]) : (xv[u] == v[q]);
+                            if (q < V && eq) found = q;
+                        }
+                    }
+                    code = (uint8_t)found;
+                    if (codes) codes[(r0 + rr) * ldc + c0 + c] = code;
+                }
+                code_rc[rr][c] = code;
+                code_cr[c][rr] = code;
+            }
         }
     }
     __syncthreads();
 
-    // ---- step 2: A[r, k0..k1)
-    // fast path (every column of the tile has 3 values and k0 is word-aligned, i.e. 0/1/2
-    // genotypes): 4 codes -> 12 one-hot bytes = three 32-bit words built with shifts
-    const bool v3 = __syncthreads_and((tid >= ncols) || (toff[c0 + (tid < ncols ? tid : 0) + 1] - toff[c0 + (tid < ncols ? tid : 0)] == 3)) &&
-                    (k0 & 3) == 0 && (ncols & 3) == 0;
+    // ---- step 2: U[r, k0..k1), Wd[r, k0..k1), s[r]
+    // fast path (every column of the tile has 3 values and k0 is 16-byte aligned, i.e. 0/1/2
+    // genotypes): 8 codes -> 16 bytes of U and of Wd, built with shifts
+    const bool v3 = __syncthreads_and((tid >= ncols) || clast[tid < ncols ? tid : 0] == 2) && (k0 & 15) == 0 &&
+                    (ncols & 7) == 0;
     if (v3) {
-        const int ngroups = ncols >> 2;                           // 4 columns per thread-iteration
-        for (int rr = tid >> 4; rr < nrows; rr += 16)
-            for (int g = tid & 15; g < ngroups; g += 16) {
-                const uint32_t cw = *reinterpret_cast<const uint32_t *>(&code_rc[rr][4 * g]);
-                // p_i = one-hot triple of code i as a 24-bit little-endian pattern
-                const uint32_t p0 = 1u << (8 * (cw & 0xffu)), p1 = 1u << (8 * ((cw >> 8) & 0xffu));
-                const uint32_t p2 = 1u << (8 * ((cw >> 16) & 0xffu)), p3 = 1u << (8 * (cw >> 24));
-                uint32_t *dst = reinterpret_cast<uint32_t *>(A + (r0 + rr) * K + k0 + 12 * g);
-                dst[0] = p0 | (p1 << 24);
-                dst[1] = (p1 >> 8) | (p2 << 16);
-                dst[2] = (p2 >> 16) | (p3 << 8);
+        const int ngroups = ncols >> 3;
+        for (int item = tid; item < ENC_ROWS * 8; item += 256) {      // uniform trip count (shuffles below)
+            const int rr = item >> 3, g = item & 7;
+            int cnt = 0;
+            if (rr < nrows && g < ngroups) {
+                const uint2 cw = *reinterpret_cast<const uint2 *>(&code_rc[rr][8 * g]);
+                uint4 u, w;
+                expand_v3(cw.x, u.x, u.y, w.x, w.y, cnt);
+                expand_v3(cw.y, u.z, u.w, w.z, w.w, cnt);
+                const int64_t o = (r0 + rr) * K + k0 + 16 * g;
+                *reinterpret_cast<uint4 *>(U + o) = u;
+                *reinterpret_cast<uint4 *>(Wd + o) = w;
             }
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+            if (g == 0 && rr < nrows && cnt) atomicAdd(&srow[r0 + rr], cnt);
+        }
     } else {
         // general path: 32-bit words where the whole word belongs to this tile, single bytes at
         // the unaligned edges (a neighbouring tile owns the rest of that word)
         const int w0 = k0 >> 2, w1 = (k1 + 3) >> 2;               // word range covering [k0, k1)
-        for (int rr = tid >> 5; rr < nrows; rr += 8)
-        for (int w = w0 + (tid & 31); w < w1; w += 32) {
-            uint32_t word = 0;
-            bool full = true;
+        for (int rr = tid >> 5; rr < ENC_ROWS; rr += 8) {          // uniform trip count
+            int cnt = 0;
+            if (rr < nrows) {
+                for (int w = w0 + lane; w < w1; w += 32) {
+                    uint32_t uw = 0, ww = 0;
+                    bool full = true;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int k = 4 * w + b;
-                if (k >= k0 && k < k1) {
-                    const uint32_t on = code_rc[rr][kcol[k - k0]] == kval[k - k0] ? 1u : 0u;
-                    word |= on << (8 * b);
-                } else {
-                    full = false;
-                }
-            }
-            int8_t *dst = A + (r0 + rr) * K + 4 * (int64_t)w;
-            if (full) {
-                *reinterpret_cast<uint32_t *>(dst) = word;
-            } else {
+                    for (int b = 0; b < 4; ++b) {
+                        const int k = 4 * w + b;
+                        if (k >= k0 && k < k1) {
+                            const int col = kcol[k - k0];
+                            const uint32_t code = code_rc[rr][col];
+                            const uint32_t on = code == kval[k - k0] ? 1u : 0u;
+                            uw |= on << (8 * b);
+                            ww |= (on + (code != clast[col] ? 1u : 0u)) << (8 * b);
+                        } else {
+                            full = false;
+                        }
+                    }
+                    const int64_t o = (r0 + rr) * K + 4 * (int64_t)w;
+                    if (full) {
+                        *reinterpret_cast<uint32_t *>(U + o) = uw;
+                        *reinterpret_cast<uint32_t *>(Wd + o) = ww;
+                    } else {
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int k = 4 * w + b;
-                    if (k >= k0 && k < k1) dst[b] = (int8_t)((word >> (8 * b)) & 0xffu);
+                        for (int b = 0; b < 4; ++b) {
+                            const int k = 4 * w + b;
+                            if (k >= k0 && k < k1) {
+                                U[o + b] = (int8_t)((uw >> (8 * b)) & 0xffu);
+                                Wd[o + b] = (int8_t)((ww >> (8 * b)) & 0xffu);
+                            }
+                        }
+                    }
                 }
+                for (int c = lane; c < ncols; c += 32) cnt += code_rc[rr][c] != clast[c] ? 1 : 0;
             }
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if (lane == 0 && rr < nrows && cnt) atomicAdd(&srow[r0 + rr], cnt);
         }
     }
-    // ---- step 3: At[k, r0..r0+128): one warp instruction writes one 128-byte row segment
+    // ---- step 3: At[k, r0..r0+128) and codesT[c, r0..r0+128): 16 samples per store
     {
-        const int lane4 = (tid & 31) * 4;
-        for (int k = k0 + (tid >> 5); k < k1; k += 8) {
-            const uint32_t cw = *reinterpret_cast<const uint32_t *>(&code_cr[kcol[k - k0]][lane4]);
-            const uint32_t val = kval[k - k0];
-            const uint32_t word = __vcmpeq4(cw, val * 0x01010101u) & 0x01010101u;
-            int8_t *dst = At + (int64_t)k * ldt + r0 + lane4;       // r0, ldt multiples of 128: aligned
-            if (lane4 + 4 <= nrows) {
-                *reinterpret_cast<uint32_t *>(dst) = word;
+        const int nk = k1 - k0;
+        for (int item = tid; item < nk * 8; item += 256) {
+            const int kk = item >> 3, seg = item & 7;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&code_cr[kcol[kk]][16 * seg]);
+            const uint32_t val = kval[kk] * 0x01010101u;
+            uint4 o;
+            o.x = __vcmpeq4(src[0], val) & 0x01010101u;
+            o.y = __vcmpeq4(src[1], val) & 0x01010101u;
+            o.z = __vcmpeq4(src[2], val) & 0x01010101u;
+            o.w = __vcmpeq4(src[3], val) & 0x01010101u;
+            int8_t *dst = At + (int64_t)(k0 + kk) * ldt + r0 + 16 * seg;     // r0, ldt multiples of 128: aligned
+            if (16 * seg + 16 <= nrows) {
+                *reinterpret_cast<uint4 *>(dst) = o;
             } else {
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (lane4 + b < nrows) dst[b] = (int8_t)((word >> (8 * b)) & 0xffu);
+                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+                for (int b = 0; b < 16; ++b)
+                    if (16 * seg + b < nrows) dst[b] = (int8_t)((ow[b >> 2] >> (8 * (b & 3))) & 0xffu);
+            }
+        }
+        for (int item = tid; item < ncols * 8; item += 256) {
+            const int c = item >> 3, seg = item & 7;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&code_cr[c][16 * seg]);
+            const uint4 o = make_uint4(src[0], src[1], src[2], src[3]);
+            uint8_t *dst = codesT + (c0 + c) * ldt + r0 + 16 * seg;
+            if (16 * seg + 16 <= nrows) {
+                *reinterpret_cast<uint4 *>(dst) = o;
+            } else {
+                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+                for (int b = 0; b < 16; ++b)
+                    if (16 * seg + b < nrows) dst[b] = (uint8_t)((ow[b >> 2] >> (8 * (b & 3))) & 0xffu);
             }
         }
     }
@@ -215,36 +305,45 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(const Tin *__restric
 void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     const int64_t n = ds->n, pt = ws.pt;
     ws.h_toff.assign(pt + 1, 0);
-    for (int64_t c = 0; c < pt; ++c) ws.h_toff[c + 1] = ws.h_toff[c] + ds->cnt[ws.h_tcol[c]];
+    for (int64_t c = 0; c < pt; ++c) ws.h_toff[c + 1] = ws.h_toff[c] + (ds->cnt[ws.h_tcol[c]] - 1);
     ws.K_used = ws.h_toff[pt];
     ws.K = round_up(ws.K_used, 128);
     ws.ldt = round_up(n, 128);
     ws.ldc = round_up(pt, 16);
     FS_REQUIRE(ws.K < (1LL << 31), FS_ERR_INVALID, "one-hot contraction length too large");
+    FS_REQUIRE(pt < (1LL << 24), FS_ERR_INVALID, "too many one-hot columns (%lld)", (long long)pt);
     std::vector<int32_t> toff32(ws.h_toff.begin(), ws.h_toff.end());
     ws.tcol.reserve(pt);
     ws.tout.reserve(pt);
     ws.toff.reserve(pt + 1);
-    ws.A.reserve((size_t)n * ws.K);
+    ws.U.reserve((size_t)n * ws.K);
+    ws.Wd.reserve((size_t)n * ws.K);
     ws.At.reserve((size_t)ws.K * ws.ldt);
-    ws.codes.reserve((size_t)n * ws.ldc);
+    ws.codesT.reserve((size_t)pt * ws.ldt);
+    if (ws.have_codes) ws.codes.reserve((size_t)n * ws.ldc);
+    ws.srow.reserve(ws.ldt);   // padded: the distance epilogue reads it in 16-byte vectors
+    ws.krow.reserve(ws.K);
     cudaStream_t st = ds->stream;
     FS_CUDA(cudaMemcpyAsync(ws.tcol.ptr, ws.h_tcol.data(), pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     FS_CUDA(cudaMemcpyAsync(ws.tout.ptr, ws.h_tout.data(), pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     FS_CUDA(cudaMemcpyAsync(ws.toff.ptr, toff32.data(), (pt + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    // the encode kernel writes every used byte of A, At and codes exactly once; only the K
-    // padding (one-hot indices K_used..K) has to be cleared.  Sample padding of At rows
-    // (columns n..ldt) and code padding are never read (the TMA maps are n bytes wide).
+    FS_CUDA(cudaMemsetAsync(ws.srow.ptr, 0, ws.ldt * sizeof(int32_t), st));
+    // the encode kernel writes every used byte of U, Wd, At and codesT exactly once; only the K
+    // padding (reduced rows K_used..K) has to be cleared.  Sample padding of the feature-major
+    // rows (columns n..ldt) is never read (the TMA maps are n bytes wide).
     if (ws.K > ws.K_used) {
-        FS_CUDA(cudaMemset2DAsync(ws.A.ptr + ws.K_used, (size_t)ws.K, 0, (size_t)(ws.K - ws.K_used), (size_t)n, st));
+        FS_CUDA(cudaMemset2DAsync(ws.U.ptr + ws.K_used, (size_t)ws.K, 0, (size_t)(ws.K - ws.K_used), (size_t)n, st));
+        FS_CUDA(cudaMemset2DAsync(ws.Wd.ptr + ws.K_used, (size_t)ws.K, 0, (size_t)(ws.K - ws.K_used), (size_t)n, st));
         FS_CUDA(cudaMemsetAsync(ws.At.ptr + (size_t)ws.K_used * ws.ldt, 0, (size_t)(ws.K - ws.K_used) * ws.ldt, st));
     }
     dim3 grid((unsigned)ceil_div(pt, ENC_COLS), (unsigned)ceil_div(n, ENC_ROWS));
     const int as_f32 = (ds->arith == FS_ARITH_F32 && ds->dtype == FS_F64) ? 1 : 0;
-#define FS_ENCODE(T)                                                                                              \
-    onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,        \
+#define FS_ENCODE(T)                                                                                             \
+    onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,       \
                                                   ws.tcol.ptr, ws.toff.ptr, ds->d_vals.ptr, as_f32, n, pt, ws.K, \
-                                                  ws.ldt, ws.ldc, ws.A.ptr, ws.At.ptr, ws.codes.ptr)
+                                                  ws.ldt, ws.ldc, ws.U.ptr, ws.Wd.ptr, ws.At.ptr,                \
+                                                  ws.codesT.ptr, ws.have_codes ? ws.codes.ptr : nullptr,         \
+                                                  ws.srow.ptr, ws.krow.ptr)
     switch (ds->dtype) {
         case FS_U8: FS_ENCODE(uint8_t); break;
         case FS_I8: FS_ENCODE(int8_t); break;
@@ -261,21 +360,25 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
 // distance
 // ---------------------------------------------------------------------------
 void launch_dist_tensor(fs_dataset *ds, const WorkSet &ws, int64_t r0_internal, const int64_t *h_row_ids,
-                        bool contiguous, int64_t R, int32_t *Dd, int64_t ldn, cudaStream_t st, int *launches) {
+                        const int64_t *d_row_ids, bool contiguous, int64_t R, int32_t *Dd, int64_t ldn,
+                        cudaStream_t st, int *launches, double *ops) {
     const int8_t *a_rows;
     if (contiguous) {
-        a_rows = ws.A.ptr + (size_t)r0_internal * ws.K;
+        a_rows = ws.U.ptr + (size_t)r0_internal * ws.K;
     } else {
         DevBuf<int8_t> &g = ds->a_gather;
         g.reserve((size_t)R * ws.K);
         for (int64_t r = 0; r < R; ++r)
-            FS_CUDA(cudaMemcpyAsync(g.ptr + (size_t)r * ws.K, ws.A.ptr + (size_t)h_row_ids[r] * ws.K, ws.K,
+            FS_CUDA(cudaMemcpyAsync(g.ptr + (size_t)r * ws.K, ws.U.ptr + (size_t)h_row_ids[r] * ws.K, ws.K,
                                     cudaMemcpyDeviceToDevice, st));
         a_rows = g.ptr;
     }
+    // all samples are targets: D is symmetric, only the upper-triangular tiles are computed
+    const char *env = getenv("FS_B200_SYMMETRIC");
+    const bool symmetric = contiguous && r0_internal == 0 && R == ds->n && !(env && env[0] == '0');
     const CUtensorMap ta = make_tmap_u8_sw128(a_rows, ws.K, R, ws.K, 128);
-    const CUtensorMap tb = make_tmap_u8_sw128(ws.A.ptr, ws.K, ds->n, ws.K, 256);
-    launch_tc_dist(ta, tb, ws.K, (int32_t)ws.pt, R, ds->n, Dd, ldn, st, launches);
+    const CUtensorMap tb = make_tmap_u8_sw128(ws.Wd.ptr, ws.K, ds->n, ws.K, 256);
+    launch_tc_dist(ta, tb, ws.K, ws.srow.ptr, d_row_ids, R, ds->n, Dd, ldn, symmetric, st, launches, ops);
 }
 
 // ---------------------------------------------------------------------------
@@ -343,9 +446,8 @@ __global__ void __launch_bounds__(256) reduce_code_partials_kernel(const double 
 void launch_accum_tensor(fs_dataset *ds, const WorkSet &ws, int algo, const int64_t *d_row_ids,
                          const int64_t *h_row_ids, bool contiguous, int64_t R, const int8_t *sel, int64_t ldn,
                          const RowInfo *rinfo, const int32_t *nbr_idx, const double *nbr_w, const int32_t *nbr_cnt,
-                         int32_t nbr_cap, double *wsum, cudaStream_t st, int *launches) {
+                         int32_t nbr_cap, double *wsum, cudaStream_t st, int *launches, double *ops) {
     (void)sel;
-    (void)h_row_ids;
     const int64_t n = ds->n;
     if (algo == FS_RELIEFF) {
         const int64_t ctiles = ceil_div(ws.pt, 128);
@@ -369,8 +471,9 @@ void launch_accum_tensor(fs_dataset *ds, const WorkSet &ws, int algo, const int6
     const CUtensorMap tat = make_tmap_u8_sw128(ws.At.ptr, (uint64_t)n, (uint64_t)ws.K, (uint64_t)ws.ldt, 128);
     const CUtensorMap tmh = make_tmap_u8_sw128(ds->maskH.ptr, (uint64_t)n, (uint64_t)R, (uint64_t)ldn, 256);
     const CUtensorMap tmm = make_tmap_u8_sw128(ds->maskM.ptr, (uint64_t)n, (uint64_t)R, (uint64_t)ldn, 256);
-    launch_tc_accum(tat, tmh, tmm, n, R, d_row_ids, contiguous, ds->d_y.ptr, ds->d_cls_start.ptr, rinfo, ws.At.ptr,
-                    ws.ldt, ws.K_used, ds->tpartial.ptr, st, launches);
+    launch_tc_accum(tat, tmh, tmm, n, R, d_row_ids, contiguous, ds->d_y.ptr, ds->d_cls_start.ptr, rinfo,
+                    ws.codesT.ptr, ws.ldt, ws.krow.ptr, ws.K_used, ds->tpartial.ptr, st, launches, h_row_ids,
+                    ds->y_sorted.data(), ds->cls_start.data(), ops);
     reduce_tensor_partials_kernel<<<(unsigned)ceil_div(ws.pt, 256), 256, 0, st>>>(ds->tpartial.ptr, groups, ws.K_used,
                                                                                  ws.toff.ptr, ws.tout.ptr, ws.pt, wsum);
     FS_CUDA(cudaGetLastError());

@@ -14,11 +14,13 @@ namespace fs {
 // tensor path (onehot.cu / tc_dist.cu / tc_accum.cu)
 bool tensor_path_available();
 void launch_dist_tensor(fs_dataset *ds, const WorkSet &ws, int64_t r0_internal, const int64_t *h_row_ids,
-                        bool contiguous, int64_t R, int32_t *Dd, int64_t ldn, cudaStream_t st, int *launches);
+                        const int64_t *d_row_ids, bool contiguous, int64_t R, int32_t *Dd, int64_t ldn,
+                        cudaStream_t st, int *launches, double *ops);
 void launch_accum_tensor(fs_dataset *ds, const WorkSet &ws, int algo, const int64_t *d_row_ids,
                          const int64_t *h_row_ids, bool contiguous, int64_t R, const int8_t *sel, int64_t ldn,
                          const RowInfo *rinfo, const int32_t *nbr_idx, const double *nbr_w,
-                         const int32_t *nbr_cnt, int32_t nbr_cap, double *wsum, cudaStream_t st, int *launches);
+                         const int32_t *nbr_cnt, int32_t nbr_cap, double *wsum, cudaStream_t st, int *launches,
+                         double *ops);
 
 enum Phase { PH_GATHER = 0, PH_DIST_T, PH_DIST_G, PH_SELECT, PH_ACC_T, PH_ACC_G, PH_REDUCE, PH_COUNT };
 
@@ -113,12 +115,13 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
     alloc_stream() = st;
     const int64_t n = ds->n;
     int launches = 0;
+    double ops_dist = 0.0, ops_accum = 0.0;
     Timer timer(stats != nullptr, st);
 
     const char *env_t = getenv("FS_B200_TENSOR");
     const bool allow_tensor = tensor_path_available() && !(env_t && env_t[0] == '0');
     timer.begin(PH_GATHER);
-    build_workset(ds, feat_idx, n_kept, allow_tensor, &launches);
+    build_workset(ds, feat_idx, n_kept, allow_tensor, algo == FS_RELIEFF, &launches);
     timer.end();
     const WorkSet &ws = ds->ws;
 
@@ -172,7 +175,7 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
         // ---- distances
         if (ws.pt > 0) {
             timer.begin(PH_DIST_T);
-            launch_dist_tensor(ds, ws, h_ids[0], h_ids, contiguous, R, ds->Dd.ptr, ldn, st, &launches);
+            launch_dist_tensor(ds, ws, h_ids[0], h_ids, ds->row_ids.ptr, contiguous, R, ds->Dd.ptr, ldn, st, &launches, &ops_dist);
             timer.end();
         }
         if (ws.pg > 0) {
@@ -196,7 +199,7 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
             timer.begin(PH_ACC_T);
             launch_accum_tensor(ds, ws, algo, ds->row_ids.ptr, h_ids, contiguous, R, ds->sel.ptr, ldn,
                                 ds->rinfo.ptr, ds->nbr_idx.ptr, ds->nbr_w.ptr, ds->nbr_cnt.ptr, nbr_cap, d_wsum,
-                                st, &launches);
+                                st, &launches, &ops_accum);
             timer.end();
         }
         if (ws.pg > 0) {
@@ -260,6 +263,8 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
         stats->n_general_cols = ws.n_cont + ws.n_cmp;
         stats->onehot_k = ws.K;
         stats->pairs_selected = (int64_t)sel_pairs;
+        stats->ops_dist_tensor = ops_dist;
+        stats->ops_accum_tensor = ops_accum;
     }
 }
 

@@ -4,13 +4,17 @@
 //
 // Replaces the discrete branch of the reference's accumulation loops and their
 // normalisation (MultiSURF.py:218-251, SURF.py:165-195).  For a discrete feature f with
-// one-hot rows (f, v):
-//     sum_j c_ij [x_if != x_jf] = sum_j c_ij - sum_j c_ij A_{x_if}[j, f],
+// value codes c_jf:
+//     sum_j c_ij [x_if != x_jf] = sum_j c_ij - sum_j c_ij [c_jf = c_if],
 // and with c_ij = -aH_i * mH_ij + aM_i * mM_ij (mH, mM in {-1, 0, 1}: near/far hit and
 // miss masks, aH_i = 1/|H_i|, aM_i = 1/|M_i| or 1) the inner sums are the integer GEMMs
 //     GH[(f,v), i] = sum_j At[(f,v), j] * mH[i, j],   GM likewise,
-// so  W_i[f] = sum_v At[(f,v), i] * ( -aH_i (rsH_i - GH) + aM_i (rsM_i - GM) ),
-// rsH_i / rsM_i being the row sums of the masks.  All counts are exact integers; the
+// over the REDUCED one-hot rows v < last_f (onehot.cu); the implied last plane follows from
+// sum_v G[(f,v), i] = rs_i (the mask's row sum), so
+//     W_i[f] = sum_{v<last} [c_if = v] * k_i (rs_i - G[(f,v), i])  +  [c_if = last] * k_i * sum_{v<last} G[(f,v), i]
+// for each of the two masks (k_i = -aH_i or +aM_i).  The thread that owns one-hot row (f,v)
+// therefore adds k_i (rs_i - G) for targets whose code is v and k_i G for targets whose
+// code is the last one: no exchange between rows.  All counts are exact integers; the
 // per-target scaling and the reduction over targets are done in float64.
 //
 // Kernel: a CTA owns 128 one-hot rows (UMMA M = TMEM lanes) and a group of up to 8
@@ -19,13 +23,16 @@
 // epilogue of one item overlaps the MMAs of the next).  Warp 0: TMA producer (At tile +
 // mask tile per K block of 128 samples, 128B swizzle, 4-stage mbarrier ring); warp 1:
 // one thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=256, K=32); warps 2-9
-// (lane quarter x column half): epilogue -- tcgen05.ld the accumulator, pick the plane the target itself carries (the
-// one-hot byte At[(f,v), i]), scale, and add into one float64 register per one-hot row;
+// (lane quarter x column half): epilogue -- tcgen05.ld the accumulator, test the target's
+// own value code (codesT), scale, and add into float64 registers per one-hot row;
 // the reduction over a tile's targets is a loop over TMEM columns inside one thread.
 // Samples are class-sorted, so for a class-homogeneous target tile the hit mask is
 // non-zero only in the K blocks of the tile's own class and the miss mask only outside:
-// the other K blocks are skipped, which keeps the MMA work at 3 MAC per (pair, feature).
-// Partials are written per (tile group, one-hot row) and reduced in a fixed order.
+// the other K blocks are skipped, which keeps the MMA work at 2 MAC per (pair, feature)
+// for 3-valued genotypes.  Partials are written per (tile group, one-hot row) and reduced
+// in a fixed order.
+#include <algorithm>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -86,7 +93,8 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                 const __grid_constant__ CUtensorMap tmap_mm, int num_k_blocks, int64_t n, int64_t R,
                 int num_tiles, const int64_t *__restrict__ ids, int contiguous, const int32_t *__restrict__ y,
                 const int64_t *__restrict__ cls_start, const RowInfo *__restrict__ rinfo,
-                const int8_t *__restrict__ At, int64_t ldt, int64_t K_rows, double *__restrict__ tpartial) {
+                const uint8_t *__restrict__ codesT, int64_t ldt, const uint32_t *__restrict__ krow, int64_t K_rows,
+                double *__restrict__ tpartial) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
@@ -190,12 +198,17 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
         const int ethread = (warp - 2) * 32 + lane;           // 0..255
         const int64_t mrow = (int64_t)m0 + et;
         const bool row_live = mrow < K_rows;
-        const int8_t *at_row = At + (row_live ? mrow : 0) * ldt;
+        // this one-hot row's column (codesT row), value code and the column's last code
+        const uint32_t meta = row_live ? krow[mrow] : 0u;
+        const uint8_t *at_row = codesT + (int64_t)(meta & 0xffffffu) * ldt;
+        const uint32_t own4 = ((meta >> 24) & 0xfu) * 0x01010101u;
+        // dead rows (beyond K_rows) match nothing: 0xff is not a code
+        const uint32_t last4 = row_live ? (meta >> 28) * 0x01010101u : 0xffffffffu;
         double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
         int item = 0;
         for (int t = tile_begin; t < tile_end; ++t) {
             const TileFlags tf = tile_flags(ids, R, t, contiguous != 0, y, cls_start, n);
-            // one-hot bytes of this thread's 128 targets at its one-hot row (issued before the
+            // value codes of this thread's 128 targets in its column (issued before the
             // accumulator wait so the loads overlap the MMAs); shared by both phases
             uint32_t oh[HALF / 4];
             {
@@ -215,8 +228,8 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
 #pragma unroll
                         for (int b = 0; b < 4; ++b) {
                             const int64_t r = rbase + w * 4 + b;
-                            uint32_t byte = 0u;
-                            if (r < R) byte = (uint32_t)(uint8_t)(contiguous ? at_row[id0 + w * 4 + b] : at_row[ids[r]]);
+                            uint32_t byte = 0xffu;      // not a code: contributes nothing
+                            if (r < R) byte = (uint32_t)(contiguous ? at_row[id0 + w * 4 + b] : at_row[ids[r]]);
                             x |= byte << (8 * b);
                         }
                         oh[w] = x;
@@ -257,15 +270,17 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
 #pragma unroll
                     for (int e = 0; e < 32; e += 4) {
                         const uint32_t w = oh[(c0 + e) >> 2];
-                        // term = on ? c * (rs - G) : 0, four independent float64 chains
-                        const double t0 = (double)(rr[e] - (int)v[e]);
-                        const double t1 = (double)(rr[e + 1] - (int)v[e + 1]);
-                        const double t2 = (double)(rr[e + 2] - (int)v[e + 2]);
-                        const double t3 = (double)(rr[e + 3] - (int)v[e + 3]);
-                        acc0 = fma((w & 0x000000ffu) ? cc[e] : 0.0, t0, acc0);
-                        acc1 = fma((w & 0x0000ff00u) ? cc[e + 1] : 0.0, t1, acc1);
-                        acc2 = fma((w & 0x00ff0000u) ? cc[e + 2] : 0.0, t2, acc2);
-                        acc3 = fma((w & 0xff000000u) ? cc[e + 3] : 0.0, t3, acc3);
+                        const uint32_t own = __vcmpeq4(w, own4), lst = __vcmpeq4(w, last4);
+                        // t = own ? rs - G : (last ? G : 0); four independent float64 chains
+                        const int g0 = (int)v[e], g1 = (int)v[e + 1], g2 = (int)v[e + 2], g3 = (int)v[e + 3];
+                        const int t0 = (own & 0x000000ffu) ? rr[e] - g0 : ((lst & 0x000000ffu) ? g0 : 0);
+                        const int t1 = (own & 0x0000ff00u) ? rr[e + 1] - g1 : ((lst & 0x0000ff00u) ? g1 : 0);
+                        const int t2 = (own & 0x00ff0000u) ? rr[e + 2] - g2 : ((lst & 0x00ff0000u) ? g2 : 0);
+                        const int t3 = (own & 0xff000000u) ? rr[e + 3] - g3 : ((lst & 0xff000000u) ? g3 : 0);
+                        acc0 = fma(cc[e], (double)t0, acc0);
+                        acc1 = fma(cc[e + 1], (double)t1, acc1);
+                        acc2 = fma(cc[e + 2], (double)t2, acc2);
+                        acc3 = fma(cc[e + 3], (double)t3, acc3);
                     }
                 }
                 tc::tc_fence_before();
@@ -288,16 +303,40 @@ int tc_accum_groups(int64_t R) { return 2 * (int)ceil_div(ceil_div(R, BN), GROUP
 
 void launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
                      int64_t R, const int64_t *d_ids, bool contiguous, const int32_t *d_y,
-                     const int64_t *d_cls_start, const RowInfo *rinfo, const int8_t *At, int64_t ldt, int64_t K_rows,
-                     double *tpartial, cudaStream_t st, int *launches) {
+                     const int64_t *d_cls_start, const RowInfo *rinfo, const uint8_t *codesT, int64_t ldt,
+                     const uint32_t *krow, int64_t K_rows, double *tpartial, cudaStream_t st, int *launches,
+                     const int64_t *h_ids, const int32_t *h_y, const int64_t *h_cls_start, double *ops) {
     FS_CUDA(cudaFuncSetAttribute(tc_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     const int num_tiles = (int)ceil_div(R, BN);
     dim3 grid((unsigned)(tc_accum_groups(R) / 2), (unsigned)ceil_div(K_rows, BM));
     tc_accum_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmap_at, tmap_mh, tmap_mm, (int)ceil_div(n, BK), n, R, num_tiles,
-                                                       d_ids, contiguous ? 1 : 0, d_y, d_cls_start, rinfo, At, ldt,
-                                                       K_rows, tpartial);
+                                                       d_ids, contiguous ? 1 : 0, d_y, d_cls_start, rinfo, codesT,
+                                                       ldt, krow, K_rows, tpartial);
     FS_CUDA(cudaGetLastError());
     ++*launches;
+    if (ops) {
+        // K blocks actually contracted: the kernel's own tile_flags / need_block rule, on the host
+        const int nkb = (int)ceil_div(n, BK);
+        int64_t blocks = 0;
+        for (int t = 0; t < num_tiles; ++t) {
+            int64_t hs = 0, he = n;
+            bool mixed = true;
+            if (contiguous) {
+                const int64_t ra = h_ids[0] + (int64_t)t * BN;
+                const int64_t rb = std::min<int64_t>(ra + BN, h_ids[0] + R);
+                const int c_lo = h_y[ra], c_hi = h_y[rb - 1];
+                hs = h_cls_start[c_lo];
+                he = h_cls_start[c_hi + 1];
+                mixed = c_lo != c_hi;
+            }
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int64_t k0 = (int64_t)kb * BK;
+                blocks += (k0 < he && k0 + BK > hs) ? 1 : 0;
+                blocks += (mixed || !(k0 >= hs && k0 + BK <= he)) ? 1 : 0;
+            }
+        }
+        *ops += 2.0 * BM * BN * BK * (double)blocks * (double)grid.y;
+    }
 }
 
 }  // namespace fs

@@ -2,18 +2,23 @@
 //
 // Replaces the discrete branch of the reference's distance loops
 // (MultiSURF.py:184-185, SURF.py:153-154, ReliefF.py:151-152):
-//     d_ij = sum_f [x_if != x_jf] = p_disc - sum_k A[i,k] * A[j,k],
-// where A is the one-hot image of the discrete columns (one int8 column per
-// (feature, value); K = sum_f V_f).  The contraction is an int8 GEMM A * A^T with
+//     d_ij = sum_f [x_if != x_jf] = s_i + s_j - sum_k U[i,k] * Wd[j,k],
+// where U / Wd are the reduced one-hot images of the discrete columns (onehot.cu: V_f - 1
+// int8 columns per feature, K = sum_f (V_f - 1)) and s_i counts the columns in which sample
+// i does not carry its column's last value.  The contraction is an int8 GEMM U * Wd^T with
 // int32 accumulation, so the distances are exact integers.
 //
 // Kernel: one CTA per 128 x 256 tile of D.  Warp 0 streams 128-byte-wide K slabs of
 // both operands with TMA (128B swizzle) through a 4-stage mbarrier ring; one elected
 // thread of warp 1 issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=256, K=32) into
 // a 256-column TMEM accumulator; warps 2-5 read the accumulator back with
-// tcgen05.ld (32 lanes x 32 columns per instruction), form p_disc - acc and store
-// int32 rows (each thread writes whole 128-byte lines).  Tensor-pipe bound:
-// 6 int-ops per (sample pair, feature) for 3-valued genotypes.
+// tcgen05.ld (32 lanes x 32 columns per instruction), form s_i + s_j - acc and store
+// int32 rows (each thread writes whole 128-byte lines).  When every sample is a target
+// (one GPU, one chunk) D is symmetric: only tiles that reach the diagonal or lie above it
+// are computed, and their strictly-upper part is also stored transposed (a warp's 32 lanes
+// hold 32 consecutive rows of one column, so the mirrored store is one 128-byte line).
+// Tensor-pipe bound: 4 int-ops per (sample pair, feature) for 3-valued genotypes, half of
+// that in symmetric mode.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -32,7 +37,10 @@ constexpr int THREADS = 192;
 
 __global__ void __launch_bounds__(THREADS, 1)
 tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               int num_k_blocks, int32_t p_disc, int64_t R, int64_t n, int32_t *__restrict__ Dd, int64_t ldd) {
+               int num_k_blocks, const int32_t *__restrict__ srow, const int64_t *__restrict__ ids, int64_t R,
+               int64_t n, int32_t *__restrict__ Dd, int64_t ldd, int symmetric) {
+    // symmetric mode: tile (by, bx) is needed iff its columns reach the diagonal block of its rows
+    if (symmetric && (int)blockIdx.x < ((int)blockIdx.y >> 1)) return;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *smem_a = smem;
@@ -94,30 +102,40 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     } else {
         // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +32 =====
         const int q = warp & 3;
+        const int64_t row = (int64_t)m0 + q * 32 + lane;
+        const int32_t s_i = row < R ? srow[ids[row]] : 0;      // issued before the accumulator wait
+        // symmetric mode (ids[r] = r): columns below diag_lo are the mirror image of another tile's
+        // stores and are skipped here; columns from diag_hi on are also stored transposed
+        const int64_t diag_lo = symmetric ? (int64_t)m0 : 0;
+        const int64_t diag_hi = symmetric ? (int64_t)m0 + BM : (int64_t)1 << 62;
         tc::mbar_wait(accum_bar, 0);
         tc::tc_fence_after();
-        const int64_t row = (int64_t)m0 + q * 32 + lane;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
+            const int64_t col = (int64_t)n0 + c0;
+            if (col + 32 <= diag_lo || col >= n) continue;     // warp-uniform
             uint32_t v[32];
             tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             tc::tmem_ld_wait();
-            const int64_t col = (int64_t)n0 + c0;
-            if (row < R && col < n) {
-                int32_t *dst = Dd + row * ldd + col;       // ldd is a multiple of 128: 16-byte aligned
-                if (col + 32 <= ldd) {
+            // distances of this thread's row to samples col .. col+31 (srow is padded to ldd)
 #pragma unroll
-                    for (int e = 0; e < 32; e += 4) {
-                        int4 o;
-                        o.x = p_disc - (int32_t)v[e];
-                        o.y = p_disc - (int32_t)v[e + 1];
-                        o.z = p_disc - (int32_t)v[e + 2];
-                        o.w = p_disc - (int32_t)v[e + 3];
-                        *reinterpret_cast<int4 *>(dst + e) = o;
-                    }
-                } else {
-                    for (int e = 0; e < 32 && col + e < ldd; ++e) dst[e] = p_disc - (int32_t)v[e];
-                }
+            for (int e = 0; e < 32; e += 4) {
+                const int4 sj = *reinterpret_cast<const int4 *>(srow + col + e);
+                v[e] = (uint32_t)(s_i + sj.x - (int32_t)v[e]);
+                v[e + 1] = (uint32_t)(s_i + sj.y - (int32_t)v[e + 1]);
+                v[e + 2] = (uint32_t)(s_i + sj.z - (int32_t)v[e + 2]);
+                v[e + 3] = (uint32_t)(s_i + sj.w - (int32_t)v[e + 3]);
+            }
+            if (row < R) {
+                int32_t *dst = Dd + row * ldd + col;           // ldd is a multiple of 128: 16-byte aligned
+#pragma unroll
+                for (int e = 0; e < 32; e += 4)
+                    *reinterpret_cast<int4 *>(dst + e) = make_int4((int)v[e], (int)v[e + 1], (int)v[e + 2], (int)v[e + 3]);
+            }
+            if (col >= diag_hi && row < R) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                    if (col + e < n) Dd[(col + e) * ldd + row] = (int32_t)v[e];
             }
         }
         tc::tc_fence_before();
@@ -129,17 +147,25 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
 }
 
-void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_t K, int32_t p_disc, int64_t R,
-                    int64_t n, int32_t *Dd, int64_t ldd, cudaStream_t st, int *launches) {
+void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_t K, const int32_t *srow,
+                    const int64_t *d_ids, int64_t R, int64_t n, int32_t *Dd, int64_t ldd, bool symmetric,
+                    cudaStream_t st, int *launches, double *ops) {
     static bool configured = false;
     if (!configured) {
         FS_CUDA(cudaFuncSetAttribute(tc_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
     }
     dim3 grid((unsigned)ceil_div(n, BN), (unsigned)ceil_div(R, BM));
-    tc_dist_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmap_a, tmap_b, (int)(K / BK), p_disc, R, n, Dd, ldd);
+    tc_dist_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmap_a, tmap_b, (int)(K / BK), srow, d_ids, R, n, Dd, ldd,
+                                                      symmetric ? 1 : 0);
     FS_CUDA(cudaGetLastError());
     ++*launches;
+    if (ops) {
+        int64_t tiles = 0;
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) tiles += (!symmetric || bx >= (by >> 1)) ? 1 : 0;
+        *ops += 2.0 * BM * BN * (double)K * (double)tiles;
+    }
 }
 
 }  // namespace fs

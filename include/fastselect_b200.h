@@ -32,7 +32,7 @@ extern "C" {
 #define FS_API
 #endif
 
-#define FS_ABI_VERSION 1
+#define FS_ABI_VERSION 2
 /* distinct values tracked per column by fs_dataset_create; a column with more
  * distinct values reports FS_DISTINCT_CAP + 1 */
 #define FS_DISTINCT_CAP 16
@@ -72,8 +72,10 @@ typedef struct fs_stats {
     int32_t n_chunks;        /* target-row chunks processed */
     int64_t n_tensor_cols;   /* active columns on the one-hot tensor-core path */
     int64_t n_general_cols;  /* active columns on the CUDA-core path */
-    int64_t onehot_k;        /* contraction length of the one-hot operands (sum of V_f, padded) */
+    int64_t onehot_k;        /* contraction length of the one-hot operands (sum of V_f - 1, padded) */
     int64_t pairs_selected;  /* neighbour pairs with a non-zero coefficient */
+    double ops_dist_tensor;  /* int8 operations (2 per MAC) issued to the tensor pipe by the distance kernel(s) */
+    double ops_accum_tensor; /* same, accumulation kernel(s) */
 } fs_stats;
 
 /* Number of usable sm_100 devices (0 when there is no driver/GPU).  Replaces

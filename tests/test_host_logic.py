@@ -78,7 +78,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib = ctypes.CDLL(_native.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.fs_abi_version() == 1
+    assert lib.fs_abi_version() == _native.FS_ABI_VERSION
     out = subprocess.run(["nm", "-D", "--defined-only", _native.LIB_PATH], capture_output=True, text=True).stdout
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
     assert declared <= exported
