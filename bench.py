@@ -309,7 +309,15 @@ def own_arm(args):
     rows = hi - lo
     u_rank = float(rows) * n * p
     top = max(("ms_dist_tensor", "ms_dist_general", "ms_accum_tensor", "ms_accum_general"), key=lambda q: phases[q])
-    bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+    # tensor peak: MEASURED_PEAKS.json has the cuBLAS bf16 figure as a burst (kernel timed alone, SM
+    # clocks at max) and sustained under the power cap; int8 dense is nominally 2 x bf16 on B200.
+    # The kernels here run for milliseconds: use the burst figure when the clocks sampled during
+    # the timed region stayed at max, the sustained one otherwise.
+    clk = sampler.summary()
+    at_max = bool(clk.get("sm_mhz")) and clk["sm_mhz"] >= 0.9 * (clk.get("sm_max_mhz") or 1e9)
+    bf16 = peaks.get("bf16_tflops" if at_max else "bf16_tflops_sustained", 1590.0 if at_max else 1400.0)
+    peak_src = ("2 x measured %s bf16 (MEASURED_PEAKS.json)" % ("burst" if at_max else "sustained")) if peaks \
+        else "2 x fallback bf16 (%s)" % ("1.59 PF burst" if at_max else "1.4 PF sustained")
     hbm = peaks.get("hbm_gbs", 6650.0)
     int8_peak = 2.0 * bf16
     traffic = load_traffic(args.workload if world == 1 else None)
@@ -331,8 +339,7 @@ def own_arm(args):
         kernels["ms_gather"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                                 "traffic": traffic.get("ms_gather")}
     if top.endswith("tensor"):
-        roof = dict(kernels[top], kernel=top,
-                    peak_source=("2 x measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "2 x fallback 1.4 PF"))
+        roof = dict(kernels[top], kernel=top, peak_source=peak_src)
     else:
         # CUDA-core kernels re-use every loaded element >= 64 times: algorithmic bytes are one
         # read of both operand slabs plus the D slab write
@@ -352,7 +359,7 @@ def own_arm(args):
             "config": {"workload": w["desc"], "n": n, "p": p, "algo": w["algo"] + ("*" if w["star"] else ""),
                        "rows_per_gpu": rows, "sharding": f"target rows x{world}, one NCCL allreduce",
                        "l2": "inputs larger than L2 (no flush needed)", "step": "encode + distances + select + accumulate"},
-            "clocks": sampler.summary(),
+            "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "seconds_per_fit": dt / e2e_steps, "matches_resident_run": same},
             "gpu_launches": int(agg.get("launches", 0)),

@@ -76,6 +76,28 @@ struct DevBuf {
     }
 };
 
+// Pinned host staging buffer (grow-only): host->device copies of index arrays run at PCIe
+// speed and are truly asynchronous.
+template <typename T>
+struct PinnedBuf {
+    T *ptr = nullptr;
+    size_t count = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    ~PinnedBuf() {
+        if (ptr) cudaFreeHost(ptr);
+    }
+    void reserve(size_t n) {
+        if (n <= count) return;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        count = 0;
+        FS_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ptr), n * sizeof(T)));
+        count = n;
+    }
+};
+
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -116,6 +138,8 @@ struct WorkSet {
     std::vector<int64_t> h_tcol, h_tout, h_toff;
     DevBuf<int64_t> tcol, tout;     // [pt]
     DevBuf<int32_t> toff;           // [pt+1] first reduced one-hot row of each column
+    PinnedBuf<int64_t> p_tcol, p_tout;   // pinned staging of tcol / tout / toff
+    PinnedBuf<int32_t> p_toff;
     DevBuf<int8_t> U;               // [n, K]    sample-major, U[i,(f,v)] = [code == v]            (target side of the distance GEMM)
     DevBuf<int8_t> Wd;              // [n, K]    sample-major, U + [code != last]                 (sample side of the distance GEMM)
     DevBuf<int8_t> At;              // [K, ldt]  feature-major reduced one-hot (sample index contiguous)
@@ -174,6 +198,7 @@ struct fs_dataset {
     fs::DevBuf<float> d_class_probs;
     fs::DevBuf<char> xa_gather;   // gathered target rows (fs_debug_rows)
     fs::DevBuf<double> tpartial;  // tensor-path accumulation partials
+    fs::DevBuf<int32_t> tile_desc; // target-tile descriptors of the accumulation kernel
     fs::DevBuf<int8_t> maskH, maskM;
     fs::DevBuf<int8_t> a_gather;  // gathered one-hot target rows (fs_debug_rows)
     fs::DevBuf<int32_t> tie_flag, tie_order;   // ReliefF reference tie order (select.cu)

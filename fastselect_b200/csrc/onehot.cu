@@ -22,12 +22,13 @@ namespace fs {
 void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_t K, const int32_t *srow,
                     const int64_t *d_ids, int64_t R, int64_t n, int32_t *Dd, int64_t ldd, bool symmetric,
                     cudaStream_t st, int *launches, double *ops);
-int tc_accum_groups(int64_t R);
-void launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
-                     int64_t R, const int64_t *d_ids, bool contiguous, const int32_t *d_y,
-                     const int64_t *d_cls_start, const RowInfo *rinfo, const uint8_t *codesT, int64_t ldt,
-                     const uint32_t *krow, int64_t K_rows, double *tpartial, cudaStream_t st, int *launches,
-                     const int64_t *h_ids, const int32_t *h_y, const int64_t *h_cls_start, double *ops);
+int tc_accum_groups(int64_t R, int n_classes);
+int tc_accum_tile_desc_ints();
+int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
+                    int64_t R, const int64_t *d_ids, bool contiguous, const RowInfo *rinfo, const uint8_t *codesT,
+                    int64_t ldt, const uint32_t *krow, int64_t K_rows, double *tpartial, int32_t *d_tiles,
+                    cudaStream_t st, int *launches, const int64_t *h_ids, const int32_t *h_y,
+                    const int64_t *h_cls_start, double *ops);
 
 bool tensor_path_available() { return true; }
 
@@ -312,21 +313,26 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     ws.ldc = round_up(pt, 16);
     FS_REQUIRE(ws.K < (1LL << 31), FS_ERR_INVALID, "one-hot contraction length too large");
     FS_REQUIRE(pt < (1LL << 24), FS_ERR_INVALID, "too many one-hot columns (%lld)", (long long)pt);
-    std::vector<int32_t> toff32(ws.h_toff.begin(), ws.h_toff.end());
+    ws.p_tcol.reserve(pt);
+    ws.p_tout.reserve(pt);
+    ws.p_toff.reserve(pt + 1);
+    std::copy(ws.h_tcol.begin(), ws.h_tcol.end(), ws.p_tcol.ptr);
+    std::copy(ws.h_tout.begin(), ws.h_tout.end(), ws.p_tout.ptr);
+    for (int64_t c = 0; c <= pt; ++c) ws.p_toff.ptr[c] = (int32_t)ws.h_toff[c];
     ws.tcol.reserve(pt);
     ws.tout.reserve(pt);
     ws.toff.reserve(pt + 1);
     ws.U.reserve((size_t)n * ws.K);
     ws.Wd.reserve((size_t)n * ws.K);
     ws.At.reserve((size_t)ws.K * ws.ldt);
-    ws.codesT.reserve((size_t)pt * ws.ldt);
+    ws.codesT.reserve((size_t)pt * ws.ldt + 512);   // slack: the accumulation epilogue reads whole 128-byte runs
     if (ws.have_codes) ws.codes.reserve((size_t)n * ws.ldc);
     ws.srow.reserve(ws.ldt);   // padded: the distance epilogue reads it in 16-byte vectors
     ws.krow.reserve(ws.K);
     cudaStream_t st = ds->stream;
-    FS_CUDA(cudaMemcpyAsync(ws.tcol.ptr, ws.h_tcol.data(), pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    FS_CUDA(cudaMemcpyAsync(ws.tout.ptr, ws.h_tout.data(), pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    FS_CUDA(cudaMemcpyAsync(ws.toff.ptr, toff32.data(), (pt + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    FS_CUDA(cudaMemcpyAsync(ws.tcol.ptr, ws.p_tcol.ptr, pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    FS_CUDA(cudaMemcpyAsync(ws.tout.ptr, ws.p_tout.ptr, pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    FS_CUDA(cudaMemcpyAsync(ws.toff.ptr, ws.p_toff.ptr, (pt + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     FS_CUDA(cudaMemsetAsync(ws.srow.ptr, 0, ws.ldt * sizeof(int32_t), st));
     // the encode kernel writes every used byte of U, Wd, At and codesT exactly once; only the K
     // padding (reduced rows K_used..K) has to be cleared.  Sample padding of the feature-major
@@ -353,7 +359,8 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
 #undef FS_ENCODE
     FS_CUDA(cudaGetLastError());
     ++*launches;
-    FS_CUDA(cudaStreamSynchronize(st));   // staging vectors above are stack/temporary
+    // no synchronisation here: the pinned staging buffers live in the working set and are only
+    // rewritten by the next build, which starts after fs_score's final stream synchronisation
 }
 
 // ---------------------------------------------------------------------------
@@ -465,16 +472,16 @@ void launch_accum_tensor(fs_dataset *ds, const WorkSet &ws, int algo, const int6
         *launches += 2;
         return;
     }
-    const int groups = tc_accum_groups(R);
-    ds->tpartial.reserve((size_t)groups * ws.K_used);
+    ds->tpartial.reserve((size_t)tc_accum_groups(R, ds->n_classes) * ws.K_used);
+    ds->tile_desc.reserve(tc_accum_tile_desc_ints());
     // K of this GEMM is the sample index: rows of At and of the masks are n bytes long
     const CUtensorMap tat = make_tmap_u8_sw128(ws.At.ptr, (uint64_t)n, (uint64_t)ws.K, (uint64_t)ws.ldt, 128);
     const CUtensorMap tmh = make_tmap_u8_sw128(ds->maskH.ptr, (uint64_t)n, (uint64_t)R, (uint64_t)ldn, 256);
     const CUtensorMap tmm = make_tmap_u8_sw128(ds->maskM.ptr, (uint64_t)n, (uint64_t)R, (uint64_t)ldn, 256);
-    launch_tc_accum(tat, tmh, tmm, n, R, d_row_ids, contiguous, ds->d_y.ptr, ds->d_cls_start.ptr, rinfo,
-                    ws.codesT.ptr, ws.ldt, ws.krow.ptr, ws.K_used, ds->tpartial.ptr, st, launches, h_row_ids,
-                    ds->y_sorted.data(), ds->cls_start.data(), ops);
-    reduce_tensor_partials_kernel<<<(unsigned)ceil_div(ws.pt, 256), 256, 0, st>>>(ds->tpartial.ptr, groups, ws.K_used,
+    const int parts = launch_tc_accum(tat, tmh, tmm, n, R, d_row_ids, contiguous, rinfo, ws.codesT.ptr, ws.ldt,
+                                      ws.krow.ptr, ws.K_used, ds->tpartial.ptr, ds->tile_desc.ptr, st, launches,
+                                      h_row_ids, ds->y_sorted.data(), ds->cls_start.data(), ops);
+    reduce_tensor_partials_kernel<<<(unsigned)ceil_div(ws.pt, 256), 256, 0, st>>>(ds->tpartial.ptr, parts, ws.K_used,
                                                                                  ws.toff.ptr, ws.tout.ptr, ws.pt, wsum);
     FS_CUDA(cudaGetLastError());
     ++*launches;
