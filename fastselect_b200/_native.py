@@ -29,7 +29,8 @@ class FsStats(C.Structure):
                 ("ms_accum_general", C.c_float), ("ms_reduce", C.c_float), ("launches", C.c_int32),
                 ("n_chunks", C.c_int32), ("n_tensor_cols", C.c_int64), ("n_general_cols", C.c_int64),
                 ("onehot_k", C.c_int64), ("pairs_selected", C.c_int64),
-                ("ops_dist_tensor", C.c_double), ("ops_accum_tensor", C.c_double)]
+                ("ops_dist_tensor", C.c_double), ("ops_accum_tensor", C.c_double),
+                ("ms_host_prep", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

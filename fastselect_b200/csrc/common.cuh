@@ -117,6 +117,10 @@ struct RowInfo {
     int32_t n_hit, n_miss, n_far_hit, n_far_miss;   // near hits, near misses, far hits, far misses
 };
 
+// Per-column path of the scoring pipeline (fs_dataset::col_info): bits 0-1 the path, bit 2
+// "value is its own code", bits 4-7 V - 1 for tensor-path columns.
+enum : unsigned { kColContinuous = 0, kColTensor = 1, kColCompare = 2, kColConst = 3, kColPathMask = 3, kColIdent = 4 };
+
 // Working set of one fs_score call: the active columns split by path.
 struct WorkSet {
     // general (CUDA-core) path
@@ -135,10 +139,10 @@ struct WorkSet {
     int64_t pt = 0;                 // active tensor-path columns (V >= 2)
     int64_t K = 0;                  // K_used padded to 128
     int64_t K_used = 0;             // sum of (V_f - 1): reduced one-hot rows in use
-    std::vector<int64_t> h_tcol, h_tout, h_toff;
+    bool all_ident = false;         // every tensor column's value is its own code (one-byte input, values 0..V-1)
     DevBuf<int64_t> tcol, tout;     // [pt]
     DevBuf<int32_t> toff;           // [pt+1] first reduced one-hot row of each column
-    PinnedBuf<int64_t> p_tcol, p_tout;   // pinned staging of tcol / tout / toff
+    PinnedBuf<int64_t> p_tcol, p_tout;   // host copies of tcol / tout / toff (pinned staging)
     PinnedBuf<int32_t> p_toff;
     DevBuf<int8_t> U;               // [n, K]    sample-major, U[i,(f,v)] = [code == v]            (target side of the distance GEMM)
     DevBuf<int8_t> Wd;              // [n, K]    sample-major, U + [code != last]                 (sample side of the distance GEMM)
@@ -183,6 +187,7 @@ struct fs_dataset {
     int arith = FS_ARITH_F32;
     std::vector<uint8_t> is_discrete;
     std::vector<float> recip;
+    std::vector<uint8_t> col_info;           // kCol* flags per column
     // per-call scratch, kept between calls (TuRF re-scores the same data set)
     fs::WorkSet ws;
     fs::DevBuf<double> Dc;        // [R, ldn] continuous/general distance part

@@ -243,49 +243,78 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches);  // onehot.cu
 void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool allow_tensor, bool need_codes,
                    int *launches) {
     WorkSet &ws = ds->ws;
-    std::vector<int64_t> key(n_kept + 2);
+    // cache key: flags + the explicit column list (none when every column is active)
+    const bool all = feat_idx == nullptr;
+    std::vector<int64_t> key(3 + (all ? 0 : n_kept));
     key[0] = allow_tensor ? 1 : 0;
     key[1] = ds->arith;
-    for (int64_t c = 0; c < n_kept; ++c) key[c + 2] = feat_idx ? feat_idx[c] : c;
+    key[2] = all ? -1 : n_kept;
+    if (!all) memcpy(key.data() + 3, feat_idx, n_kept * sizeof(int64_t));
     if (ws.valid && ws.key == key && (ws.have_codes || !need_codes || ws.pt == 0)) return;
     ws.valid = false;
     const int chunk = kChunkBytes / (ds->arith == FS_ARITH_F64 ? 8 : 4);
     ws.elem = ds->arith == FS_ARITH_F64 ? 8 : 4;
 
-    // split the active columns: one-hot tensor path (discrete, V <= FS_DISTINCT_CAP),
-    // continuous, and wide discrete ("compare") columns
-    std::vector<int64_t> cont_col, cont_out, cmp_col, cmp_out, const_col, const_out;
-    ws.h_tcol.clear();
-    ws.h_tout.clear();
+    // split the active columns: one-hot tensor path (discrete, 2 <= V <= FS_DISTINCT_CAP),
+    // continuous, and wide discrete ("compare") columns.  The tensor-path lists are written
+    // straight into the pinned staging buffers the encode kernel's inputs are copied from;
+    // the per-column decisions were made once in fs_dataset_set_features (col_info).
+    std::vector<int64_t> cont_col, cont_out, cmp_col, cmp_out;
+    ws.p_tcol.reserve(n_kept);
+    ws.p_tout.reserve(n_kept);
+    ws.p_toff.reserve(n_kept + 1);
+    int64_t *tcol = ws.p_tcol.ptr, *tout = ws.p_tout.ptr;
+    int32_t *toff = ws.p_toff.ptr;
+    const uint8_t *info = ds->col_info.data();
+    int64_t pt = 0, K = 0, first_const = -1, first_const_out = -1;
+    unsigned ident = kColIdent;
     for (int64_t c = 0; c < n_kept; ++c) {
-        int64_t f = key[c + 2];
+        const int64_t f = all ? c : feat_idx[c];
         FS_REQUIRE(f >= 0 && f < ds->p, FS_ERR_INVALID, "feat_idx[%lld]=%lld outside [0,%lld)", (long long)c,
                    (long long)f, (long long)ds->p);
-        if (ds->is_discrete[f]) {
-            if (ds->cnt[f] == 1) {
+        const unsigned ci = info[f];
+        switch (ci & kColPathMask) {
+            case kColTensor:
+                if (allow_tensor) {
+                    tcol[pt] = f;
+                    tout[pt] = c;
+                    toff[pt] = (int32_t)K;
+                    K += ci >> 4;                  // V - 1 reduced one-hot rows
+                    ident &= ci;
+                    ++pt;
+                } else {
+                    cmp_col.push_back(f);
+                    cmp_out.push_back(c);
+                }
+                break;
+            case kColConst:
                 // a constant column: every per-feature term is 0 (MultiSURF.py:184-185), so it
                 // adds nothing to any distance and its weight stays 0 -- it takes no part
-                const_col.push_back(f);
-                const_out.push_back(c);
-            } else if (allow_tensor && ds->cnt[f] <= FS_DISTINCT_CAP) {
-                ws.h_tcol.push_back(f);
-                ws.h_tout.push_back(c);
-            } else {
+                if (first_const < 0) {
+                    first_const = f;
+                    first_const_out = c;
+                }
+                break;
+            case kColCompare:
                 cmp_col.push_back(f);
                 cmp_out.push_back(c);
-            }
-        } else {
-            cont_col.push_back(f);
-            cont_out.push_back(c);
+                break;
+            default:
+                cont_col.push_back(f);
+                cont_out.push_back(c);
         }
     }
-    if (ws.h_tcol.empty() && cont_col.empty() && cmp_col.empty()) {
+    FS_REQUIRE(K < (1LL << 31) - 128, FS_ERR_INVALID, "one-hot contraction length too large");
+    toff[pt] = (int32_t)K;
+    if (pt == 0 && cont_col.empty() && cmp_col.empty()) {
         // nothing but constant columns: keep one on the compare path so the pipeline has a
         // (zero) distance matrix to select on
-        cmp_col.push_back(const_col[0]);
-        cmp_out.push_back(const_out[0]);
+        cmp_col.push_back(first_const);
+        cmp_out.push_back(first_const_out);
     }
-    ws.pt = (int64_t)ws.h_tcol.size();
+    ws.pt = pt;
+    ws.K_used = K;
+    ws.all_ident = (ident & kColIdent) != 0;
     ws.n_cont = (int64_t)cont_col.size();
     ws.n_cmp = (int64_t)cmp_col.size();
 
@@ -417,6 +446,25 @@ int fs_dataset_set_features(fs_dataset *ds, const uint8_t *is_discrete, const fl
     ds->is_discrete.assign(is_discrete, is_discrete + ds->p);
     ds->recip.assign(recip, recip + ds->p);
     ds->arith = arith;
+    // per-column path of the scoring pipeline, decided once (build_workset reads one byte per column)
+    ds->col_info.resize(ds->p);
+    const bool byte_input = ds->dtype == FS_U8 || ds->dtype == FS_I8;
+    for (int64_t f = 0; f < ds->p; ++f) {
+        unsigned ci = kColContinuous;
+        if (is_discrete[f]) {
+            const int v = ds->cnt[f];
+            if (v == 1) {
+                ci = kColConst;
+            } else if (v <= FS_DISTINCT_CAP) {
+                ci = kColTensor | ((unsigned)(v - 1) << 4);
+                // one-byte integer input whose V distinct values span exactly 0..V-1: the value is its own code
+                if (byte_input && ds->cmin[f] == 0.0 && ds->cmax[f] == (double)(v - 1)) ci |= kColIdent;
+            } else {
+                ci = kColCompare;
+            }
+        }
+        ds->col_info[f] = (uint8_t)ci;
+    }
     ds->have_features = true;
     ds->ws.valid = false;
     return FS_OK;

@@ -90,16 +90,18 @@ constexpr int ENC_COLS = 64;
 constexpr int ENC_CR_LD = ENC_ROWS + 4;                       // conflict-free transposed stores
 constexpr int ENC_KMAX = ENC_COLS * (FS_DISTINCT_CAP - 1);
 
-// 4 genotype codes (one per byte, each 0/1/2) -> 8 bytes of U, 8 bytes of Wd, count of codes != 2
+// 4 genotype codes (one per byte, each 0/1/2) -> 8 bytes of U, 8 bytes of Wd, count of codes != 2.
+// Byte-parallel: e_v = [code == v] per byte from the two low bits of each code.
 __device__ __forceinline__ void expand_v3(uint32_t cw, uint32_t &u0, uint32_t &u1, uint32_t &w0, uint32_t &w1, int &cnt) {
-    const uint32_t p0 = (1u << (8 * (cw & 0xffu))) & 0xffffu, p1 = (1u << (8 * ((cw >> 8) & 0xffu))) & 0xffffu;
-    const uint32_t p2 = (1u << (8 * ((cw >> 16) & 0xffu))) & 0xffffu, p3 = (1u << (8 * (cw >> 24))) & 0xffffu;
-    const uint32_t ne = __vcmpne4(cw, 0x02020202u) & 0x01010101u;      // byte i = [code_i != last]
+    const uint32_t e1 = cw & 0x01010101u, e2 = (cw >> 1) & 0x01010101u;
+    const uint32_t ne = e2 ^ 0x01010101u;             // [code != last]
+    const uint32_t e0 = ne ^ e1;                      // [code == 0]
     cnt += __popc(ne);
-    u0 = p0 | (p1 << 16);
-    u1 = p2 | (p3 << 16);
-    w0 = u0 + (ne & 1u) * 0x0101u + ((ne >> 8) & 1u) * 0x01010000u;
-    w1 = u1 + ((ne >> 16) & 1u) * 0x0101u + (ne >> 24) * 0x01010000u;
+    u0 = __byte_perm(e0, e1, 0x5140);                 // (e0.b0, e1.b0, e0.b1, e1.b1)
+    u1 = __byte_perm(e0, e1, 0x7362);
+    const uint32_t a0 = e0 + ne, a1 = e1 + ne;        // no carries: every byte <= 2
+    w0 = __byte_perm(a0, a1, 0x5140);
+    w1 = __byte_perm(a0, a1, 0x7362);
 }
 
 template <typename Tin>
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
     const int32_t *__restrict__ toff, const double *__restrict__ vals, int as_f32, int64_t n, int64_t pt, int64_t K,
     int64_t ldt, int64_t ldc, int8_t *__restrict__ U, int8_t *__restrict__ Wd, int8_t *__restrict__ At,
     uint8_t *__restrict__ codesT, uint8_t *__restrict__ codes, int32_t *__restrict__ srow,
-    uint32_t *__restrict__ krow) {
+    uint32_t *__restrict__ krow, int all_ident) {
     __shared__ __align__(16) uint8_t code_rc[ENC_ROWS][ENC_COLS];       // [sample][column]
     __shared__ __align__(16) uint8_t code_cr[ENC_COLS][ENC_CR_LD];      // [column][sample]
     __shared__ uint8_t kcol[ENC_KMAX];                                  // reduced row -> column in tile
@@ -137,12 +139,14 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
             f = tcol[c0 + c];
             const int off = toff[c0 + c];
             V = toff[c0 + c + 1] - off + 1;
+            if (!all_ident) {
 #pragma unroll
-            for (int q = 0; q < FS_DISTINCT_CAP; ++q) {
-                const double d = q < V ? vals[f * FS_DISTINCT_CAP + q] : 0.0;
-                v[q] = (Tin)d;
-                vf[q] = (float)d;
-                ident = ident && (q >= V || d == (double)q);
+                for (int q = 0; q < FS_DISTINCT_CAP; ++q) {
+                    const double d = q < V ? vals[f * FS_DISTINCT_CAP + q] : 0.0;
+                    v[q] = (Tin)d;
+                    vf[q] = (float)d;
+                    ident = ident && (q >= V || d == (double)q);
+                }
             }
             if (tid < ENC_COLS) {
                 clast[c] = (uint8_t)(V - 1);
@@ -154,44 +158,64 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
                 }
             }
         }
-        __syncthreads();            // sperm
-        // 32 samples per thread (rows tid/64 + 4i): the loads of a batch of 8 are issued before
-        // any of them is used, so 8 requests per thread are in flight
-        constexpr int kBatch = 8;
-        for (int i0 = 0; i0 < ENC_ROWS / 4; i0 += kBatch) {
-            Tin xv[kBatch];
+        // whole-tile fast path: one-byte input, identity codes, and the tile's 64 columns are 64
+        // consecutive, 16-byte aligned bytes of every row of x -> 16-byte loads, no table look-ups
+        const int64_t f0 = tcol[c0];
+        const bool fast1 = __syncthreads_and(sizeof(Tin) == 1 && ncols == ENC_COLS && ident && f == f0 + c &&
+                                             (ldx & 15) == 0 && ((reinterpret_cast<uintptr_t>(x) + f0) & 15) == 0);
+        if (fast1) {
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int rr = (tid >> 6) + 4 * (i0 + u);
-                xv[u] = (c < ncols && rr < nrows) ? x[sperm[rr] * ldx + f] : (Tin)0;
-            }
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int rr = (tid >> 6) + 4 * (i0 + u);
-                uint8_t code = 0;
-                if (c < ncols && rr < nrows) {
-                    int found = 0;
-                    if (ident) {
-                        found = (int)xv[u];
-                    } else if (V <= 4) {                 // genotype-like columns: 3 compares, no loop
-#pragma unroll
-                        for (int q = 3; q >= 1; --q) {
-                            const bool eq = as_f32 ? ((float)xv[u] == vf[q]) : (xv[u] == v[q]);
-                            if (q < V && eq) found = q;
-                        }
-                        if (as_f32 ? ((float)xv[u] == vf[0]) : (xv[u] == v[0])) found = 0;   // lowest match wins
-                    } else {
-#pragma unroll
-                        for (int q = FS_DISTINCT_CAP - 1; q >= 0; --q) {
-                            const bool eq = as_f32 ? ((float)xv[u] == vf[q]) : (xv[u] == v[q]);
-                            if (q < V && eq) found = q;
-                        }
-                    }
-                    code = (uint8_t)found;
-                    if (codes) codes[(r0 + rr) * ldc + c0 + c] = code;
+            for (int i = 0; i < 2; ++i) {
+                const int item = tid + 256 * i, rr = item >> 2, ch = item & 3;
+                uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                if (rr < nrows) {
+                    q = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(x) + sperm[rr] * ldx + f0 + 16 * ch);
+                    if (codes) *reinterpret_cast<uint4 *>(codes + (r0 + rr) * ldc + c0 + 16 * ch) = q;   // ldc, c0: multiples of 16
                 }
-                code_rc[rr][c] = code;
-                code_cr[c][rr] = code;
+                *reinterpret_cast<uint4 *>(&code_rc[rr][16 * ch]) = q;
+                const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int b = 0; b < 16; ++b) code_cr[16 * ch + b][rr] = (uint8_t)(qw[b >> 2] >> (8 * (b & 3)));
+            }
+        } else {
+            // 32 samples per thread (rows tid/64 + 4i): the loads of a batch of 8 are issued before
+            // any of them is used, so 8 requests per thread are in flight
+            constexpr int kBatch = 8;
+            for (int i0 = 0; i0 < ENC_ROWS / 4; i0 += kBatch) {
+                Tin xv[kBatch];
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    const int rr = (tid >> 6) + 4 * (i0 + u);
+                    xv[u] = (c < ncols && rr < nrows) ? x[sperm[rr] * ldx + f] : (Tin)0;
+                }
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    const int rr = (tid >> 6) + 4 * (i0 + u);
+                    uint8_t code = 0;
+                    if (c < ncols && rr < nrows) {
+                        int found = 0;
+                        if (ident) {
+                            found = (int)xv[u];
+                        } else if (V <= 4) {                 // genotype-like columns: 3 compares, no loop
+#pragma unroll
+                            for (int q = 3; q >= 1; --q) {
+                                const bool eq = as_f32 ? ((float)xv[u] == vf[q]) : (xv[u] == v[q]);
+                                if (q < V && eq) found = q;
+                            }
+                            if (as_f32 ? ((float)xv[u] == vf[0]) : (xv[u] == v[0])) found = 0;   // lowest match wins
+                        } else {
+#pragma unroll
+                            for (int q = FS_DISTINCT_CAP - 1; q >= 0; --q) {
+                                const bool eq = as_f32 ? ((float)xv[u] == vf[q]) : (xv[u] == v[q]);
+                                if (q < V && eq) found = q;
+                            }
+                        }
+                        code = (uint8_t)found;
+                        if (codes) codes[(r0 + rr) * ldc + c0 + c] = code;
+                    }
+                    code_rc[rr][c] = code;
+                    code_cr[c][rr] = code;
+                }
             }
         }
     }
@@ -267,7 +291,23 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
         }
     }
     // ---- step 3: At[k, r0..r0+128) and codesT[c, r0..r0+128): 16 samples per store
-    {
+    if (v3 && nrows == ENC_ROWS) {
+        // 0/1/2 fast path: one item = 16 samples of one column -> its two At rows and its codesT row
+        for (int item = tid; item < ncols * 8; item += 256) {
+            const int c = item >> 3, seg = item & 7;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&code_cr[c][16 * seg]);
+            const uint4 w = make_uint4(src[0], src[1], src[2], src[3]);
+            uint4 e0, e1;
+            e1.x = w.x & 0x01010101u; e0.x = ((w.x >> 1) & 0x01010101u) ^ 0x01010101u ^ e1.x;
+            e1.y = w.y & 0x01010101u; e0.y = ((w.y >> 1) & 0x01010101u) ^ 0x01010101u ^ e1.y;
+            e1.z = w.z & 0x01010101u; e0.z = ((w.z >> 1) & 0x01010101u) ^ 0x01010101u ^ e1.z;
+            e1.w = w.w & 0x01010101u; e0.w = ((w.w >> 1) & 0x01010101u) ^ 0x01010101u ^ e1.w;
+            const int64_t o = r0 + 16 * seg;                                  // r0, ldt multiples of 128: aligned
+            *reinterpret_cast<uint4 *>(At + (int64_t)(k0 + 2 * c) * ldt + o) = e0;
+            *reinterpret_cast<uint4 *>(At + (int64_t)(k0 + 2 * c + 1) * ldt + o) = e1;
+            *reinterpret_cast<uint4 *>(codesT + (c0 + c) * ldt + o) = w;
+        }
+    } else {
         const int nk = k1 - k0;
         for (int item = tid; item < nk * 8; item += 256) {
             const int kk = item >> 3, seg = item & 7;
@@ -305,20 +345,11 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
 
 void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     const int64_t n = ds->n, pt = ws.pt;
-    ws.h_toff.assign(pt + 1, 0);
-    for (int64_t c = 0; c < pt; ++c) ws.h_toff[c + 1] = ws.h_toff[c] + (ds->cnt[ws.h_tcol[c]] - 1);
-    ws.K_used = ws.h_toff[pt];
+    // tcol / tout / toff, K_used and all_ident were filled by build_workset (pinned staging)
     ws.K = round_up(ws.K_used, 128);
     ws.ldt = round_up(n, 128);
     ws.ldc = round_up(pt, 16);
-    FS_REQUIRE(ws.K < (1LL << 31), FS_ERR_INVALID, "one-hot contraction length too large");
     FS_REQUIRE(pt < (1LL << 24), FS_ERR_INVALID, "too many one-hot columns (%lld)", (long long)pt);
-    ws.p_tcol.reserve(pt);
-    ws.p_tout.reserve(pt);
-    ws.p_toff.reserve(pt + 1);
-    std::copy(ws.h_tcol.begin(), ws.h_tcol.end(), ws.p_tcol.ptr);
-    std::copy(ws.h_tout.begin(), ws.h_tout.end(), ws.p_tout.ptr);
-    for (int64_t c = 0; c <= pt; ++c) ws.p_toff.ptr[c] = (int32_t)ws.h_toff[c];
     ws.tcol.reserve(pt);
     ws.tout.reserve(pt);
     ws.toff.reserve(pt + 1);
@@ -344,12 +375,13 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     }
     dim3 grid((unsigned)ceil_div(pt, ENC_COLS), (unsigned)ceil_div(n, ENC_ROWS));
     const int as_f32 = (ds->arith == FS_ARITH_F32 && ds->dtype == FS_F64) ? 1 : 0;
+    const int all_ident = ws.all_ident ? 1 : 0;
 #define FS_ENCODE(T)                                                                                             \
     onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,       \
                                                   ws.tcol.ptr, ws.toff.ptr, ds->d_vals.ptr, as_f32, n, pt, ws.K, \
                                                   ws.ldt, ws.ldc, ws.U.ptr, ws.Wd.ptr, ws.At.ptr,                \
                                                   ws.codesT.ptr, ws.have_codes ? ws.codes.ptr : nullptr,         \
-                                                  ws.srow.ptr, ws.krow.ptr)
+                                                  ws.srow.ptr, ws.krow.ptr, all_ident)
     switch (ds->dtype) {
         case FS_U8: FS_ENCODE(uint8_t); break;
         case FS_I8: FS_ENCODE(int8_t); break;

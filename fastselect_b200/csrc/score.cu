@@ -5,6 +5,7 @@
 // (MultiSURF.py:147-162), _surf_gpu_host_caller (SURF.py:117-128) and
 // _relieff_gpu_host_caller (ReliefF.py:127-134), minus their final "/ n_samples".
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 
 #include "common.cuh"
@@ -121,7 +122,9 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
     const char *env_t = getenv("FS_B200_TENSOR");
     const bool allow_tensor = tensor_path_available() && !(env_t && env_t[0] == '0');
     timer.begin(PH_GATHER);
+    const auto prep0 = std::chrono::steady_clock::now();
     build_workset(ds, feat_idx, n_kept, allow_tensor, algo == FS_RELIEFF, &launches);
+    const double ms_prep = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - prep0).count();
     timer.end();
     const WorkSet &ws = ds->ws;
 
@@ -265,6 +268,7 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
         stats->pairs_selected = (int64_t)sel_pairs;
         stats->ops_dist_tensor = ops_dist;
         stats->ops_accum_tensor = ops_accum;
+        stats->ms_host_prep = ms_prep;
     }
 }
 

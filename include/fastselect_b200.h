@@ -76,6 +76,7 @@ typedef struct fs_stats {
     int64_t pairs_selected;  /* neighbour pairs with a non-zero coefficient */
     double ops_dist_tensor;  /* int8 operations (2 per MAC) issued to the tensor pipe by the distance kernel(s) */
     double ops_accum_tensor; /* same, accumulation kernel(s) */
+    double ms_host_prep;     /* host wall time spent preparing the working set (inside ms_gather) */
 } fs_stats;
 
 /* Number of usable sm_100 devices (0 when there is no driver/GPU).  Replaces
