@@ -40,9 +40,11 @@ UNIT = "sample-pair*features/s"
 # --------------------------------------------------------------------------- #
 # workloads
 # --------------------------------------------------------------------------- #
-def make_workload(name, n_gpus, scaling, n_override=None, p_override=None):
+def make_workload(name, n_gpus, scaling, n_override=None, p_override=None, rows=None):
     from datasets import epistatic_genotypes
 
+    if name == "c5":
+        return make_c5(n_override or 20_000, p_override or 500_000, rows)
     if name == "c3":
         n, p = 4000, 100_000
         algo, star = "MultiSURF", False
@@ -81,6 +83,37 @@ def make_workload(name, n_gpus, scaling, n_override=None, p_override=None):
         x[:, h] += 1.0 * y
         desc = f"C4: MultiSURF* on mixed {n} x {p} (half genotype, half gaussian)"
     return dict(name=name, x=x, y=y, n=n, p=p, algo=algo, star=star, desc=desc)
+
+
+def make_c5(n, p, rows=None):
+    """int8 0/1/2 genotypes n x p, epistatic label on SNPs 25 and 75, for
+    TuRF(MultiSURF, pct_remove=0.1).  Generated in independent 1000-row blocks (seed = [44, block])
+    so that the CPU arm can build just the first `rows` samples of the very same matrix."""
+    m = n if rows is None else min(rows, n)
+    x = np.empty((m, p), np.int8)
+    for b0 in range(0, m, 1000):
+        b1 = min(b0 + 1000, m)
+        x[b0:b1] = np.random.default_rng([44, b0 // 1000]).integers(0, 3, size=(b1 - b0, p), dtype=np.int8)
+    rs = np.random.RandomState(44)
+    y = np.zeros(m, np.int64)
+    y[(x[:, 25] == 1) & (x[:, 75] == 1)] = 1
+    need = m // 2 - int(y.sum())
+    if need > 0:
+        y[rs.choice(np.flatnonzero(y == 0), need, replace=False)] = 1
+    desc = f"C5: TuRF(MultiSURF, pct_remove=0.1) on int8 0/1/2 genotypes {n} samples x {p} SNPs, epistatic label"
+    return dict(name="c5", x=x, y=y, n=n, p=p, algo="MultiSURF", star=False, desc=desc)
+
+
+def turf_schedule(p, n_select=10, pct=0.1):
+    """Column counts of every scoring pass of TuRF (TuRF.py:94-113): the first fit and one per iteration."""
+    sizes, cur = [p], p
+    while cur > n_select:
+        k = max(1, int(cur * pct))
+        if cur - k < n_select:
+            k = cur - n_select
+        cur -= k
+        sizes.append(cur)
+    return sizes
 
 
 def make_estimator(w):
@@ -128,7 +161,7 @@ class ClockSampler(threading.Thread):
 # CPU baseline (oracle port on a bounded sample)
 # --------------------------------------------------------------------------- #
 def cpu_sample(w, n_s=1000, p_s=4000):
-    n_s, p_s = min(n_s, w["n"]), min(p_s, w["p"])
+    n_s, p_s = min(n_s, w["n"], w["x"].shape[0]), min(p_s, w["p"])
     return w["x"][:n_s, :p_s], w["y"][:n_s], n_s, p_s
 
 
@@ -169,7 +202,7 @@ def reference_arm(args):
 
     R.build()
     R.set_threads(os.cpu_count() or 1)
-    w = make_workload(args.workload, 1, "weak", args.n, args.p)
+    w = make_workload(args.workload, 1, "weak", args.n, args.p, rows=1000)
     xs, ys, n_s, p_s = cpu_sample(w)
     for _ in range(args.warmup):
         run_cpu_port(w, xs[:200], ys[:200])
@@ -373,19 +406,151 @@ def own_arm(args):
         dist.destroy_process_group()
 
 
+def turf_arm(args):
+    """--workload c5: one step = one whole TuRF(MultiSURF) run (first fit + every pruning iteration)
+    on a resident data set; e2e = TuRF(...).fit from host buffers."""
+    import torch
+    import torch.distributed as dist
+
+    import fastselect_b200 as fsb
+    from fastselect_b200 import _native
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    _native.load()
+    if _native.device_count() < 1:
+        raise SystemExit("bench.py: no usable sm_100 GPU (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    os.environ["FASTSELECT_B200_DEVICE"] = str(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t_gen = time.perf_counter()
+    w = make_workload("c5", world, "strong", args.n, args.p)
+    t_gen = time.perf_counter() - t_gen
+    n, p = w["n"], w["p"]
+    x_pinned = torch.from_numpy(w["x"]).pin_memory()
+    x_in = x_pinned.numpy()
+    w["x"] = x_in
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    def new_turf():
+        return fsb.TuRF(fsb.MultiSURF(n_features_to_select=10, backend="gpu"), n_features_to_select=10, pct_remove=0.1)
+
+    sizes = turf_schedule(p)
+    units = float(n) * n * float(sum(sizes))
+
+    # ---- resident run: the session stays open, every step is a whole pruning run
+    base = fsb.MultiSURF(n_features_to_select=10, backend="gpu")
+    sess, _ = base._open_session(x_in, w["y"])
+    agg = {}
+
+    def score(active=None):
+        out = sess.score(active, want_stats=True)
+        for k_, v in (sess.last_stats or {}).items():
+            agg[k_] = agg.get(k_, 0) + v
+        return out
+
+    def step():
+        t = new_turf()
+        t.n_features_in_ = p
+        t._prune(score(), score)
+        return t
+
+    for _ in range(args.warmup):
+        score()                          # warm-up: full-width scoring passes (allocations, clocks)
+    agg.clear()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        resident = step()
+    barrier()
+    dt = time.perf_counter() - t0
+    sampler.stop_flag.set()
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    sess.close()
+    value = units * args.steps / dt
+
+    # ---- end to end: TuRF(...).fit from host buffers (upload, column scan, every pass)
+    barrier()
+    t0 = time.perf_counter()
+    fitted = new_turf().fit(x_in, w["y"])
+    barrier()
+    de = time.perf_counter() - t0
+    tt = torch.tensor([de], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    de = float(tt.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    steps = args.steps
+    phases = {k_: agg.get(k_, 0.0) / steps for k_ in ("ms_gather", "ms_dist_tensor", "ms_select", "ms_accum_tensor",
+                                                      "ms_reduce", "ms_total", "ms_host_prep")}
+    at_max = False                       # second-scale steps: sustained peak
+    bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+    int8_peak = 2.0 * bf16
+    kernels = {}
+    for ph, key in (("ms_dist_tensor", "ops_dist_tensor"), ("ms_accum_tensor", "ops_accum_tensor")):
+        ex = agg.get(key, 0.0) / steps / (phases[ph] / 1e3) / 1e12
+        kernels[ph] = {"bound": "tensor", "achieved": ex, "peak": int8_peak, "unit": "TOP/s int8", "frac": ex / int8_peak,
+                       "traffic": None}
+    top = max(kernels, key=lambda q: phases[q])
+    roof = dict(kernels[top], kernel=top,
+                peak_source="2 x measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "2 x fallback 1.4 PF")
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8 one-hot / int32 accum (genotype)", "data": "synthetic",
+            "config": {"workload": w["desc"], "n": n, "p": p, "algo": "TuRF(MultiSURF)", "scoring_passes": len(sizes),
+                       "sum_p_t": int(sum(sizes)), "sharding": f"target rows x{world}, one NCCL allreduce per pass",
+                       "l2": "inputs larger than L2 (no flush needed)",
+                       "step": "one whole TuRF run: first fit + every pruning iteration (encode + distances + select + accumulate each)",
+                       "timing": "host wall clock around the run (barrier + synchronize both sides), max over ranks",
+                       "generate_s": t_gen},
+            "clocks": sampler.summary(),
+            "e2e": {"value": units / de, "unit": UNIT, "h2d_bytes_per_step": int(x_in.nbytes + 4 * n + 9 * p),
+                    "d2h_bytes_per_step": int(20 * p + 8 * sum(sizes)), "steps": 1, "seconds_per_fit": de,
+                    "matches_resident_run": bool(np.array_equal(fitted.top_features_, resident.top_features_))},
+            "gpu_launches": int(agg.get("launches", 0)), "roofline": roof, "kernels": kernels, "phases_ms": phases,
+            "cpu_baseline": None, "top_features": fitted.top_features_.tolist(), "seconds_per_turf_run": dt / steps}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--n", type=int, default=None)
     ap.add_argument("--p", type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
+    elif args.workload == "c5":
+        turf_arm(args)
     else:
         own_arm(args)
 

@@ -32,6 +32,42 @@ class TuRF(TransformerMixin, BaseEstimator):
             n_to_remove = n_active - self.n_features_to_select
         return n_to_remove
 
+    @staticmethod
+    def _worst(scores, n_to_remove):
+        """The set ``np.argsort(scores)[:n_to_remove]`` (TuRF.py:104) without a full sort: an
+        O(p) selection gives the same set unless equal scores straddle the cut, in which
+        case the reference's own argsort decides which of them go."""
+        if n_to_remove >= scores.size:
+            return np.arange(scores.size)
+        kth = np.partition(scores, n_to_remove - 1)[n_to_remove - 1]
+        below = scores <= kth
+        if int(np.count_nonzero(below)) == n_to_remove:
+            return np.flatnonzero(below)
+        return np.argsort(scores)[:n_to_remove]
+
+    def _prune(self, current_scores, score_active):
+        """The pruning loop of TuRF.py:90-119.  ``score_active(active)`` returns the base
+        estimator's importances for the column subset ``active``."""
+        active = np.arange(self.n_features_in_)
+        self.feature_importances_ = current_scores.copy()                                       # TuRF.py:88
+        iteration = 0
+        while True:
+            if len(active) <= self.n_features_to_select:
+                break
+            if self.n_iterations is not None and iteration >= self.n_iterations:
+                break
+            n_to_remove = self._n_to_remove(len(active))
+            worst = self._worst(current_scores, n_to_remove)                                    # TuRF.py:104
+            active = np.delete(active, worst)
+            if self.verbose:
+                print(f"Iteration {iteration}: {len(active)} features remaining.")
+            current_scores = score_active(active)
+            iteration += 1
+        order = np.argsort(current_scores)[::-1]
+        self.top_features_ = np.sort(active[order])                                             # TuRF.py:117-119
+        self.n_iterations_run_ = iteration
+        return self
+
     def fit(self, X, y):
         resident = isinstance(self.estimator, _ReliefBase)
         if resident:
@@ -45,48 +81,21 @@ class TuRF(TransformerMixin, BaseEstimator):
         if not 0 < self.pct_remove < 1:
             raise ValueError("pct_remove must be between 0 and 1.")
 
-        active = np.arange(self.n_features_in_)
         base_estimator = clone(self.estimator)
+        if not resident:
+            def refit(active):
+                base_estimator.fit(Xv[:, active], y)                                            # TuRF.py:110-111
+                return base_estimator.feature_importances_
 
-        session = None
-        if resident:
-            session, _ = base_estimator._open_session(Xv, y)
-        try:
-            if session is not None:
-                current_scores = session.score()
-            elif resident:          # single-class ReliefF: zero scores (ReliefF.py:351-356)
-                current_scores = base_estimator.feature_importances_
-            else:
-                base_estimator.fit(Xv, y)
-                current_scores = base_estimator.feature_importances_
-            self.feature_importances_ = current_scores.copy()                                   # TuRF.py:88
+            base_estimator.fit(Xv, y)
+            return self._prune(base_estimator.feature_importances_, refit)
 
-            iteration = 0
-            while True:
-                if len(active) <= self.n_features_to_select:
-                    break
-                if self.n_iterations is not None and iteration >= self.n_iterations:
-                    break
-                n_to_remove = self._n_to_remove(len(active))
-                worst = np.argsort(current_scores)[:n_to_remove]                                # TuRF.py:104
-                active = np.delete(active, worst)
-                if self.verbose:
-                    print(f"Iteration {iteration}: {len(active)} features remaining.")
-                if session is not None:
-                    current_scores = session.score(active)
-                elif resident:
-                    current_scores = np.zeros(len(active), dtype=np.float32)
-                else:
-                    base_estimator.fit(Xv[:, active], y)
-                    current_scores = base_estimator.feature_importances_
-                iteration += 1
-        finally:
-            if session is not None:
-                session.close()
-
-        order = np.argsort(current_scores)[::-1]
-        self.top_features_ = np.sort(active[order])                                             # TuRF.py:117-119
-        return self
+        session, _ = base_estimator._open_session(Xv, y)
+        if session is None:         # single-class ReliefF: zero scores (ReliefF.py:351-356)
+            return self._prune(base_estimator.feature_importances_,
+                               lambda active: np.zeros(len(active), dtype=np.float32))
+        with session:
+            return self._prune(session.score(), session.score)
 
     def transform(self, X):
         check_is_fitted(self)

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -98,6 +99,19 @@ struct PinnedBuf {
     }
 };
 
+// Host-side scope timer, printed to stderr when FS_B200_TRACE is set (debugging aid).
+struct Trace {
+    const char *name;
+    std::chrono::steady_clock::time_point t0;
+    bool on;
+    explicit Trace(const char *nm) : name(nm), t0(std::chrono::steady_clock::now()), on(getenv("FS_B200_TRACE") != nullptr) {}
+    ~Trace() {
+        if (on)
+            fprintf(stderr, "[fs trace] %-28s %8.3f ms\n", name,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -120,6 +134,11 @@ struct RowInfo {
 // Per-column path of the scoring pipeline (fs_dataset::col_info): bits 0-1 the path, bit 2
 // "value is its own code", bits 4-7 V - 1 for tensor-path columns.
 enum : unsigned { kColContinuous = 0, kColTensor = 1, kColCompare = 2, kColConst = 3, kColPathMask = 3, kColIdent = 4 };
+
+// How the one-hot distance slab of a call is obtained: computed from scratch, updated by
+// subtracting the contribution of the columns removed since the cached slab (TuRF iterations:
+// d_ij -= sum over removed f of [x_if != x_jf], exact integers), or reused as it is.
+enum DistMode : int { kDistFull = 0, kDistIncremental = 1, kDistReuse = 2 };
 
 // Working set of one fs_score call: the active columns split by path.
 struct WorkSet {
@@ -153,6 +172,18 @@ struct WorkSet {
     DevBuf<uint32_t> krow;          // [K] per reduced row: column | value << 24 | last << 28
     int64_t ldt = 0, ldc = 0;
     bool have_codes = false;
+    bool have_dist_ops = false;     // U / Wd / srow of the active columns are built
+    // distance plan of this call (see DistMode) and, for an incremental update, the reduced
+    // one-hot operands of the columns that left the active set since the cached slab was built
+    int dist_mode = 0;
+    std::vector<int64_t> removed;   // original column indices
+    int64_t Kr = 0, Kr_used = 0;
+    PinnedBuf<int64_t> p_rcol;
+    PinnedBuf<int32_t> p_roff;
+    DevBuf<int64_t> rcol;
+    DevBuf<int32_t> roff;
+    DevBuf<int8_t> Ur, Wdr;         // [n, Kr]
+    DevBuf<int32_t> srow_r;         // [n]
     // cache key
     std::vector<int64_t> key;
     bool valid = false;
@@ -192,6 +223,11 @@ struct fs_dataset {
     fs::WorkSet ws;
     fs::DevBuf<double> Dc;        // [R, ldn] continuous/general distance part
     fs::DevBuf<int32_t> Dd;       // [R, ldn] one-hot mismatch counts
+    // what Dd holds after the last call (kept for TuRF's incremental distance update):
+    // the tensor-path columns it sums over and the target rows it covers
+    bool dd_valid = false;
+    std::vector<int64_t> dd_cols;
+    int64_t dd_r0 = -1, dd_R = -1;
     fs::DevBuf<int8_t> sel;       // [R, ldn] neighbour codes
     fs::DevBuf<fs::RowInfo> rinfo;
     fs::DevBuf<int64_t> row_ids;
@@ -214,8 +250,10 @@ struct fs_dataset {
 namespace fs {
 
 // dataset.cu
+// r0 / R / slab_cacheable: the (contiguous) target rows of this call and whether their distance
+// slab fits one chunk -- decides between a full, an incremental and no distance computation
 void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool allow_tensor, bool need_codes,
-                   int *launches);
+                   int64_t r0, int64_t R, bool slab_cacheable, int *launches);
 
 // dist_general.cu: D[r, j] = sum over general columns of the per-feature term
 // between target row r (rows of xa) and sample j (rows of xb).

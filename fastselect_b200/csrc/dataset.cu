@@ -240,9 +240,38 @@ static void run_gather(fs_dataset *ds, WorkSet &ws, int *launches) {
 
 void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches);  // onehot.cu
 
+// Can the cached distance slab serve this call?  tcol[0..pt) are the tensor-path columns now active.
+static int plan_dist(fs_dataset *ds, const int64_t *tcol, int64_t pt, int64_t r0, int64_t R, bool cacheable,
+                     std::vector<int64_t> &removed) {
+    removed.clear();
+    const char *env = getenv("FS_B200_INCREMENTAL");
+    if (env && env[0] == '0') return kDistFull;
+    if (!cacheable || !ds->dd_valid || ds->dd_r0 != r0 || ds->dd_R != R || pt == 0) return kDistFull;
+    const std::vector<int64_t> &old = ds->dd_cols;
+    if ((size_t)pt > old.size()) return kDistFull;
+    // the active columns must be a subsequence of the cached ones (TuRF only ever deletes)
+    size_t j = 0;
+    for (int64_t i = 0; i < pt; ++i) {
+        while (j < old.size() && old[j] != tcol[i]) removed.push_back(old[j++]);
+        if (j == old.size()) {
+            removed.clear();
+            return kDistFull;
+        }
+        ++j;
+    }
+    while (j < old.size()) removed.push_back(old[j++]);
+    if (removed.empty()) return kDistReuse;
+    if ((int64_t)removed.size() >= pt) {           // subtracting would cost more than recomputing
+        removed.clear();
+        return kDistFull;
+    }
+    return kDistIncremental;
+}
+
 void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool allow_tensor, bool need_codes,
-                   int *launches) {
+                   int64_t r0, int64_t R, bool slab_cacheable, int *launches) {
     WorkSet &ws = ds->ws;
+    Trace tr_all("build_workset");
     // cache key: flags + the explicit column list (none when every column is active)
     const bool all = feat_idx == nullptr;
     std::vector<int64_t> key(3 + (all ? 0 : n_kept));
@@ -250,7 +279,14 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
     key[1] = ds->arith;
     key[2] = all ? -1 : n_kept;
     if (!all) memcpy(key.data() + 3, feat_idx, n_kept * sizeof(int64_t));
-    if (ws.valid && ws.key == key && (ws.have_codes || !need_codes || ws.pt == 0)) return;
+    if (ws.valid && ws.key == key && (ws.have_codes || !need_codes || ws.pt == 0)) {
+        // same columns as the last call: the slab is either still there or recomputed in full
+        const int mode = plan_dist(ds, ws.p_tcol.ptr, ws.pt, r0, R, slab_cacheable, ws.removed);
+        if (mode == kDistReuse || ws.have_dist_ops || ws.pt == 0) {
+            ws.dist_mode = mode == kDistReuse ? kDistReuse : kDistFull;
+            return;
+        }
+    }
     ws.valid = false;
     const int chunk = kChunkBytes / (ds->arith == FS_ARITH_F64 ? 8 : 4);
     ws.elem = ds->arith == FS_ARITH_F64 ? 8 : 4;
@@ -260,6 +296,7 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
     // straight into the pinned staging buffers the encode kernel's inputs are copied from;
     // the per-column decisions were made once in fs_dataset_set_features (col_info).
     std::vector<int64_t> cont_col, cont_out, cmp_col, cmp_out;
+    Trace *tr_loop = new Trace("  classify columns");
     ws.p_tcol.reserve(n_kept);
     ws.p_tout.reserve(n_kept);
     ws.p_toff.reserve(n_kept + 1);
@@ -304,6 +341,7 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
                 cont_out.push_back(c);
         }
     }
+    delete tr_loop;
     FS_REQUIRE(K < (1LL << 31) - 128, FS_ERR_INVALID, "one-hot contraction length too large");
     toff[pt] = (int32_t)K;
     if (pt == 0 && cont_col.empty() && cmp_col.empty()) {
@@ -362,7 +400,15 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
     }
     ws.K = 0;
     ws.have_codes = need_codes;
-    if (ws.pt > 0) build_onehot(ds, ws, launches);
+    {
+        Trace tr("  plan_dist");
+        ws.dist_mode = plan_dist(ds, ws.p_tcol.ptr, ws.pt, r0, R, slab_cacheable, ws.removed);
+    }
+    ws.have_dist_ops = ws.dist_mode == kDistFull;
+    if (ws.pt > 0) {
+        Trace tr("  build_onehot");
+        build_onehot(ds, ws, launches);
+    }
     ws.key = std::move(key);
     ws.valid = true;
 }
@@ -467,6 +513,7 @@ int fs_dataset_set_features(fs_dataset *ds, const uint8_t *is_discrete, const fl
     }
     ds->have_features = true;
     ds->ws.valid = false;
+    ds->dd_valid = false;
     return FS_OK;
 }
 

@@ -21,7 +21,7 @@ namespace fs {
 
 void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_t K, const int32_t *srow,
                     const int64_t *d_ids, int64_t R, int64_t n, int32_t *Dd, int64_t ldd, bool symmetric,
-                    cudaStream_t st, int *launches, double *ops);
+                    bool subtract, cudaStream_t st, int *launches, double *ops);
 int tc_accum_groups(int64_t R, int n_classes);
 int tc_accum_tile_desc_ints();
 int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
                 for (int q = 0; q < V - 1; ++q) {
                     kcol[off - k0 + q] = (uint8_t)c;
                     kval[off - k0 + q] = (uint8_t)q;
-                    if (blockIdx.y == 0)
+                    if (blockIdx.y == 0 && krow)
                         krow[off + q] = (uint32_t)(c0 + c) | ((uint32_t)q << 24) | ((uint32_t)(V - 1) << 28);
                 }
             }
@@ -226,7 +226,9 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
     // genotypes): 8 codes -> 16 bytes of U and of Wd, built with shifts
     const bool v3 = __syncthreads_and((tid >= ncols) || clast[tid < ncols ? tid : 0] == 2) && (k0 & 15) == 0 &&
                     (ncols & 7) == 0;
-    if (v3) {
+    if (U == nullptr) {
+        // distance operands not wanted (the slab is updated incrementally from other columns)
+    } else if (v3) {
         const int ngroups = ncols >> 3;
         for (int item = tid; item < ENC_ROWS * 8; item += 256) {      // uniform trip count (shuffles below)
             const int rr = item >> 3, g = item & 7;
@@ -291,7 +293,9 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
         }
     }
     // ---- step 3: At[k, r0..r0+128) and codesT[c, r0..r0+128): 16 samples per store
-    if (v3 && nrows == ENC_ROWS) {
+    if (At == nullptr) {
+        // accumulation operands not wanted (columns that only update the distance slab)
+    } else if (v3 && nrows == ENC_ROWS) {
         // 0/1/2 fast path: one item = 16 samples of one column -> its two At rows and its codesT row
         for (int item = tid; item < ncols * 8; item += 256) {
             const int c = item >> 3, seg = item & 7;
@@ -343,6 +347,56 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
     }
 }
 
+// Distance operands (Ur, Wdr, srow_r) of the columns removed since the cached slab was built.
+static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
+    Trace tr("    build_removed");
+    const int64_t n = ds->n, pr = (int64_t)ws.removed.size();
+    ws.p_rcol.reserve(pr);
+    ws.p_roff.reserve(pr + 1);
+    int64_t K = 0;
+    unsigned ident = kColIdent;
+    for (int64_t c = 0; c < pr; ++c) {
+        const unsigned ci = ds->col_info[ws.removed[c]];
+        ws.p_rcol.ptr[c] = ws.removed[c];
+        ws.p_roff.ptr[c] = (int32_t)K;
+        K += ci >> 4;
+        ident &= ci;
+    }
+    ws.p_roff.ptr[pr] = (int32_t)K;
+    ws.Kr_used = K;
+    ws.Kr = round_up(K, 128);
+    ws.rcol.reserve(pr);
+    ws.roff.reserve(pr + 1);
+    ws.Ur.reserve((size_t)n * ws.Kr);
+    ws.Wdr.reserve((size_t)n * ws.Kr);
+    ws.srow_r.reserve(ws.ldt);
+    cudaStream_t st = ds->stream;
+    FS_CUDA(cudaMemcpyAsync(ws.rcol.ptr, ws.p_rcol.ptr, pr * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    FS_CUDA(cudaMemcpyAsync(ws.roff.ptr, ws.p_roff.ptr, (pr + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    FS_CUDA(cudaMemsetAsync(ws.srow_r.ptr, 0, ws.ldt * sizeof(int32_t), st));
+    if (ws.Kr > ws.Kr_used) {
+        FS_CUDA(cudaMemset2DAsync(ws.Ur.ptr + ws.Kr_used, (size_t)ws.Kr, 0, (size_t)(ws.Kr - ws.Kr_used), (size_t)n, st));
+        FS_CUDA(cudaMemset2DAsync(ws.Wdr.ptr + ws.Kr_used, (size_t)ws.Kr, 0, (size_t)(ws.Kr - ws.Kr_used), (size_t)n, st));
+    }
+    dim3 grid((unsigned)ceil_div(pr, ENC_COLS), (unsigned)ceil_div(n, ENC_ROWS));
+    const int as_f32 = (ds->arith == FS_ARITH_F32 && ds->dtype == FS_F64) ? 1 : 0;
+    const int all_ident = (ident & kColIdent) ? 1 : 0;
+#define FS_ENCODE_R(T)                                                                                            \
+    onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,        \
+                                                  ws.rcol.ptr, ws.roff.ptr, ds->d_vals.ptr, as_f32, n, pr, ws.Kr, \
+                                                  ws.ldt, 0, ws.Ur.ptr, ws.Wdr.ptr, nullptr, nullptr, nullptr,    \
+                                                  ws.srow_r.ptr, nullptr, all_ident)
+    switch (ds->dtype) {
+        case FS_U8: FS_ENCODE_R(uint8_t); break;
+        case FS_I8: FS_ENCODE_R(int8_t); break;
+        case FS_F32: FS_ENCODE_R(float); break;
+        case FS_F64: FS_ENCODE_R(double); break;
+    }
+#undef FS_ENCODE_R
+    FS_CUDA(cudaGetLastError());
+    ++*launches;
+}
+
 void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     const int64_t n = ds->n, pt = ws.pt;
     // tcol / tout / toff, K_used and all_ident were filled by build_workset (pinned staging)
@@ -353,24 +407,29 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     ws.tcol.reserve(pt);
     ws.tout.reserve(pt);
     ws.toff.reserve(pt + 1);
-    ws.U.reserve((size_t)n * ws.K);
-    ws.Wd.reserve((size_t)n * ws.K);
+    const bool ops = ws.have_dist_ops;
+    if (ops) {
+        ws.U.reserve((size_t)n * ws.K);
+        ws.Wd.reserve((size_t)n * ws.K);
+        ws.srow.reserve(ws.ldt);   // padded: the distance epilogue reads it in 16-byte vectors
+    }
     ws.At.reserve((size_t)ws.K * ws.ldt);
     ws.codesT.reserve((size_t)pt * ws.ldt + 512);   // slack: the accumulation epilogue reads whole 128-byte runs
     if (ws.have_codes) ws.codes.reserve((size_t)n * ws.ldc);
-    ws.srow.reserve(ws.ldt);   // padded: the distance epilogue reads it in 16-byte vectors
     ws.krow.reserve(ws.K);
     cudaStream_t st = ds->stream;
     FS_CUDA(cudaMemcpyAsync(ws.tcol.ptr, ws.p_tcol.ptr, pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     FS_CUDA(cudaMemcpyAsync(ws.tout.ptr, ws.p_tout.ptr, pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     FS_CUDA(cudaMemcpyAsync(ws.toff.ptr, ws.p_toff.ptr, (pt + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    FS_CUDA(cudaMemsetAsync(ws.srow.ptr, 0, ws.ldt * sizeof(int32_t), st));
     // the encode kernel writes every used byte of U, Wd, At and codesT exactly once; only the K
     // padding (reduced rows K_used..K) has to be cleared.  Sample padding of the feature-major
     // rows (columns n..ldt) is never read (the TMA maps are n bytes wide).
+    if (ops) FS_CUDA(cudaMemsetAsync(ws.srow.ptr, 0, ws.ldt * sizeof(int32_t), st));
     if (ws.K > ws.K_used) {
-        FS_CUDA(cudaMemset2DAsync(ws.U.ptr + ws.K_used, (size_t)ws.K, 0, (size_t)(ws.K - ws.K_used), (size_t)n, st));
-        FS_CUDA(cudaMemset2DAsync(ws.Wd.ptr + ws.K_used, (size_t)ws.K, 0, (size_t)(ws.K - ws.K_used), (size_t)n, st));
+        if (ops) {
+            FS_CUDA(cudaMemset2DAsync(ws.U.ptr + ws.K_used, (size_t)ws.K, 0, (size_t)(ws.K - ws.K_used), (size_t)n, st));
+            FS_CUDA(cudaMemset2DAsync(ws.Wd.ptr + ws.K_used, (size_t)ws.K, 0, (size_t)(ws.K - ws.K_used), (size_t)n, st));
+        }
         FS_CUDA(cudaMemsetAsync(ws.At.ptr + (size_t)ws.K_used * ws.ldt, 0, (size_t)(ws.K - ws.K_used) * ws.ldt, st));
     }
     dim3 grid((unsigned)ceil_div(pt, ENC_COLS), (unsigned)ceil_div(n, ENC_ROWS));
@@ -379,9 +438,10 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
 #define FS_ENCODE(T)                                                                                             \
     onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,       \
                                                   ws.tcol.ptr, ws.toff.ptr, ds->d_vals.ptr, as_f32, n, pt, ws.K, \
-                                                  ws.ldt, ws.ldc, ws.U.ptr, ws.Wd.ptr, ws.At.ptr,                \
-                                                  ws.codesT.ptr, ws.have_codes ? ws.codes.ptr : nullptr,         \
-                                                  ws.srow.ptr, ws.krow.ptr, all_ident)
+                                                  ws.ldt, ws.ldc, ops ? ws.U.ptr : nullptr,                      \
+                                                  ops ? ws.Wd.ptr : nullptr, ws.At.ptr, ws.codesT.ptr,           \
+                                                  ws.have_codes ? ws.codes.ptr : nullptr,                        \
+                                                  ops ? ws.srow.ptr : nullptr, ws.krow.ptr, all_ident)
     switch (ds->dtype) {
         case FS_U8: FS_ENCODE(uint8_t); break;
         case FS_I8: FS_ENCODE(int8_t); break;
@@ -393,6 +453,7 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     ++*launches;
     // no synchronisation here: the pinned staging buffers live in the working set and are only
     // rewritten by the next build, which starts after fs_score's final stream synchronisation
+    if (ws.dist_mode == kDistIncremental) build_removed(ds, ws, launches);
 }
 
 // ---------------------------------------------------------------------------
@@ -401,23 +462,27 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
 void launch_dist_tensor(fs_dataset *ds, const WorkSet &ws, int64_t r0_internal, const int64_t *h_row_ids,
                         const int64_t *d_row_ids, bool contiguous, int64_t R, int32_t *Dd, int64_t ldn,
                         cudaStream_t st, int *launches, double *ops) {
+    // incremental update: the operands are those of the removed columns and the result is subtracted
+    const bool incr = ws.dist_mode == kDistIncremental;
+    const int8_t *Uop = incr ? ws.Ur.ptr : ws.U.ptr, *Wop = incr ? ws.Wdr.ptr : ws.Wd.ptr;
+    const int32_t *sop = incr ? ws.srow_r.ptr : ws.srow.ptr;
+    const int64_t K = incr ? ws.Kr : ws.K;
     const int8_t *a_rows;
     if (contiguous) {
-        a_rows = ws.U.ptr + (size_t)r0_internal * ws.K;
+        a_rows = Uop + (size_t)r0_internal * K;
     } else {
         DevBuf<int8_t> &g = ds->a_gather;
-        g.reserve((size_t)R * ws.K);
+        g.reserve((size_t)R * K);
         for (int64_t r = 0; r < R; ++r)
-            FS_CUDA(cudaMemcpyAsync(g.ptr + (size_t)r * ws.K, ws.U.ptr + (size_t)h_row_ids[r] * ws.K, ws.K,
-                                    cudaMemcpyDeviceToDevice, st));
+            FS_CUDA(cudaMemcpyAsync(g.ptr + (size_t)r * K, Uop + (size_t)h_row_ids[r] * K, K, cudaMemcpyDeviceToDevice, st));
         a_rows = g.ptr;
     }
     // all samples are targets: D is symmetric, only the upper-triangular tiles are computed
     const char *env = getenv("FS_B200_SYMMETRIC");
     const bool symmetric = contiguous && r0_internal == 0 && R == ds->n && !(env && env[0] == '0');
-    const CUtensorMap ta = make_tmap_u8_sw128(a_rows, ws.K, R, ws.K, 128);
-    const CUtensorMap tb = make_tmap_u8_sw128(ws.Wd.ptr, ws.K, ds->n, ws.K, 256);
-    launch_tc_dist(ta, tb, ws.K, ws.srow.ptr, d_row_ids, R, ds->n, Dd, ldn, symmetric, st, launches, ops);
+    const CUtensorMap ta = make_tmap_u8_sw128(a_rows, K, R, K, 128);
+    const CUtensorMap tb = make_tmap_u8_sw128(Wop, K, ds->n, K, 256);
+    launch_tc_dist(ta, tb, K, sop, d_row_ids, R, ds->n, Dd, ldn, symmetric, incr, st, launches, ops);
 }
 
 // ---------------------------------------------------------------------------

@@ -91,13 +91,13 @@ __global__ void count_selected_kernel(const RowInfo *rinfo, int64_t R, unsigned 
     atomicAdd(out, s);
 }
 
-static int64_t chunk_rows(const fs_dataset *ds, const WorkSet &ws, int64_t ldn, int algo) {
+// target rows per chunk of the distance slab; have_general / have_tensor: which slabs exist
+static int64_t chunk_rows(bool have_general, bool have_tensor, int64_t ldn, int algo) {
     int64_t budget_mb = 6144;
     if (const char *e = getenv("FS_B200_CHUNK_MB")) budget_mb = std::max<int64_t>(16, atoll(e));
-    int64_t per_row = ldn * ((ws.pg > 0 ? 8 : 0) + (ws.pt > 0 ? 4 : 0) + 1 + (ws.pt > 0 ? 2 : 0) + (algo == FS_RELIEFF ? 8 : 0));
+    int64_t per_row = ldn * ((have_general ? 8 : 0) + (have_tensor ? 4 : 0) + 1 + (have_tensor ? 2 : 0) + (algo == FS_RELIEFF ? 8 : 0));
     int64_t rows = budget_mb * (1LL << 20) / std::max<int64_t>(1, per_row);
     rows = std::max<int64_t>(128, rows / 128 * 128);
-    (void)ds;
     return rows;
 }
 
@@ -121,15 +121,21 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
 
     const char *env_t = getenv("FS_B200_TENSOR");
     const bool allow_tensor = tensor_path_available() && !(env_t && env_t[0] == '0');
+    const int64_t ldn = round_up(n, 128);
+    // the one-hot distance slab of a contiguous target range that fits one chunk is kept between
+    // calls: TuRF's next iteration subtracts the removed columns instead of recomputing it
+    const bool slab_cacheable = contiguous && dbg == nullptr &&
+                                round_up((int64_t)targets.size(), 128) <= chunk_rows(true, true, ldn, algo);
+    if (!slab_cacheable) ds->dd_valid = false;
     timer.begin(PH_GATHER);
     const auto prep0 = std::chrono::steady_clock::now();
-    build_workset(ds, feat_idx, n_kept, allow_tensor, algo == FS_RELIEFF, &launches);
+    build_workset(ds, feat_idx, n_kept, allow_tensor, algo == FS_RELIEFF, targets[0], (int64_t)targets.size(),
+                  slab_cacheable, &launches);
     const double ms_prep = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - prep0).count();
     timer.end();
     const WorkSet &ws = ds->ws;
 
-    const int64_t ldn = round_up(n, 128);
-    const int64_t Rmax = std::min<int64_t>(chunk_rows(ds, ws, ldn, algo), round_up((int64_t)targets.size(), 128));
+    const int64_t Rmax = std::min<int64_t>(chunk_rows(ws.pg > 0, ws.pt > 0, ldn, algo), round_up((int64_t)targets.size(), 128));
     if (ws.pg > 0) ds->Dc.reserve((size_t)Rmax * ldn);
     if (ws.pt > 0) ds->Dd.reserve((size_t)Rmax * ldn);
     ds->sel.reserve((size_t)Rmax * ldn);
@@ -176,10 +182,18 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
             }
         }
         // ---- distances
-        if (ws.pt > 0) {
+        if (ws.pt > 0 && ws.dist_mode != kDistReuse) {
+            ds->dd_valid = false;
             timer.begin(PH_DIST_T);
             launch_dist_tensor(ds, ws, h_ids[0], h_ids, ds->row_ids.ptr, contiguous, R, ds->Dd.ptr, ldn, st, &launches, &ops_dist);
             timer.end();
+        }
+        if (ws.pt > 0 && slab_cacheable) {
+            // Dd now holds the mismatch counts of exactly these columns for these target rows
+            ds->dd_cols.assign(ws.p_tcol.ptr, ws.p_tcol.ptr + ws.pt);
+            ds->dd_r0 = targets[0];
+            ds->dd_R = (int64_t)targets.size();
+            ds->dd_valid = true;
         }
         if (ws.pg > 0) {
             timer.begin(PH_DIST_G);

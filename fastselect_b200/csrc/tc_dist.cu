@@ -33,14 +33,29 @@ constexpr int A_BYTES = BM * BK;   // 16 KB
 constexpr int B_BYTES = BN * BK;   // 32 KB
 constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int THREADS = 192;
+constexpr int BAND = 16;        // row blocks per rasterisation band
 }  // namespace
 
 __global__ void __launch_bounds__(THREADS, 1)
 tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                int num_k_blocks, const int32_t *__restrict__ srow, const int64_t *__restrict__ ids, int64_t R,
-               int64_t n, int32_t *__restrict__ Dd, int64_t ldd, int symmetric) {
+               int64_t n, int32_t *__restrict__ Dd, int64_t ldd, int symmetric, int subtract, int tiles_y,
+               int tiles_x) {
+    // L2-friendly rasterisation: bands of BAND row blocks, walked column by column, so that the
+    // ~148 concurrently resident tiles form a roughly square region and share their operand
+    // K-slabs through L2 (16 x 128 target rows and ~9 x 256 sample rows per wave) instead of
+    // streaming a different 256-row slab of the sample operand per tile.
+    int tile_y, tile_x;
+    {
+        const int lin = (int)blockIdx.x;
+        const int band = lin / (BAND * tiles_x);
+        const int band_rows = tiles_y - band * BAND < BAND ? tiles_y - band * BAND : BAND;
+        const int in_band = lin - band * BAND * tiles_x;
+        tile_y = band * BAND + in_band % band_rows;
+        tile_x = in_band / band_rows;
+    }
     // symmetric mode: tile (by, bx) is needed iff its columns reach the diagonal block of its rows
-    if (symmetric && (int)blockIdx.x < ((int)blockIdx.y >> 1)) return;
+    if (symmetric && tile_x < (tile_y >> 1)) return;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *smem_a = smem;
@@ -51,7 +66,7 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int m0 = tile_y * BM, n0 = tile_x * BN;
 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmap_a);
@@ -126,16 +141,27 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 v[e + 2] = (uint32_t)(s_i + sj.z - (int32_t)v[e + 2]);
                 v[e + 3] = (uint32_t)(s_i + sj.w - (int32_t)v[e + 3]);
             }
+            // subtract mode (incremental update): the operands are those of removed columns and
+            // their mismatch count is taken off the resident slab
             if (row < R) {
                 int32_t *dst = Dd + row * ldd + col;           // ldd is a multiple of 128: 16-byte aligned
 #pragma unroll
-                for (int e = 0; e < 32; e += 4)
-                    *reinterpret_cast<int4 *>(dst + e) = make_int4((int)v[e], (int)v[e + 1], (int)v[e + 2], (int)v[e + 3]);
+                for (int e = 0; e < 32; e += 4) {
+                    int4 o = make_int4((int)v[e], (int)v[e + 1], (int)v[e + 2], (int)v[e + 3]);
+                    if (subtract) {
+                        const int4 old = *reinterpret_cast<const int4 *>(dst + e);
+                        o = make_int4(old.x - o.x, old.y - o.y, old.z - o.z, old.w - o.w);
+                    }
+                    *reinterpret_cast<int4 *>(dst + e) = o;
+                }
             }
             if (col >= diag_hi && row < R) {
 #pragma unroll
                 for (int e = 0; e < 32; ++e)
-                    if (col + e < n) Dd[(col + e) * ldd + row] = (int32_t)v[e];
+                    if (col + e < n) {
+                        int32_t *m = Dd + (col + e) * ldd + row;
+                        *m = subtract ? *m - (int32_t)v[e] : (int32_t)v[e];
+                    }
             }
         }
         tc::tc_fence_before();
@@ -149,21 +175,22 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
 void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_t K, const int32_t *srow,
                     const int64_t *d_ids, int64_t R, int64_t n, int32_t *Dd, int64_t ldd, bool symmetric,
-                    cudaStream_t st, int *launches, double *ops) {
+                    bool subtract, cudaStream_t st, int *launches, double *ops) {
     static bool configured = false;
     if (!configured) {
         FS_CUDA(cudaFuncSetAttribute(tc_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
     }
-    dim3 grid((unsigned)ceil_div(n, BN), (unsigned)ceil_div(R, BM));
-    tc_dist_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmap_a, tmap_b, (int)(K / BK), srow, d_ids, R, n, Dd, ldd,
-                                                      symmetric ? 1 : 0);
+    const int tiles_x = (int)ceil_div(n, BN), tiles_y = (int)ceil_div(R, BM);
+    tc_dist_kernel<<<(unsigned)(tiles_x * tiles_y), THREADS, SMEM_BYTES, st>>>(
+        tmap_a, tmap_b, (int)(K / BK), srow, d_ids, R, n, Dd, ldd, symmetric ? 1 : 0, subtract ? 1 : 0, tiles_y,
+        tiles_x);
     FS_CUDA(cudaGetLastError());
     ++*launches;
     if (ops) {
         int64_t tiles = 0;
-        for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx) tiles += (!symmetric || bx >= (by >> 1)) ? 1 : 0;
+        for (int by = 0; by < tiles_y; ++by)
+            for (int bx = 0; bx < tiles_x; ++bx) tiles += (!symmetric || bx >= (by >> 1)) ? 1 : 0;
         *ops += 2.0 * BM * BN * (double)K * (double)tiles;
     }
 }

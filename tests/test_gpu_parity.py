@@ -202,6 +202,67 @@ def test_column_scan_matches_numpy(native):
     assert cmin.tolist() == [-1] * 5 and cmax.tolist() == [1] * 5 and cnt.tolist() == [3] * 5
 
 
+def _mixed_cardinality_genotypes(seed, n, p):
+    """0/1/2 genotypes with some 2-valued, 4-valued and constant columns mixed in (exercises the
+    general encode path and one-hot rows of unequal width next to the 0/1/2 fast path)."""
+    x, y = epistatic_genotypes(seed, n, p)
+    rs = np.random.RandomState(seed + 1)
+    x[:, 5::17] = rs.randint(0, 2, x[:, 5::17].shape)
+    x[:, 9::23] = rs.randint(0, 4, x[:, 9::23].shape)
+    x[:, 11::29] = 1
+    return x, y
+
+
+@pytest.mark.parametrize("rows", [None, (130, 517)])
+def test_incremental_distance_update_equals_full_recompute(native, monkeypatch, rows):
+    """TuRF iterations: the resident distance slab is updated by subtracting the removed columns
+    (exact integers) -- scores must be bitwise those of a from-scratch computation, for a full
+    fit (symmetric tiles) and for a row shard."""
+    n, p = 700, 1500
+    x, y = _mixed_cardinality_genotypes(37, n, p)
+    isd = np.ones(p, bool)
+    recip = np.ones(p, np.float32)
+    rs = np.random.RandomState(5)
+    a1 = np.sort(rs.choice(p, int(p * 0.9), replace=False))
+    a2 = np.sort(rs.choice(a1, int(a1.size * 0.9), replace=False))
+    kw = {} if rows is None else dict(row_begin=rows[0], row_end=rows[1])
+
+    def run():
+        with native.Dataset(x, y.astype(np.int32), 2) as ds:
+            ds.set_features(isd, recip, native.FS_ARITH_F32)
+            out = [ds.score(native.FS_MULTISURF, want_stats=True, **kw)]
+            out.append(ds.score(native.FS_MULTISURF, feat_idx=a1, want_stats=True, **kw))
+            out.append(ds.score(native.FS_MULTISURF, feat_idx=a2, want_stats=True, **kw))
+            out.append(ds.score(native.FS_MULTISURF, use_star=True, feat_idx=a2, want_stats=True, **kw))   # slab reused
+        return out
+
+    inc = run()
+    monkeypatch.setenv("FS_B200_INCREMENTAL", "0")
+    full = run()
+    for (wi, si), (wf, sf) in zip(inc, full):
+        assert np.array_equal(wi, wf)
+    assert inc[0][1]["ops_dist_tensor"] == full[0][1]["ops_dist_tensor"]
+    assert 0 < inc[1][1]["ops_dist_tensor"] < 0.5 * full[1][1]["ops_dist_tensor"]
+    assert 0 < inc[2][1]["ops_dist_tensor"] < 0.5 * full[2][1]["ops_dist_tensor"]
+    assert inc[3][1]["ops_dist_tensor"] == 0 and full[3][1]["ops_dist_tensor"] > 0
+
+
+def test_general_encode_path_matches_oracle(native):
+    """Columns with 2, 3 and 4 values and constants on the one-hot path (reduced planes of unequal
+    width): distances, masks and weights against the oracle."""
+    x, y = _mixed_cardinality_genotypes(38, 400, 333)
+    xf = x.astype(np.float32)
+    x32, recip, isd = R.multisurf_prep(xf, 10)
+    tg = np.arange(0, 400, 3)
+    with native.Dataset(x, y.astype(np.int32), 2) as ds:
+        ds.set_features(isd, recip, native.FS_ARITH_F32)
+        got = ds.debug_rows(native.FS_MULTISURF, tg, use_star=True)
+    want = R.multisurf_targets(x32, y.astype(np.int64), recip, isd, True, tg)
+    assert np.array_equal(got["dist"], want["dist"])
+    assert np.array_equal(got["mask"], want["mask"])
+    np.testing.assert_allclose(got["wsum"], want["wsum"], rtol=RTOL, atol=atol_for(want["wsum"]) * tg.size)
+
+
 def test_chunked_target_rows_give_the_same_result(native, monkeypatch):
     x, y = mixed(36, 300, 40, 2)
     ds, _ = open_multisurf(native, x, y)

@@ -213,3 +213,15 @@ def test_two_rank_gloo_sharding_matches_single_process(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
     assert "rank 0 ok [(0, 31)]" in outs[0] and "rank 1 ok [(31, 61)]" in outs[1]
+
+
+def test_turf_selection_equals_argsort_prefix():
+    """TuRF._worst: O(p) selection returns the set np.argsort(scores)[:k] (TuRF.py:104), ties included."""
+    from fastselect_b200._turf import TuRF
+
+    rs = np.random.RandomState(0)
+    for trial in range(400):
+        n = rs.randint(2, 80)
+        s = rs.randint(0, 5, n).astype(np.float32) if trial % 2 else rs.standard_normal(n).astype(np.float32)
+        k = rs.randint(1, n + 1)
+        assert set(TuRF._worst(s, k).tolist()) == set(np.argsort(s)[:k].tolist())
