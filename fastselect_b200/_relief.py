@@ -129,9 +129,26 @@ class _ReliefBase(TransformerMixin, BaseEstimator):
         self.fit(x, y)
         return self.transform(x)
 
+    @staticmethod
+    def _top(scores, n_select):
+        """``np.argsort(scores)[::-1][:n_select]`` (MultiSURF.py:443, SURF.py:375, ReliefF.py:406)
+        without sorting all p scores: when the n_select largest scores are distinct and strictly
+        above the rest, their descending order IS that prefix; ties fall back to the full argsort
+        so that the reference's tie order is kept."""
+        p = scores.size
+        if n_select * 8 < p and not np.isnan(scores).any():
+            part = np.argpartition(scores, p - n_select - 1)
+            cand = part[p - n_select - 1:]                      # the n_select + 1 largest scores
+            vals = scores[cand]
+            order = np.argsort(vals)[::-1]
+            sv = vals[order]
+            if np.all(sv[:-1] > sv[1:]):                        # strictly decreasing: no ties anywhere near the cut
+                return cand[order][:n_select]
+        return np.argsort(scores)[::-1][:n_select]
+
     def _finish(self, scores, n_select):
         self.feature_importances_ = scores
-        self.top_features_ = np.argsort(scores)[::-1][:n_select]     # MultiSURF.py:443
+        self.top_features_ = self._top(scores, n_select)
         return self
 
 

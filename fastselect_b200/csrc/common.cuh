@@ -78,24 +78,28 @@ struct DevBuf {
 };
 
 // Pinned host staging buffer (grow-only): host->device copies of index arrays run at PCIe
-// speed and are truly asynchronous.
+// speed and are truly asynchronous.  Released blocks go to a process-wide free list instead of
+// cudaFreeHost (page-locking costs milliseconds; every fit opens a new data set).
+void *pinned_take(size_t bytes, size_t *got);
+void pinned_give(void *ptr, size_t bytes);
+
 template <typename T>
 struct PinnedBuf {
     T *ptr = nullptr;
-    size_t count = 0;
+    size_t count = 0, bytes = 0;
     PinnedBuf() = default;
     PinnedBuf(const PinnedBuf &) = delete;
     PinnedBuf &operator=(const PinnedBuf &) = delete;
     ~PinnedBuf() {
-        if (ptr) cudaFreeHost(ptr);
+        if (ptr) pinned_give(ptr, bytes);
     }
     void reserve(size_t n) {
         if (n <= count) return;
-        if (ptr) cudaFreeHost(ptr);
+        if (ptr) pinned_give(ptr, bytes);
         ptr = nullptr;
         count = 0;
-        FS_CUDA(cudaMallocHost(reinterpret_cast<void **>(&ptr), n * sizeof(T)));
-        count = n;
+        ptr = static_cast<T *>(pinned_take(n * sizeof(T), &bytes));
+        count = bytes / sizeof(T);
     }
 };
 

@@ -5,6 +5,7 @@
 // and TuRF's X[:, active] copy (TuRF.py:110).
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 
 #include "common.cuh"
@@ -26,6 +27,51 @@ cudaStream_t &alloc_stream() {
     return s;
 }
 
+// process-wide free list of page-locked staging blocks (see PinnedBuf)
+namespace {
+struct PinnedBlock { void *ptr; size_t bytes; };
+std::mutex g_pinned_mu;
+std::vector<PinnedBlock> g_pinned_free;
+}  // namespace
+
+void *pinned_take(size_t bytes, size_t *got) {
+    {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        // smallest cached block that is large enough
+        int best = -1;
+        for (int i = 0; i < (int)g_pinned_free.size(); ++i)
+            if (g_pinned_free[i].bytes >= bytes && (best < 0 || g_pinned_free[i].bytes < g_pinned_free[best].bytes)) best = i;
+        if (best >= 0) {
+            PinnedBlock b = g_pinned_free[best];
+            g_pinned_free.erase(g_pinned_free.begin() + best);
+            *got = b.bytes;
+            return b.ptr;
+        }
+    }
+    void *p = nullptr;
+    bytes = (size_t)round_up((int64_t)bytes, 4096);
+    FS_CUDA(cudaMallocHost(&p, bytes));
+    *got = bytes;
+    return p;
+}
+
+void pinned_give(void *ptr, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    if (g_pinned_free.size() >= 16) {           // bound the cache: drop the smallest block
+        int small = 0;
+        for (int i = 1; i < (int)g_pinned_free.size(); ++i)
+            if (g_pinned_free[i].bytes < g_pinned_free[small].bytes) small = i;
+        if (g_pinned_free[small].bytes < bytes) {
+            cudaFreeHost(g_pinned_free[small].ptr);
+            g_pinned_free[small] = PinnedBlock{ptr, bytes};
+        } else {
+            cudaFreeHost(ptr);
+        }
+        return;
+    }
+    g_pinned_free.push_back(PinnedBlock{ptr, bytes});
+}
+
 // keep freed blocks in the device's default memory pool (no trimming at synchronisation)
 void configure_pool(int device) {
     static bool done[64] = {false};
@@ -44,17 +90,29 @@ void configure_pool(int device) {
 // HBM-bound: reads n*p*sizeof(T) once.
 // ---------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(128) column_scan_kernel(const T *__restrict__ x, int64_t n, int64_t p,
-                                                          int64_t ldx, double *__restrict__ cmin,
+__global__ void __launch_bounds__(128) column_scan_kernel(const T *__restrict__ x, int64_t row_begin, int64_t row_end,
+                                                          int64_t p, int64_t ldx, double *__restrict__ cmin,
                                                           double *__restrict__ cmax, int32_t *__restrict__ cnt,
-                                                          double *__restrict__ vals) {
+                                                          double *__restrict__ vals, int first, int last) {
     int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= p) return;
+    // per-column state: carried through global memory between row chunks (the upload is chunked
+    // so that the scan of one chunk runs under the copy of the next); values came from T, so the
+    // round trip through double is exact
     T set[FS_DISTINCT_CAP] = {};
     int c = 0;
     bool over = false;
-    T mn = x[f], mx = x[f];
-    for (int64_t i = 0; i < n; ++i) {
+    T mn = x[row_begin * ldx + f], mx = mn;
+    if (!first) {
+        mn = (T)cmin[f];
+        mx = (T)cmax[f];
+        c = cnt[f];
+        over = c > FS_DISTINCT_CAP;
+        c = over ? FS_DISTINCT_CAP : c;
+#pragma unroll
+        for (int q = 0; q < FS_DISTINCT_CAP; ++q) set[q] = (T)vals[f * FS_DISTINCT_CAP + q];
+    }
+    for (int64_t i = row_begin; i < row_end; ++i) {
         T v = x[i * ldx + f];
         mn = v < mn ? v : mn;
         mx = v > mx ? v : mx;
@@ -74,16 +132,18 @@ __global__ void __launch_bounds__(128) column_scan_kernel(const T *__restrict__ 
             }
         }
     }
-    // ascending value order (odd-even transposition on registers): for 0/1/2 genotypes the
-    // value code is then the value itself, which the one-hot encoder exploits
+    if (last) {
+        // ascending value order (odd-even transposition on registers): for 0/1/2 genotypes the
+        // value code is then the value itself, which the one-hot encoder exploits
 #pragma unroll
-    for (int pass = 0; pass < FS_DISTINCT_CAP; ++pass) {
+        for (int pass = 0; pass < FS_DISTINCT_CAP; ++pass) {
 #pragma unroll
-        for (int q = pass & 1; q + 1 < FS_DISTINCT_CAP; q += 2) {
-            const bool sw = (q + 1 < c) && (set[q + 1] < set[q]);
-            const T lo = sw ? set[q + 1] : set[q], hi = sw ? set[q] : set[q + 1];
-            set[q] = lo;
-            set[q + 1] = hi;
+            for (int q = pass & 1; q + 1 < FS_DISTINCT_CAP; q += 2) {
+                const bool sw = (q + 1 < c) && (set[q + 1] < set[q]);
+                const T lo = sw ? set[q + 1] : set[q], hi = sw ? set[q] : set[q + 1];
+                set[q] = lo;
+                set[q + 1] = hi;
+            }
         }
     }
     cmin[f] = (double)mn;
@@ -94,13 +154,22 @@ __global__ void __launch_bounds__(128) column_scan_kernel(const T *__restrict__ 
 }
 
 template <typename T>
-static void run_scan(fs_dataset *ds) {
+static void run_scan(fs_dataset *ds, int64_t row_begin, int64_t row_end, bool first, bool last) {
     int64_t p = ds->p;
     dim3 grid((unsigned)ceil_div(p, 128));
-    column_scan_kernel<T><<<grid, 128, 0, ds->stream>>>(static_cast<const T *>(ds->x), ds->n, p, ds->ldx,
+    column_scan_kernel<T><<<grid, 128, 0, ds->stream>>>(static_cast<const T *>(ds->x), row_begin, row_end, p, ds->ldx,
                                                          ds->d_cmin.ptr, ds->d_cmax.ptr, ds->d_cnt.ptr,
-                                                         ds->d_vals.ptr);
+                                                         ds->d_vals.ptr, first ? 1 : 0, last ? 1 : 0);
     FS_CUDA(cudaGetLastError());
+}
+
+static void scan_rows(fs_dataset *ds, int64_t row_begin, int64_t row_end, bool first, bool last) {
+    switch (ds->dtype) {
+        case FS_U8: run_scan<uint8_t>(ds, row_begin, row_end, first, last); break;
+        case FS_I8: run_scan<int8_t>(ds, row_begin, row_end, first, last); break;
+        case FS_F32: run_scan<float>(ds, row_begin, row_end, first, last); break;
+        case FS_F64: run_scan<double>(ds, row_begin, row_end, first, last); break;
+    }
 }
 
 static size_t dtype_size(int dtype) {
@@ -113,7 +182,8 @@ static size_t dtype_size(int dtype) {
     return 0;
 }
 
-static void finish_create(fs_dataset *ds, const int32_t *y_enc) {
+// class-sorted row order + scan buffers (everything of create that does not need X)
+static void prepare_create(fs_dataset *ds, const int32_t *y_enc) {
     const int64_t n = ds->n, p = ds->p;
     // stable class sort of the samples: hits of a target are one contiguous row
     // range, each miss class another (used by ReliefF's per-class selection).
@@ -139,20 +209,18 @@ static void finish_create(fs_dataset *ds, const int32_t *y_enc) {
     FS_CUDA(cudaMemcpyAsync(ds->d_y.ptr, ds->y_sorted.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, ds->stream));
     FS_CUDA(cudaMemcpyAsync(ds->d_cls_start.ptr, ds->cls_start.data(), (ds->n_classes + 1) * sizeof(int64_t),
                             cudaMemcpyHostToDevice, ds->stream));
-    // column scan
     ds->d_cmin.alloc(p);
     ds->d_cmax.alloc(p);
     ds->d_cnt.alloc(p);
     ds->d_vals.alloc((size_t)p * FS_DISTINCT_CAP);
-    switch (ds->dtype) {
-        case FS_U8: run_scan<uint8_t>(ds); break;
-        case FS_I8: run_scan<int8_t>(ds); break;
-        case FS_F32: run_scan<float>(ds); break;
-        case FS_F64: run_scan<double>(ds); break;
-    }
     ds->cmin.resize(p);
     ds->cmax.resize(p);
     ds->cnt.resize(p);
+}
+
+// column scan results back to the host
+static void finish_create(fs_dataset *ds) {
+    const int64_t p = ds->p;
     FS_CUDA(cudaMemcpyAsync(ds->cmin.data(), ds->d_cmin.ptr, p * sizeof(double), cudaMemcpyDeviceToHost, ds->stream));
     FS_CUDA(cudaMemcpyAsync(ds->cmax.data(), ds->d_cmax.ptr, p * sizeof(double), cudaMemcpyDeviceToHost, ds->stream));
     FS_CUDA(cudaMemcpyAsync(ds->cnt.data(), ds->d_cnt.ptr, p * sizeof(int32_t), cudaMemcpyDeviceToHost, ds->stream));
@@ -436,9 +504,47 @@ int fs_dataset_create(fs_dataset **out, const void *x, int dtype, int64_t n, int
         ds->ldx = round_up(p, 16 / (int64_t)es > 0 ? 16 / (int64_t)es : 1);
         ds->x_owned.alloc((size_t)n * ds->ldx * es);
         ds->x = ds->x_owned.ptr;
-        FS_CUDA(cudaMemcpy2DAsync(ds->x_owned.ptr, ds->ldx * es, x, row_stride_elems * es, p * es, n,
-                                  cudaMemcpyHostToDevice, ds->stream));
-        finish_create(ds, y_enc);
+        // upload in row chunks on a side stream; the scan of chunk i (data set's stream) runs
+        // under the copy of chunk i + 1, so only the last chunk's scan is exposed
+        const int64_t row_bytes = p * (int64_t)es;
+        int64_t chunk_rows = std::max<int64_t>(1, (32LL << 20) / std::max<int64_t>(1, row_bytes));
+        if (ceil_div(n, chunk_rows) > 64) chunk_rows = ceil_div(n, 64);
+        const int n_chunks = (int)ceil_div(n, chunk_rows);
+        cudaStream_t copy_stream = nullptr;
+        std::vector<cudaEvent_t> done(n_chunks, nullptr);
+        FS_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        try {
+            // the copies must not start before the allocation (stream-ordered on ds->stream) exists
+            cudaEvent_t ready;
+            FS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+            FS_CUDA(cudaEventRecord(ready, ds->stream));
+            FS_CUDA(cudaStreamWaitEvent(copy_stream, ready, 0));
+            cudaEventDestroy(ready);
+            for (int c = 0; c < n_chunks; ++c) {
+                const int64_t r0 = c * chunk_rows, r1 = std::min<int64_t>(n, r0 + chunk_rows);
+                FS_CUDA(cudaMemcpy2DAsync(ds->x_owned.ptr + (size_t)r0 * ds->ldx * es, ds->ldx * es,
+                                          static_cast<const char *>(x) + (size_t)r0 * row_stride_elems * es,
+                                          row_stride_elems * es, p * es, r1 - r0, cudaMemcpyHostToDevice, copy_stream));
+                FS_CUDA(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
+                FS_CUDA(cudaEventRecord(done[c], copy_stream));
+            }
+            prepare_create(ds, y_enc);          // host work (class sort) overlaps the first copies
+            for (int c = 0; c < n_chunks; ++c) {
+                const int64_t r0 = c * chunk_rows, r1 = std::min<int64_t>(n, r0 + chunk_rows);
+                FS_CUDA(cudaStreamWaitEvent(ds->stream, done[c], 0));
+                scan_rows(ds, r0, r1, c == 0, c == n_chunks - 1);
+            }
+            finish_create(ds);
+        } catch (...) {
+            cudaStreamSynchronize(copy_stream);
+            for (auto e : done)
+                if (e) cudaEventDestroy(e);
+            cudaStreamDestroy(copy_stream);
+            throw;
+        }
+        for (auto e : done)
+            if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(copy_stream);
         *out = ds;
         return FS_OK;
     } catch (const Fail &f) {
@@ -460,7 +566,9 @@ int fs_dataset_create_device(fs_dataset **out, const void *x_dev, int dtype, int
         ds = create_common(dtype, n, p, row_stride_elems, y_enc, n_classes, device, stream);
         ds->x = x_dev;
         ds->ldx = row_stride_elems;
-        finish_create(ds, y_enc);
+        prepare_create(ds, y_enc);
+        scan_rows(ds, 0, n, true, true);
+        finish_create(ds);
         *out = ds;
         return FS_OK;
     } catch (const Fail &f) {

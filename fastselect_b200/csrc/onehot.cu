@@ -118,7 +118,11 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
     __shared__ uint8_t clast[ENC_COLS];                                 // last code of each column
     __shared__ int64_t sperm[ENC_ROWS];
     const int tid = threadIdx.x, lane = tid & 31;
-    const int64_t c0 = (int64_t)blockIdx.x * ENC_COLS, r0 = (int64_t)blockIdx.y * ENC_ROWS;
+    // row tiles vary fastest: the CTAs resident at one time cover every sample of a band of
+    // columns, so the feature-major rows (At, codesT) are written as whole contiguous rows
+    const int tiles_y = (int)((n + ENC_ROWS - 1) / ENC_ROWS);
+    const int tile_x = (int)(blockIdx.x / tiles_y), tile_y = (int)(blockIdx.x % tiles_y);
+    const int64_t c0 = (int64_t)tile_x * ENC_COLS, r0 = (int64_t)tile_y * ENC_ROWS;
     const int ncols = (int)(pt - c0 < ENC_COLS ? pt - c0 : ENC_COLS);
     const int nrows = (int)(n - r0 < ENC_ROWS ? n - r0 : ENC_ROWS);
     const int k0 = toff[c0], k1 = toff[c0 + ncols];
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
                 for (int q = 0; q < V - 1; ++q) {
                     kcol[off - k0 + q] = (uint8_t)c;
                     kval[off - k0 + q] = (uint8_t)q;
-                    if (blockIdx.y == 0 && krow)
+                    if (tile_y == 0 && krow)
                         krow[off + q] = (uint32_t)(c0 + c) | ((uint32_t)q << 24) | ((uint32_t)(V - 1) << 28);
                 }
             }
@@ -347,6 +351,145 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
     }
 }
 
+// Lean variant for the case that matters most: one-byte input whose active columns all hold
+// exactly the values 0/1/2 (the value is its own code, two reduced rows per column, k0 = 2 c0).
+// No code tables, no per-column bookkeeping: registers stay low enough for 6 CTAs per SM, which
+// is what hides the perm -> x load chain of this streaming kernel.
+__global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
+    const uint8_t *__restrict__ x, int64_t ldx, const int64_t *__restrict__ perm, const int64_t *__restrict__ tcol,
+    int64_t n, int64_t pt, int64_t K, int64_t ldt, int64_t ldc, int8_t *__restrict__ U, int8_t *__restrict__ Wd,
+    int8_t *__restrict__ At, uint8_t *__restrict__ codesT, uint8_t *__restrict__ codes, int32_t *__restrict__ srow,
+    uint32_t *__restrict__ krow) {
+    __shared__ __align__(16) uint8_t code_rc[ENC_ROWS][ENC_COLS];       // [sample][column]
+    __shared__ __align__(16) uint8_t code_cr[ENC_COLS][ENC_CR_LD];      // [column][sample]
+    __shared__ int64_t sperm[ENC_ROWS];
+    const int tid = threadIdx.x;
+    // row tiles vary fastest: the CTAs resident at one time cover every sample of a band of
+    // columns, so the feature-major rows (At, codesT) are written as whole contiguous rows
+    const int tiles_y = (int)((n + ENC_ROWS - 1) / ENC_ROWS);
+    const int tile_x = (int)(blockIdx.x / tiles_y), tile_y = (int)(blockIdx.x % tiles_y);
+    const int64_t c0 = (int64_t)tile_x * ENC_COLS, r0 = (int64_t)tile_y * ENC_ROWS;
+    const int ncols = (int)(pt - c0 < ENC_COLS ? pt - c0 : ENC_COLS);
+    const int nrows = (int)(n - r0 < ENC_ROWS ? n - r0 : ENC_ROWS);
+    const int64_t k0 = 2 * c0;
+    if (tid < ENC_ROWS) sperm[tid] = tid < nrows ? perm[r0 + tid] : 0;
+    const int c = tid & (ENC_COLS - 1);
+    const int64_t f = c < ncols ? tcol[c0 + c] : 0, f0 = tcol[c0];
+    if (tile_y == 0 && krow && tid < ncols) {
+        krow[k0 + 2 * tid] = (uint32_t)(c0 + tid) | (2u << 28);
+        krow[k0 + 2 * tid + 1] = (uint32_t)(c0 + tid) | (1u << 24) | (2u << 28);
+    }
+    // ---- step 1: codes (= values) into shared memory, both orientations
+    const bool fast1 = __syncthreads_and(ncols == ENC_COLS && f == f0 + c && (ldx & 15) == 0 &&
+                                         ((reinterpret_cast<uintptr_t>(x) + f0) & 15) == 0);
+    if (fast1) {
+        // the tile's 64 columns are 64 consecutive, 16-byte aligned bytes of every row of x
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int item = tid + 256 * i, rr = item >> 2, ch = item & 3;
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (rr < nrows) {
+                q = *reinterpret_cast<const uint4 *>(x + sperm[rr] * ldx + f0 + 16 * ch);
+                if (codes) *reinterpret_cast<uint4 *>(codes + (r0 + rr) * ldc + c0 + 16 * ch) = q;
+            }
+            *reinterpret_cast<uint4 *>(&code_rc[rr][16 * ch]) = q;
+            const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int b = 0; b < 16; ++b) code_cr[16 * ch + b][rr] = (uint8_t)(qw[b >> 2] >> (8 * (b & 3)));
+        }
+    } else {
+        // gathered columns (TuRF iterations): one column per thread, 8 loads in flight
+        constexpr int kBatch = 8;
+        for (int i0 = 0; i0 < ENC_ROWS / 4; i0 += kBatch) {
+            uint8_t xv[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int rr = (tid >> 6) + 4 * (i0 + u);
+                xv[u] = (c < ncols && rr < nrows) ? x[sperm[rr] * ldx + f] : (uint8_t)0;
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int rr = (tid >> 6) + 4 * (i0 + u);
+                if (codes && c < ncols && rr < nrows) codes[(r0 + rr) * ldc + c0 + c] = xv[u];
+                code_rc[rr][c] = xv[u];
+                code_cr[c][rr] = xv[u];
+            }
+        }
+    }
+    __syncthreads();
+    // ---- step 2: U, Wd (16 bytes per 8 codes) and the per-sample counts s
+    if (U != nullptr) {
+        if ((ncols & 7) == 0) {
+            const int ngroups = ncols >> 3;
+#pragma unroll
+            for (int it = 0; it < ENC_ROWS * 8 / 256; ++it) {
+                const int item = tid + 256 * it, rr = item >> 3, g = item & 7;
+                int cnt = 0;
+                if (rr < nrows && g < ngroups) {
+                    const uint2 cw = *reinterpret_cast<const uint2 *>(&code_rc[rr][8 * g]);
+                    uint4 u, w;
+                    expand_v3(cw.x, u.x, u.y, w.x, w.y, cnt);
+                    expand_v3(cw.y, u.z, u.w, w.z, w.w, cnt);
+                    const int64_t o = (r0 + rr) * K + k0 + 16 * g;
+                    *reinterpret_cast<uint4 *>(U + o) = u;
+                    *reinterpret_cast<uint4 *>(Wd + o) = w;
+                }
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+                if (g == 0 && rr < nrows && cnt) atomicAdd(&srow[r0 + rr], cnt);
+            }
+        } else {
+            // ragged last column tile: one (sample, column) pair per step
+            for (int rr = tid >> 5; rr < ENC_ROWS; rr += 8) {
+                int cnt = 0;
+                if (rr < nrows)
+                    for (int cc = tid & 31; cc < ncols; cc += 32) {
+                        const uint32_t code = code_rc[rr][cc];
+                        const uint32_t nl = code != 2u ? 1u : 0u;
+                        const int64_t o = (r0 + rr) * K + k0 + 2 * cc;
+                        U[o] = (int8_t)(code == 0u);
+                        U[o + 1] = (int8_t)(code == 1u);
+                        Wd[o] = (int8_t)((code == 0u) + nl);
+                        Wd[o + 1] = (int8_t)((code == 1u) + nl);
+                        cnt += (int)nl;
+                    }
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                if ((tid & 31) == 0 && rr < nrows && cnt) atomicAdd(&srow[r0 + rr], cnt);
+            }
+        }
+    }
+    // ---- step 3: the two At rows and the codesT row of each column, 16 samples per store
+    if (At != nullptr) {
+        for (int item = tid; item < ncols * 8; item += 256) {
+            const int cc = item >> 3, seg = item & 7;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&code_cr[cc][16 * seg]);
+            const uint4 w = make_uint4(src[0], src[1], src[2], src[3]);
+            uint4 e0, e1;
+            e1.x = w.x & 0x01010101u; e0.x = ((w.x >> 1) & 0x01010101u) ^ 0x01010101u ^ e1.x;
+            e1.y = w.y & 0x01010101u; e0.y = ((w.y >> 1) & 0x01010101u) ^ 0x01010101u ^ e1.y;
+            e1.z = w.z & 0x01010101u; e0.z = ((w.z >> 1) & 0x01010101u) ^ 0x01010101u ^ e1.z;
+            e1.w = w.w & 0x01010101u; e0.w = ((w.w >> 1) & 0x01010101u) ^ 0x01010101u ^ e1.w;
+            const int64_t o = r0 + 16 * seg;                                  // r0, ldt multiples of 128: aligned
+            int8_t *a0 = At + (k0 + 2 * cc) * ldt + o, *a1 = a0 + ldt;
+            uint8_t *ct = codesT + (c0 + cc) * ldt + o;
+            if (16 * seg + 16 <= nrows) {
+                *reinterpret_cast<uint4 *>(a0) = e0;
+                *reinterpret_cast<uint4 *>(a1) = e1;
+                *reinterpret_cast<uint4 *>(ct) = w;
+            } else {
+                for (int b = 0; b < 16 && 16 * seg + b < nrows; ++b) {
+                    const uint32_t code = code_cr[cc][16 * seg + b];
+                    a0[b] = (int8_t)(code == 0u);
+                    a1[b] = (int8_t)(code == 1u);
+                    ct[b] = (uint8_t)code;
+                }
+            }
+        }
+    }
+}
+
 // Distance operands (Ur, Wdr, srow_r) of the columns removed since the cached slab was built.
 static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
     Trace tr("    build_removed");
@@ -378,9 +521,17 @@ static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
         FS_CUDA(cudaMemset2DAsync(ws.Ur.ptr + ws.Kr_used, (size_t)ws.Kr, 0, (size_t)(ws.Kr - ws.Kr_used), (size_t)n, st));
         FS_CUDA(cudaMemset2DAsync(ws.Wdr.ptr + ws.Kr_used, (size_t)ws.Kr, 0, (size_t)(ws.Kr - ws.Kr_used), (size_t)n, st));
     }
-    dim3 grid((unsigned)ceil_div(pr, ENC_COLS), (unsigned)ceil_div(n, ENC_ROWS));
+    const unsigned grid = (unsigned)(ceil_div(pr, ENC_COLS) * ceil_div(n, ENC_ROWS));
     const int as_f32 = (ds->arith == FS_ARITH_F32 && ds->dtype == FS_F64) ? 1 : 0;
     const int all_ident = (ident & kColIdent) ? 1 : 0;
+    if (all_ident && ws.Kr_used == 2 * pr) {
+        onehot_encode_v3_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(ds->x), ds->ldx, ds->d_perm.ptr,
+                                                      ws.rcol.ptr, n, pr, ws.Kr, ws.ldt, 0, ws.Ur.ptr, ws.Wdr.ptr, nullptr,
+                                                      nullptr, nullptr, ws.srow_r.ptr, nullptr);
+        FS_CUDA(cudaGetLastError());
+        ++*launches;
+        return;
+    }
 #define FS_ENCODE_R(T)                                                                                            \
     onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,        \
                                                   ws.rcol.ptr, ws.roff.ptr, ds->d_vals.ptr, as_f32, n, pr, ws.Kr, \
@@ -432,9 +583,21 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
         }
         FS_CUDA(cudaMemsetAsync(ws.At.ptr + (size_t)ws.K_used * ws.ldt, 0, (size_t)(ws.K - ws.K_used) * ws.ldt, st));
     }
-    dim3 grid((unsigned)ceil_div(pt, ENC_COLS), (unsigned)ceil_div(n, ENC_ROWS));
+    const unsigned grid = (unsigned)(ceil_div(pt, ENC_COLS) * ceil_div(n, ENC_ROWS));
     const int as_f32 = (ds->arith == FS_ARITH_F32 && ds->dtype == FS_F64) ? 1 : 0;
     const int all_ident = ws.all_ident ? 1 : 0;
+    if (ws.all_ident && ws.K_used == 2 * pt) {
+        // every active column holds exactly the byte values 0/1/2: lean kernel
+        onehot_encode_v3_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(ds->x), ds->ldx, ds->d_perm.ptr,
+                                                      ws.tcol.ptr, n, pt, ws.K, ws.ldt, ws.ldc, ops ? ws.U.ptr : nullptr,
+                                                      ops ? ws.Wd.ptr : nullptr, ws.At.ptr, ws.codesT.ptr,
+                                                      ws.have_codes ? ws.codes.ptr : nullptr,
+                                                      ops ? ws.srow.ptr : nullptr, ws.krow.ptr);
+        FS_CUDA(cudaGetLastError());
+        ++*launches;
+        if (ws.dist_mode == kDistIncremental) build_removed(ds, ws, launches);
+        return;
+    }
 #define FS_ENCODE(T)                                                                                             \
     onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,       \
                                                   ws.tcol.ptr, ws.toff.ptr, ds->d_vals.ptr, as_f32, n, pt, ws.K, \

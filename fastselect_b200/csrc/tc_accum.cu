@@ -80,7 +80,7 @@ __device__ __forceinline__ double i2d(int x) {
 __global__ void __launch_bounds__(THREADS, 1)
 tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_constant__ CUtensorMap tmap_mh,
                 const __grid_constant__ CUtensorMap tmap_mm, int num_k_blocks, int64_t R,
-                const TileDesc *__restrict__ tiles, int num_tiles, int groups, int m_blocks,
+                const TileDesc *__restrict__ tiles, int num_tiles, int groups, int group_tiles, int m_blocks,
                 const int64_t *__restrict__ ids, int contiguous, const RowInfo *__restrict__ rinfo,
                 const uint8_t *__restrict__ codesT, int64_t ldt, const uint32_t *__restrict__ krow, int64_t K_rows,
                 double *__restrict__ tpartial) {
@@ -127,8 +127,8 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
             int it = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 const int m0 = (u / groups) * BM, g = u % groups;
-                const int tile_end = (g + 1) * GROUP < num_tiles ? (g + 1) * GROUP : num_tiles;
-                for (int t = g * GROUP; t < tile_end; ++t) {
+                const int tile_end = (g + 1) * group_tiles < num_tiles ? (g + 1) * group_tiles : num_tiles;
+                for (int t = g * group_tiles; t < tile_end; ++t) {
                     const TileDesc d = s_tiles[t];
                     for (int phase = 0; phase < 2; ++phase) {
                         const CUtensorMap *tm = phase == 0 ? &tmap_mh : &tmap_mm;
@@ -154,13 +154,14 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = tc::make_idesc_i8(BM, BN);
             int it = 0, item = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 const int g = u % groups;
-                const int tile_end = (g + 1) * GROUP < num_tiles ? (g + 1) * GROUP : num_tiles;
-                for (int t = g * GROUP; t < tile_end; ++t) {
+                const int tile_end = (g + 1) * group_tiles < num_tiles ? (g + 1) * group_tiles : num_tiles;
+                for (int t = g * group_tiles; t < tile_end; ++t) {
                     const TileDesc d = s_tiles[t];
+                    // a partial tile (class tail) only needs N = its row count rounded up to 16
+                    const uint32_t idesc = tc::make_idesc_i8(BM, ((d.rows + 15) >> 4) << 4);
                     for (int phase = 0; phase < 2; ++phase) {
                         const int nblk = phase == 0 ? d.hb1 - d.hb0 : d.ib0 + (num_k_blocks - d.ib1);
                         if (nblk == 0) continue;                          // mask is all zero: nothing to add
@@ -203,7 +204,7 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
         int item = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const int g = u % groups;
-            const int tile_end = (g + 1) * GROUP < num_tiles ? (g + 1) * GROUP : num_tiles;
+            const int tile_end = (g + 1) * group_tiles < num_tiles ? (g + 1) * group_tiles : num_tiles;
             const int64_t mrow = (int64_t)(u / groups) * BM + et;
             const bool row_live = mrow < K_rows;
             // this one-hot row's column (codesT row), value code and the column's last code
@@ -212,7 +213,7 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
             const uint32_t own4 = ((meta >> 24) & 0xfu) * 0x01010101u;
             const uint32_t last4 = (meta >> 28) * 0x01010101u;
             double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-            for (int t = g * GROUP; t < tile_end; ++t) {
+            for (int t = g * group_tiles; t < tile_end; ++t) {
                 const TileDesc d = s_tiles[t];
                 // value codes of this thread's 128 targets in its column (issued before the
                 // accumulator wait so the loads overlap the MMAs); shared by both phases.
@@ -322,7 +323,7 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
 // Host plan: class-aligned tiles of <= 256 target rows and the K blocks their masks need.
 struct AccumPlan {
     std::vector<TileDesc> tiles;
-    int64_t blocks = 0;      // K blocks contracted per one-hot row block (both phases, all tiles)
+    double blocks = 0;       // K blocks contracted per one-hot row block (both phases, all tiles), in units of full 256-column tiles
 };
 
 static AccumPlan make_plan(int64_t n, int64_t R, bool contiguous, const int64_t *h_ids, const int32_t *h_y,
@@ -343,7 +344,7 @@ static AccumPlan make_plan(int64_t n, int64_t R, bool contiguous, const int64_t 
             d.ib1 = he == n ? nkb : (int32_t)(he / BK);
             if (d.ib1 < d.ib0) d.ib1 = d.ib0;
         }
-        plan.blocks += (d.hb1 - d.hb0) + d.ib0 + (nkb - d.ib1);
+        plan.blocks += (double)((d.hb1 - d.hb0) + d.ib0 + (nkb - d.ib1)) * (double)(((rows + 15) >> 4) << 4) / BN;
         plan.tiles.push_back(d);
     };
     if (!contiguous) {
@@ -384,20 +385,22 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
     // at most MAX_TILES tile descriptors per launch
     for (size_t t0 = 0; t0 < plan.tiles.size(); t0 += MAX_TILES) {
         const int nt = (int)std::min<size_t>(MAX_TILES, plan.tiles.size() - t0);
+        // equal-sized groups (work units are dealt round-robin: unequal units would unbalance the SMs)
         const int groups = (int)ceil_div(nt, GROUP);
+        const int group_tiles = (int)ceil_div(nt, groups);
         // pageable source: the copy is staged before cudaMemcpyAsync returns
         FS_CUDA(cudaMemcpyAsync(d_tiles, plan.tiles.data() + t0, nt * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
         const int units = m_blocks * groups;
         const int grid = units < sms ? units : sms;
         tc_accum_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(
             tmap_at, tmap_mh, tmap_mm, (int)ceil_div(n, BK), R, reinterpret_cast<const TileDesc *>(d_tiles), nt,
-            groups, m_blocks, d_ids, contiguous ? 1 : 0, rinfo, codesT, ldt, krow, K_rows,
+            groups, group_tiles, m_blocks, d_ids, contiguous ? 1 : 0, rinfo, codesT, ldt, krow, K_rows,
             tpartial + (size_t)groups_done * 2 * K_rows);
         FS_CUDA(cudaGetLastError());
         ++*launches;
         groups_done += groups;
     }
-    if (ops) *ops += 2.0 * BM * BN * BK * (double)plan.blocks * (double)m_blocks;
+    if (ops) *ops += 2.0 * BM * BN * BK * plan.blocks * (double)m_blocks;
     return 2 * groups_done;
 }
 
