@@ -25,8 +25,8 @@
 // and one 256-column TMEM accumulator each (double-buffered, so the epilogue of one item
 // overlaps the MMAs of the next).  Warp 0: TMA producer (At tile +
 // mask tile per K block of 128 samples, 128B swizzle, 4-stage mbarrier ring); warp 1:
-// one thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=256, K=32); warps 2-9
-// (lane quarter x column half): epilogue -- tcgen05.ld the accumulator, test the target's
+// one thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=256, K=32); warps 2-17
+// (lane quarter x column quarter): epilogue -- tcgen05.ld the accumulator, test the target's
 // own value code (codesT), scale, and add into float64 registers per one-hot row;
 // the reduction over a tile's targets is a loop over TMEM columns inside one thread.
 // The epilogue is the critical path next to the MMAs: int32 -> float64 goes through an
@@ -53,12 +53,15 @@ constexpr int B_BYTES = BN * BK;                  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 48 KB
 constexpr int GROUP = 8;                          // target tiles per work unit
 constexpr int MAX_TILES = 256;                    // tile descriptors per launch (staged in shared memory)
-constexpr int CONST_BYTES = 2 * BN * 16;          // [2][BN] x {double c; int rs; int pad}
+constexpr int CONST_BYTES = 2 * BN * 16;          // [2][BN] x {int2 coefficient limbs; int rs; int pad}
 constexpr int DESC_BYTES = MAX_TILES * 32;
 constexpr int BAR_BYTES = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + CONST_BYTES + DESC_BYTES;
-constexpr int THREADS = 320;              // TMA warp, MMA warp, 8 epilogue warps
-constexpr int HALF = BN / 2;              // target columns per epilogue thread
+constexpr int EPI_WARPS = 16;            // epilogue warps: 4 per TMEM lane quarter, one column quarter each
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = 64 + EPI_THREADS; // TMA warp, MMA warp, epilogue warps
+constexpr int HALF = BN / (EPI_WARPS / 4); // target columns per epilogue thread
+constexpr int PARTS = EPI_WARPS / 4;      // column parts = partial vectors per (group, one-hot row)
 constexpr int TMEM_COLS = 512;                    // 2 accumulator buffers x 256 columns
 
 // A tile of target rows and the K blocks (of 128 samples) its two masks can be non-zero in:
@@ -70,10 +73,16 @@ struct __align__(16) TileDesc {
 };
 static_assert(sizeof(TileDesc) == 32, "TileDesc layout");
 
-// exact int32 -> float64 without the XU pipe: the double with high word 0x43300000 and low
-// word (x + 2^31) is 2^52 + 2^31 + x
-__device__ __forceinline__ double i2d(int x) {
-    return __hiloint2double(0x43300000, (int)((unsigned)x ^ 0x80000000u)) - 4503601774854144.0;
+// Fixed-point image of a per-target coefficient c (|c| <= 1): C = round(c * 2^52) split into a
+// signed high limb and a 26-bit low limb, so that c * t for an integer t is accumulated EXACTLY
+// in two int64 sums (sum t*Chi, sum t*Clo) with integer multiply-adds.  No float64 instruction
+// is left in the epilogue's inner loop: on B200 DADD/DFMA and the tensor pipe could not be kept
+// busy at the same time (ncu: math-pipe throttle on every FP64 instruction while the MMA issuer
+// waited for the epilogue; FP64 time and MMA time added up instead of overlapping).
+constexpr int kCoefBits = 52, kLimbBits = 26;
+__device__ __forceinline__ int2 coef_limbs(double c) {
+    const long long C = __double2ll_rn(c * 4503599627370496.0);       // 2^52
+    return make_int2((int)(C >> kLimbBits), (int)(C & ((1LL << kLimbBits) - 1)));
 }
 }  // namespace
 
@@ -111,7 +120,7 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
         }
         for (int b = 0; b < 2; ++b) {
             tc::mbar_init(&tfull_bar[b], 1);
-            tc::mbar_init(&tempty_bar[b], 256);           // all epilogue threads arrive
+            tc::mbar_init(&tempty_bar[b], EPI_THREADS);   // all epilogue threads arrive
         }
         tc::fence_barrier_init();
     }
@@ -194,12 +203,12 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
             }
         }
     } else {
-        // ===== epilogue (warps 2..9: lane quarter = warp % 4, column half = (warp - 2) / 4) =====
-        // thread = one-hot row (TMEM lane) x half of the work item's 256 target columns
+        // ===== epilogue (warps 2..: lane quarter = warp % 4, column part = (warp - 2) / 4) =====
+        // thread = one-hot row (TMEM lane) x one part of the work item's 256 target columns
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         const int et = q * 32 + lane;                         // 0..127: TMEM lane / local one-hot row
-        const int ethread = (warp - 2) * 32 + lane;           // 0..255
+        const int ethread = (warp - 2) * 32 + lane;           // 0..EPI_THREADS-1
         const int64_t ids0 = contiguous ? ids[0] : 0;
         int item = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -212,7 +221,7 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
             const uint8_t *at_row = codesT + (int64_t)(meta & 0xffffffu) * ldt;
             const uint32_t own4 = ((meta >> 24) & 0xfu) * 0x01010101u;
             const uint32_t last4 = (meta >> 28) * 0x01010101u;
-            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+            long long ah0 = 0, ah1 = 0, al0 = 0, al1 = 0;     // exact fixed-point sums (two chains)
             for (int t = g * group_tiles; t < tile_end; ++t) {
                 const TileDesc d = s_tiles[t];
                 // value codes of this thread's 128 targets in its column (issued before the
@@ -262,10 +271,11 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                     const int buf = item & 1;
                     const uint32_t tph = (item >> 1) & 1;
                     ++item;
-                    // per-target constants: c = -aH (hit phase) or +aM (miss phase); rs = mask row sum
-                    double *s_c = reinterpret_cast<double *>(s_const + buf * BN * 16);
+                    // per-target constants: c = -aH (hit phase) or +aM (miss phase) as fixed-point
+                    // limbs; rs = mask row sum
+                    int2 *s_c = reinterpret_cast<int2 *>(s_const + buf * BN * 16);
                     int32_t *s_rs = reinterpret_cast<int32_t *>(s_const + buf * BN * 16 + BN * 8);
-                    {
+                    if (ethread < BN) {
                         double c = 0.0;
                         int rs = 0;
                         if (ethread < d.rows) {
@@ -273,10 +283,10 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                             c = phase == 0 ? ri.coef[FS_MASK_NEAR_HIT] : ri.coef[FS_MASK_NEAR_MISS];
                             rs = phase == 0 ? ri.n_hit - ri.n_far_hit : ri.n_miss - ri.n_far_miss;
                         }
-                        s_c[ethread] = c;
+                        s_c[ethread] = coef_limbs(c);
                         s_rs[ethread] = rs;
                     }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                     tc::mbar_wait(&tfull_bar[buf], tph);
                     tc::tc_fence_after();
                     const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * HALF);
@@ -285,32 +295,36 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                         uint32_t v[32];
                         tc::tmem_ld_32x32(tacc + c0, v);
                         tc::tmem_ld_wait();
-                        const double2 *cc = reinterpret_cast<const double2 *>(s_c + half * HALF + c0);
+                        const int4 *cc = reinterpret_cast<const int4 *>(s_c + half * HALF + c0);
                         const int4 *rr = reinterpret_cast<const int4 *>(s_rs + half * HALF + c0);
 #pragma unroll
                         for (int e = 0; e < 32; e += 4) {
                             const uint32_t w = oh[(c0 + e) >> 2];
                             const uint32_t own = __vcmpeq4(w, own4), lst = __vcmpeq4(w, last4);
                             const int4 rs4 = rr[e >> 2];
-                            const double2 ca = cc[e >> 1], cb = cc[(e >> 1) + 1];
-                            // t = own ? rs - G : (last ? G : 0); four independent float64 chains
+                            const int4 ca = cc[e >> 1], cb = cc[(e >> 1) + 1];   // (Chi, Clo) of two targets each
+                            // t = own ? rs - G : (last ? G : 0)
                             const int g0 = (int)v[e], g1 = (int)v[e + 1], g2 = (int)v[e + 2], g3 = (int)v[e + 3];
                             const int t0 = (own & 0x000000ffu) ? rs4.x - g0 : ((lst & 0x000000ffu) ? g0 : 0);
                             const int t1 = (own & 0x0000ff00u) ? rs4.y - g1 : ((lst & 0x0000ff00u) ? g1 : 0);
                             const int t2 = (own & 0x00ff0000u) ? rs4.z - g2 : ((lst & 0x00ff0000u) ? g2 : 0);
                             const int t3 = (own & 0xff000000u) ? rs4.w - g3 : ((lst & 0xff000000u) ? g3 : 0);
-                            acc0 = fma(ca.x, i2d(t0), acc0);
-                            acc1 = fma(ca.y, i2d(t1), acc1);
-                            acc2 = fma(cb.x, i2d(t2), acc2);
-                            acc3 = fma(cb.y, i2d(t3), acc3);
+                            ah0 += (long long)t0 * ca.x; al0 += (long long)t0 * ca.y;
+                            ah1 += (long long)t1 * ca.z; al1 += (long long)t1 * ca.w;
+                            ah0 += (long long)t2 * cb.x; al0 += (long long)t2 * cb.y;
+                            ah1 += (long long)t3 * cb.z; al1 += (long long)t3 * cb.w;
                         }
                     }
                     tc::tc_fence_before();
                     tc::mbar_arrive(&tempty_bar[buf]);
                 }
             }
-            // two column halves per one-hot row: partial layout [group][half][row]
-            if (row_live) tpartial[((int64_t)g * 2 + half) * K_rows + mrow] = (acc0 + acc1) + (acc2 + acc3);
+            // PARTS column parts per one-hot row: partial layout [group][part][row]
+            // |t| <= n < 2^22 (checked by the launcher), limbs < 2^27, at most 2^11 terms per thread
+            // and unit: the sums stay below 2^60
+            if (row_live)
+                tpartial[((int64_t)g * PARTS + half) * K_rows + mrow] =
+                    ((double)(ah0 + ah1) * (double)(1 << kLimbBits) + (double)(al0 + al1)) * (1.0 / 4503599627370496.0);
         }
     }
     __syncthreads();
@@ -362,14 +376,14 @@ static AccumPlan make_plan(int64_t n, int64_t R, bool contiguous, const int64_t 
     return plan;
 }
 
-// partial vectors written per launch: (tile groups) x (2 column halves); an upper bound that
+// partial vectors written per launch: (tile groups) x (PARTS column parts); an upper bound that
 // does not depend on the class layout (every class adds at most one partial tile)
 int tc_accum_groups(int64_t R, int n_classes) {
     const int64_t tiles = ceil_div(R, BN) + n_classes;
-    return 2 * (int)(ceil_div(tiles, GROUP) + ceil_div(tiles, MAX_TILES));
+    return PARTS * (int)(ceil_div(tiles, GROUP) + ceil_div(tiles, MAX_TILES));
 }
 
-// Returns the number of partial vectors written ([groups x 2 halves][K_rows] doubles).
+// Returns the number of partial vectors written ([groups x PARTS][K_rows] doubles).
 int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
                     int64_t R, const int64_t *d_ids, bool contiguous, const RowInfo *rinfo, const uint8_t *codesT,
                     int64_t ldt, const uint32_t *krow, int64_t K_rows, double *tpartial, int32_t *d_tiles,
@@ -379,6 +393,7 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
     int dev = 0, sms = 0;
     FS_CUDA(cudaGetDevice(&dev));
     FS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FS_REQUIRE(n < (1LL << 22), FS_ERR_INVALID, "one-hot accumulation supports up to 2^22 samples (got %lld)", (long long)n);
     const AccumPlan plan = make_plan(n, R, contiguous, h_ids, h_y, h_cls_start);
     const int m_blocks = (int)ceil_div(K_rows, BM);
     int groups_done = 0;
@@ -395,13 +410,13 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
         tc_accum_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(
             tmap_at, tmap_mh, tmap_mm, (int)ceil_div(n, BK), R, reinterpret_cast<const TileDesc *>(d_tiles), nt,
             groups, group_tiles, m_blocks, d_ids, contiguous ? 1 : 0, rinfo, codesT, ldt, krow, K_rows,
-            tpartial + (size_t)groups_done * 2 * K_rows);
+            tpartial + (size_t)groups_done * PARTS * K_rows);
         FS_CUDA(cudaGetLastError());
         ++*launches;
         groups_done += groups;
     }
     if (ops) *ops += 2.0 * BM * BN * BK * plan.blocks * (double)m_blocks;
-    return 2 * groups_done;
+    return PARTS * groups_done;
 }
 
 int tc_accum_tile_desc_ints() { return MAX_TILES * (int)(sizeof(TileDesc) / sizeof(int32_t)); }
