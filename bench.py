@@ -274,7 +274,8 @@ def own_arm(args):
     x_pinned = torch.from_numpy(w["x"]).pin_memory()
     x_in = x_pinned.numpy()
     sess, _ = est._open_session(x_in, w["y"])
-    lo, hi = shard_rows(n, world, rank)
+    lo, hi = shard_rows(n, world, rank, sess.row_align)
+    sess_peers = bool(sess.peers)
     buf = torch.empty(p, dtype=torch.float64, device="cuda")
     last_stats = {}
 
@@ -391,7 +392,7 @@ def own_arm(args):
             "vs_baseline": None, "dtype": "u8 one-hot / int32 accum (genotype), f32 terms + f64 accum (continuous)",
             "data": "synthetic",
             "config": {"workload": w["desc"], "n": n, "p": p, "algo": w["algo"] + ("*" if w["star"] else ""),
-                       "rows_per_gpu": rows, "sharding": f"target rows x{world}, one NCCL allreduce",
+                       "rows_per_gpu": rows, "sharding": f"target rows x{world}, one NCCL allreduce" + (", symmetric distances via NVLink peer stores" if sess_peers else ""),
                        "l2": "inputs larger than L2 (no flush needed)", "step": "encode + distances + select + accumulate"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -14,7 +14,7 @@ FS_RELIEFF, FS_SURF, FS_MULTISURF = 0, 1, 2
 FS_U8, FS_I8, FS_F32, FS_F64 = 0, 1, 2, 3
 FS_ARITH_F32, FS_ARITH_F64 = 0, 1
 FS_DISTINCT_CAP = 16
-FS_ABI_VERSION = 2
+FS_ABI_VERSION = 3
 
 _DTYPES = {np.dtype(np.uint8): FS_U8, np.dtype(np.int8): FS_I8,
            np.dtype(np.float32): FS_F32, np.dtype(np.float64): FS_F64}
@@ -35,6 +35,9 @@ class FsStats(C.Structure):
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
+
+# barrier(ctx) callback of fs_dataset_set_peers
+BARRIER_FN = C.CFUNCTYPE(None, C.c_void_p)
 
 _lib = None
 
@@ -61,6 +64,8 @@ def load():
     lib.fs_dataset_row_order.argtypes = [vp, vp]
     lib.fs_score.argtypes = [vp, C.c_int, C.c_int, i32, vp, vp, i64, i64, i64, vp, C.c_int, C.POINTER(FsStats)]
     lib.fs_debug_rows.argtypes = [vp, C.c_int, C.c_int, i32, vp, vp, i64, vp, i64, vp, vp, vp, vp]
+    lib.fs_dataset_peer_slab.argtypes = [vp, i64, vp, C.POINTER(vp)]
+    lib.fs_dataset_set_peers.argtypes = [vp, i32, i32, vp, vp, vp, BARRIER_FN, vp]
     if lib.fs_abi_version() != FS_ABI_VERSION:
         raise RuntimeError(f"fastselect_b200: {LIB_PATH} has ABI version {lib.fs_abi_version()}, "
                            f"this package needs {FS_ABI_VERSION}; rebuild it (make -C fastselect_b200/csrc)")
@@ -159,6 +164,29 @@ class Dataset:
         rc = load().fs_dataset_set_features(self._h, _ptr(is_discrete), _ptr(recip), int(arith))
         if rc != 0:
             _raise(rc, "fs_dataset_set_features")
+
+    def peer_slab(self, rows):
+        """Allocate this rank's exportable distance slab; returns (64-byte IPC handle, device pointer)."""
+        handle = np.zeros(64, np.uint8)
+        ptr = C.c_void_p()
+        rc = load().fs_dataset_peer_slab(self._h, int(rows), _ptr(handle), C.byref(ptr))
+        if rc != 0:
+            _raise(rc, "fs_dataset_peer_slab")
+        return handle, ptr.value
+
+    def set_peers(self, rank, world, row_starts, handles=None, raw_ptrs=None, barrier=None):
+        """Configure multi-GPU symmetric distances (see include/fastselect_b200.h).  ``barrier`` is a
+        Python callable; it is kept alive on this object for as long as the data set is open."""
+        starts = np.ascontiguousarray(row_starts, np.int64)
+        self._barrier_cb = BARRIER_FN(lambda _ctx: barrier())
+        hs = None if handles is None else np.ascontiguousarray(handles, np.uint8)
+        rp = None
+        if raw_ptrs is not None:
+            rp = (C.c_void_p * world)(*[C.c_void_p(int(q)) for q in raw_ptrs])
+        rc = load().fs_dataset_set_peers(self._h, int(rank), int(world), _ptr(starts), _ptr(hs), rp,
+                                         self._barrier_cb, None)
+        if rc != 0:
+            _raise(rc, "fs_dataset_set_peers")
 
     def row_order(self):
         perm = np.empty(self.n, np.int64)

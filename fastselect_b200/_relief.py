@@ -16,7 +16,7 @@ from sklearn.base import BaseEstimator, TransformerMixin
 from sklearn.utils.validation import check_is_fitted, validate_data
 
 from . import _native
-from ._shard import score_sharded
+from ._shard import score_sharded, setup_peers
 
 _NO_GPU_MULTISURF = ("backend='gpu' was selected, but no compatible "
                      "NVIDIA GPU was found or CUDA toolkit is not installed.")       # MultiSURF.py:399-403
@@ -71,6 +71,10 @@ class _Session:
         self.is_discrete, self.recip, self.arith = is_discrete, recip, arith
         self.ds.set_features(is_discrete, recip, arith)
         self.last_stats = None
+        # one process per GPU: shard starts are multiples of 4 and, where the GPUs can map each
+        # other's memory, distances are computed symmetrically across ranks (_shard.setup_peers)
+        self.row_align = 4
+        self.peers = setup_peers(self.ds, self.n, self.row_align)
 
     def score(self, feat_idx=None, want_stats=False):
         n_kept = self.p if feat_idx is None else len(feat_idx)
@@ -82,7 +86,7 @@ class _Session:
                 res, self.last_stats = res
             return res
 
-        wsum = score_sharded(self.n, n_kept, score_rows, device_buffers=True)
+        wsum = score_sharded(self.n, n_kept, score_rows, device_buffers=True, align=self.row_align)
         # "/ n_samples" of the reference host callers (MultiSURF.py:162, SURF.py:128, ReliefF.py:134)
         return (wsum / self.n).astype(np.float32)
 

@@ -12,14 +12,25 @@ from __future__ import annotations
 import numpy as np
 
 
-def shard_rows(n: int, world_size: int, rank: int) -> tuple[int, int]:
-    """Contiguous, balanced partition of ``range(n)``: rank r gets ``[lo, hi)``."""
+def shard_rows(n: int, world_size: int, rank: int, align: int = 1) -> tuple[int, int]:
+    """Contiguous, balanced partition of ``range(n)``: rank r gets ``[lo, hi)``.  With
+    ``align`` > 1 every boundary but the last is rounded down to a multiple of it (the
+    multi-GPU symmetric distance kernel wants shard starts that are multiples of 4)."""
     if world_size < 1 or not 0 <= rank < world_size:
         raise ValueError(f"bad rank/world_size {rank}/{world_size}")
     base, extra = divmod(n, world_size)
-    lo = rank * base + min(rank, extra)
-    hi = lo + base + (1 if rank < extra else 0)
-    return lo, hi
+
+    def start(r):
+        if r >= world_size:
+            return n
+        return (r * base + min(r, extra)) // align * align
+
+    return start(rank), start(rank + 1)
+
+
+def shard_starts(n: int, world_size: int, align: int = 1) -> list[int]:
+    """``[lo_0, lo_1, ..., lo_{world-1}, n]`` of :func:`shard_rows`."""
+    return [shard_rows(n, world_size, r, align)[0] for r in range(world_size)] + [n]
 
 
 def dist_info() -> tuple[int, int]:
@@ -45,14 +56,59 @@ def allreduce_sum_numpy(partial: np.ndarray) -> np.ndarray:
     return t.cpu().numpy()
 
 
-def score_sharded(n: int, n_kept: int, score_rows, device_buffers: bool):
+def setup_peers(ds, n: int, align: int = 4) -> bool:
+    """Multi-GPU symmetric distances for one open data set: exchange the ranks' slab handles
+    (one all_gather) and hand the library a cross-rank barrier.  Returns False (and leaves the
+    plain row-sharded path in place) when there is a single rank, no NCCL, or no peer access."""
+    rank, world = dist_info()
+    if world == 1:
+        return False
+    import torch
+    import torch.distributed as dist
+
+    if dist.get_backend() != "nccl" or world > 16:
+        return False
+    starts = shard_starts(n, world, align)
+    ok = torch.ones(1, dtype=torch.int32, device="cuda")
+    handles = torch.zeros(world * 64, dtype=torch.uint8, device="cuda")
+    try:
+        handle, _ = ds.peer_slab(starts[rank + 1] - starts[rank])
+        mine = torch.from_numpy(handle).cuda()
+    except Exception:
+        ok.zero_()
+        mine = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    dist.all_gather_into_tensor(handles, mine)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 0:
+        return False
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    try:
+        ds.set_peers(rank, world, starts, handles=handles.cpu().numpy(), barrier=barrier)
+    except Exception:
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)      # all ranks or none: the barrier inside fs_score must match
+    if int(ok.item()) == 0:
+        # some rank could not map its peers: every rank falls back to the unsymmetric path
+        try:
+            ds.set_peers(rank, 1, [0, n], raw_ptrs=[0], barrier=lambda: None)
+        except Exception:
+            pass
+        return False
+    return True
+
+
+def score_sharded(n: int, n_kept: int, score_rows, device_buffers: bool, align: int = 1):
     """Run ``score_rows(lo, hi, out_device_ptr)`` on this rank's target rows and return
     the allreduced float64 weight sums.
 
     ``score_rows`` returns a float64 numpy vector when ``out_device_ptr`` is None and
     writes the device buffer otherwise (fastselect_b200._native.Dataset.score)."""
     rank, world = dist_info()
-    lo, hi = shard_rows(n, world, rank)
+    lo, hi = shard_rows(n, world, rank, align)
     if world == 1:
         return score_rows(lo, hi, None)
     if device_buffers:

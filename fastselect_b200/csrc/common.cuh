@@ -144,6 +144,16 @@ enum : unsigned { kColContinuous = 0, kColTensor = 1, kColCompare = 2, kColConst
 // d_ij -= sum over removed f of [x_if != x_jf], exact integers), or reused as it is.
 enum DistMode : int { kDistFull = 0, kDistIncremental = 1, kDistReuse = 2 };
 
+// Who owns which target rows (one process per GPU) and where their distance slabs live; passed
+// by value to the distance kernel.  A single rank is the trivial case {starts = {0, n}}.
+constexpr int kMaxRanks = 16;
+struct DistPeers {
+    int32_t *slab[kMaxRanks];       // [world] distance slab of every rank (own: local; others: CUDA IPC mappings)
+    int64_t starts[kMaxRanks + 1];  // [world + 1] first target row (internal order) of every rank's shard
+    int32_t sb_base[kMaxRanks + 1]; // [world + 1] running count of 256-row super-blocks of the shards
+    int32_t world, rank;
+};
+
 // Working set of one fs_score call: the active columns split by path.
 struct WorkSet {
     // general (CUDA-core) path
@@ -232,6 +242,17 @@ struct fs_dataset {
     bool dd_valid = false;
     std::vector<int64_t> dd_cols;
     int64_t dd_r0 = -1, dd_R = -1;
+    const int32_t *dd_buf = nullptr;
+    // multi-GPU symmetric distances (fs_dataset_set_peers): this rank's IPC-exportable slab, the
+    // peers' mapped slabs, and the cross-rank barrier called between distances and selection
+    fs::DistPeers peers{};
+    bool peers_on = false;
+    int32_t *peer_slab = nullptr;
+    size_t peer_slab_count = 0;
+    std::vector<void *> peer_mapped;         // cudaIpcOpenMemHandle results (to close)
+    void (*barrier_fn)(void *) = nullptr;
+    void *barrier_ctx = nullptr;
+    bool last_dist_exchanged = false;        // the last distance launch stored into peer slabs
     fs::DevBuf<int8_t> sel;       // [R, ldn] neighbour codes
     fs::DevBuf<fs::RowInfo> rinfo;
     fs::DevBuf<int64_t> row_ids;

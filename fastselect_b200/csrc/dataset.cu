@@ -634,10 +634,92 @@ int fs_dataset_row_order(const fs_dataset *ds, int64_t *perm_out) {
     return FS_OK;
 }
 
+int fs_dataset_peer_slab(fs_dataset *ds, int64_t rows, void *ipc_handle_out, void **dev_ptr_out) {
+    try {
+        FS_REQUIRE(ds && rows >= 0, FS_ERR_INVALID, "fs_dataset_peer_slab: invalid argument");
+        FS_CUDA(cudaSetDevice(ds->device));
+        const size_t count = (size_t)round_up(std::max<int64_t>(rows, 1), 128) * (size_t)round_up(ds->n, 128);
+        if (ds->peer_slab == nullptr || ds->peer_slab_count < count) {
+            FS_REQUIRE(!ds->peers_on, FS_ERR_STATE, "fs_dataset_peer_slab: peers already configured");
+            if (ds->peer_slab) cudaFree(ds->peer_slab);
+            ds->peer_slab = nullptr;
+            // plain cudaMalloc: stream-ordered pool memory cannot be exported through CUDA IPC
+            FS_CUDA(cudaMalloc(reinterpret_cast<void **>(&ds->peer_slab), count * sizeof(int32_t)));
+            ds->peer_slab_count = count;
+        }
+        if (ipc_handle_out) {
+            cudaIpcMemHandle_t h;
+            FS_CUDA(cudaIpcGetMemHandle(&h, ds->peer_slab));
+            static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+            memcpy(ipc_handle_out, &h, sizeof(h));
+        }
+        if (dev_ptr_out) *dev_ptr_out = ds->peer_slab;
+        return FS_OK;
+    } catch (const Fail &f) {
+        return f.code;
+    }
+}
+
+int fs_dataset_set_peers(fs_dataset *ds, int32_t rank, int32_t world, const int64_t *row_starts,
+                         const void *ipc_handles, void *const *raw_ptrs, void (*barrier)(void *), void *barrier_ctx) {
+    try {
+        FS_REQUIRE(ds && row_starts && barrier, FS_ERR_INVALID, "fs_dataset_set_peers: null pointer");
+        FS_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, FS_ERR_INVALID,
+                   "fs_dataset_set_peers: bad rank/world %d/%d (at most %d ranks)", rank, world, kMaxRanks);
+        FS_REQUIRE(ipc_handles || raw_ptrs, FS_ERR_INVALID, "fs_dataset_set_peers: no handles");
+        FS_REQUIRE(ds->peer_slab != nullptr, FS_ERR_STATE, "fs_dataset_set_peers: call fs_dataset_peer_slab first");
+        FS_REQUIRE(row_starts[0] == 0 && row_starts[world] == ds->n, FS_ERR_INVALID,
+                   "fs_dataset_set_peers: row_starts must run from 0 to n");
+        FS_CUDA(cudaSetDevice(ds->device));
+        DistPeers pr{};
+        pr.world = world;
+        pr.rank = rank;
+        int32_t sb = 0;
+        for (int r = 0; r <= world; ++r) {
+            if (r < world)
+                FS_REQUIRE(row_starts[r] <= row_starts[r + 1] && (row_starts[r] & 3) == 0, FS_ERR_INVALID,
+                           "fs_dataset_set_peers: row_starts must be ascending multiples of 4");
+            pr.starts[r] = row_starts[r];
+            pr.sb_base[r] = sb;
+            if (r < world) sb += (int32_t)ceil_div(row_starts[r + 1] - row_starts[r], 256);
+        }
+        FS_REQUIRE((size_t)round_up(std::max<int64_t>(pr.starts[rank + 1] - pr.starts[rank], 1), 128) *
+                           (size_t)round_up(ds->n, 128) <= ds->peer_slab_count,
+                   FS_ERR_INVALID, "fs_dataset_set_peers: slab smaller than this rank's shard");
+        for (void *m : ds->peer_mapped) cudaIpcCloseMemHandle(m);
+        ds->peer_mapped.clear();
+        ds->peers_on = false;
+        for (int r = 0; r < world; ++r) {
+            if (r == rank) {
+                pr.slab[r] = ds->peer_slab;
+            } else if (raw_ptrs) {
+                pr.slab[r] = static_cast<int32_t *>(raw_ptrs[r]);
+            } else {
+                cudaIpcMemHandle_t h;
+                memcpy(&h, static_cast<const char *>(ipc_handles) + (size_t)r * sizeof(h), sizeof(h));
+                void *p = nullptr;
+                FS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+                ds->peer_mapped.push_back(p);
+                pr.slab[r] = static_cast<int32_t *>(p);
+            }
+        }
+        ds->peers = pr;
+        ds->barrier_fn = barrier;
+        ds->barrier_ctx = barrier_ctx;
+        ds->peers_on = world > 1;
+        ds->dd_valid = false;
+        return FS_OK;
+    } catch (const Fail &f) {
+        return f.code;
+    }
+}
+
 int fs_dataset_destroy(fs_dataset *ds) {
     if (!ds) return FS_OK;
     cudaSetDevice(ds->device);
     cudaStreamSynchronize(ds->stream);
+    for (void *m : ds->peer_mapped) cudaIpcCloseMemHandle(m);
+    if (ds->peer_slab) cudaFree(ds->peer_slab);
     alloc_stream() = ds->stream;
     delete ds;
     return FS_OK;

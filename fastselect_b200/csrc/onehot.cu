@@ -20,8 +20,8 @@
 namespace fs {
 
 void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_t K, const int32_t *srow,
-                    const int64_t *d_ids, int64_t R, int64_t n, int32_t *Dd, int64_t ldd, bool symmetric,
-                    bool subtract, cudaStream_t st, int *launches, double *ops);
+                    const int64_t *d_ids, int64_t R, int64_t n, int64_t ldd, bool symmetric, bool subtract,
+                    const DistPeers &peers, cudaStream_t st, int *launches, double *ops);
 int tc_accum_groups(int64_t R, int n_classes);
 int tc_accum_tile_desc_ints();
 int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
@@ -640,12 +640,33 @@ void launch_dist_tensor(fs_dataset *ds, const WorkSet &ws, int64_t r0_internal, 
             FS_CUDA(cudaMemcpyAsync(g.ptr + (size_t)r * K, Uop + (size_t)h_row_ids[r] * K, K, cudaMemcpyDeviceToDevice, st));
         a_rows = g.ptr;
     }
-    // all samples are targets: D is symmetric, only the upper-triangular tiles are computed
+    // Symmetric mode: the target rows of all ranks together cover every sample, so half of the
+    // off-diagonal super-blocks are computed and mirrored (tc_dist.cu).  One rank scoring all rows
+    // is the trivial case; with peers configured (fs_dataset_set_peers) this rank's rows must be
+    // exactly its shard and Dd its exported slab.  An incremental update across ranks stays
+    // non-symmetric (it would need remote read-modify-writes).
     const char *env = getenv("FS_B200_SYMMETRIC");
-    const bool symmetric = contiguous && r0_internal == 0 && R == ds->n && !(env && env[0] == '0');
+    const bool allow = contiguous && !(env && env[0] == '0');
+    DistPeers peers{};
+    bool symmetric = false;
+    if (allow && ds->peers_on && Dd == ds->peer_slab && r0_internal == ds->peers.starts[ds->peers.rank] &&
+        R == ds->peers.starts[ds->peers.rank + 1] - ds->peers.starts[ds->peers.rank] && !incr) {
+        peers = ds->peers;
+        symmetric = true;
+    } else {
+        peers.world = 1;
+        peers.rank = 0;
+        peers.slab[0] = Dd;
+        peers.starts[0] = 0;
+        peers.starts[1] = ds->n;
+        peers.sb_base[0] = 0;
+        peers.sb_base[1] = (int32_t)ceil_div(ds->n, 256);
+        symmetric = allow && r0_internal == 0 && R == ds->n;
+    }
     const CUtensorMap ta = make_tmap_u8_sw128(a_rows, K, R, K, 128);
     const CUtensorMap tb = make_tmap_u8_sw128(Wop, K, ds->n, K, 256);
-    launch_tc_dist(ta, tb, K, sop, d_row_ids, R, ds->n, Dd, ldn, symmetric, incr, st, launches, ops);
+    launch_tc_dist(ta, tb, K, sop, d_row_ids, R, ds->n, ldn, symmetric, incr, peers, st, launches, ops);
+    ds->last_dist_exchanged = symmetric && peers.world > 1;
 }
 
 // ---------------------------------------------------------------------------

@@ -137,7 +137,32 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
 
     const int64_t Rmax = std::min<int64_t>(chunk_rows(ws.pg > 0, ws.pt > 0, ldn, algo), round_up((int64_t)targets.size(), 128));
     if (ws.pg > 0) ds->Dc.reserve((size_t)Rmax * ldn);
-    if (ws.pt > 0) ds->Dd.reserve((size_t)Rmax * ldn);
+    // the one-hot distance slab: this rank's IPC-exported slab when the call scores exactly its
+    // shard (multi-GPU symmetric mode), else the data set's own buffer
+    int32_t *Dd = nullptr;
+    if (ws.pt > 0) {
+        const bool my_shard = ds->peers_on && contiguous && dbg == nullptr &&
+                              targets[0] == ds->peers.starts[ds->peers.rank] &&
+                              (int64_t)targets.size() == ds->peers.starts[ds->peers.rank + 1] - ds->peers.starts[ds->peers.rank] &&
+                              (size_t)Rmax * ldn <= ds->peer_slab_count && Rmax >= (int64_t)targets.size();
+        if (my_shard) {
+            Dd = ds->peer_slab;
+        } else {
+            ds->Dd.reserve((size_t)Rmax * ldn);
+            Dd = ds->Dd.ptr;
+        }
+        if (ds->dd_buf != Dd) {
+            // the cached slab lives in the other buffer: recompute in full (the working set may
+            // have been built for an incremental update)
+            if (ds->dd_valid && ws.dist_mode != kDistFull) {
+                ds->dd_valid = false;
+                ds->ws.valid = false;
+                build_workset(ds, feat_idx, n_kept, allow_tensor, algo == FS_RELIEFF, targets[0], (int64_t)targets.size(),
+                              slab_cacheable, &launches);
+            }
+            ds->dd_valid = false;
+        }
+    }
     ds->sel.reserve((size_t)Rmax * ldn);
     const bool use_masks = ws.pt > 0 && algo != FS_RELIEFF;
     if (use_masks) {
@@ -185,10 +210,18 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
         if (ws.pt > 0 && ws.dist_mode != kDistReuse) {
             ds->dd_valid = false;
             timer.begin(PH_DIST_T);
-            launch_dist_tensor(ds, ws, h_ids[0], h_ids, ds->row_ids.ptr, contiguous, R, ds->Dd.ptr, ldn, st, &launches, &ops_dist);
+            launch_dist_tensor(ds, ws, h_ids[0], h_ids, ds->row_ids.ptr, contiguous, R, Dd, ldn, st, &launches, &ops_dist);
             timer.end();
+            if (ds->last_dist_exchanged) {
+                // tiles computed here were also stored into the peers' slabs and theirs into this
+                // one: every rank must have finished its distance kernel before anyone selects
+                FS_CUDA(cudaStreamSynchronize(st));
+                FS_REQUIRE(ds->barrier_fn != nullptr, FS_ERR_STATE, "peer mode without a barrier callback");
+                ds->barrier_fn(ds->barrier_ctx);
+            }
         }
         if (ws.pt > 0 && slab_cacheable) {
+            ds->dd_buf = Dd;
             // Dd now holds the mismatch counts of exactly these columns for these target rows
             ds->dd_cols.assign(ws.p_tcol.ptr, ws.p_tcol.ptr + ws.pt);
             ds->dd_r0 = targets[0];
@@ -203,7 +236,7 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
         // ---- neighbour selection
         timer.begin(PH_SELECT);
         launch_select(ds, algo, use_star, k, ds->row_ids.ptr, R, ws.pg > 0 ? ds->Dc.ptr : nullptr,
-                      ws.pt > 0 ? ds->Dd.ptr : nullptr, ldn, ds->sel.ptr, use_masks ? ds->maskH.ptr : nullptr,
+                      ws.pt > 0 ? Dd : nullptr, ldn, ds->sel.ptr, use_masks ? ds->maskH.ptr : nullptr,
                       use_masks ? ds->maskM.ptr : nullptr, ds->rinfo.ptr, ds->nbr_idx.ptr,
                       ds->nbr_w.ptr, ds->nbr_cnt.ptr, nbr_cap, ds->d_class_probs.ptr, st, &launches);
         if (stats) {
@@ -247,7 +280,7 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
             }
             if (ws.pt > 0) {
                 hdd.resize((size_t)R * ldn);
-                FS_CUDA(cudaMemcpy(hdd.data(), ds->Dd.ptr, hdd.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+                FS_CUDA(cudaMemcpy(hdd.data(), Dd, hdd.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
             }
             FS_CUDA(cudaMemcpy(hs.data(), ds->sel.ptr, hs.size(), cudaMemcpyDeviceToHost));
             FS_CUDA(cudaMemcpy(hr.data(), ds->rinfo.ptr, R * sizeof(RowInfo), cudaMemcpyDeviceToHost));

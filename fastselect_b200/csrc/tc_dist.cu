@@ -13,10 +13,18 @@
 // thread of warp 1 issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=256, K=32) into
 // a 256-column TMEM accumulator; warps 2-5 read the accumulator back with
 // tcgen05.ld (32 lanes x 32 columns per instruction), form s_i + s_j - acc and store
-// int32 rows (each thread writes whole 128-byte lines).  When every sample is a target
-// (one GPU, one chunk) D is symmetric: only tiles that reach the diagonal or lie above it
-// are computed, and their strictly-upper part is also stored transposed (a warp's 32 lanes
-// hold 32 consecutive rows of one column, so the mirrored store is one 128-byte line).
+// int32 rows (each thread writes whole 128-byte lines).
+//
+// Symmetric mode.  D is symmetric, so when the target rows of all ranks together cover every
+// sample (one GPU scoring all rows, or one process per GPU each scoring its row shard) only
+// half of the off-diagonal 256 x 256 super-blocks are computed: super-block (I, J), I != J, is
+// computed on the rank that owns rows I iff ((I + J) even) == (J > I) -- a checkerboard that
+// gives every rank the same share -- and each computed tile is stored twice: into the
+// computing rank's slab, and transposed into the slab of the rank that owns rows J (a warp's 32
+// lanes hold 32 consecutive rows of one column, so the mirrored store is one 128-byte line;
+// for another rank it is a peer store over NVLink into that rank's slab, mapped through CUDA
+// IPC).  The exchange is fused into the GEMM epilogue; a cross-rank barrier before the
+// neighbour selection is all that follows.
 // Tensor-pipe bound: 4 int-ops per (sample pair, feature) for 3-valued genotypes, half of
 // that in symmetric mode.
 #include "common.cuh"
@@ -39,8 +47,8 @@ constexpr int BAND = 16;        // row blocks per rasterisation band
 __global__ void __launch_bounds__(THREADS, 1)
 tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                int num_k_blocks, const int32_t *__restrict__ srow, const int64_t *__restrict__ ids, int64_t R,
-               int64_t n, int32_t *__restrict__ Dd, int64_t ldd, int symmetric, int subtract, int tiles_y,
-               int tiles_x) {
+               int64_t n, int64_t ldd, int symmetric, int subtract, int tiles_y, int tiles_x,
+               const __grid_constant__ DistPeers peers) {
     // L2-friendly rasterisation: bands of BAND row blocks, walked column by column, so that the
     // ~148 concurrently resident tiles form a roughly square region and share their operand
     // K-slabs through L2 (16 x 128 target rows and ~9 x 256 sample rows per wave) instead of
@@ -54,8 +62,20 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tile_y = band * BAND + in_band % band_rows;
         tile_x = in_band / band_rows;
     }
-    // symmetric mode: tile (by, bx) is needed iff its columns reach the diagonal block of its rows
-    if (symmetric && tile_x < (tile_y >> 1)) return;
+    // column tile -> the rank that owns those samples as target rows, and the sample range.
+    // Column tiles are the 256-row super-blocks of every rank's shard, numbered globally.
+    int owner = 0;
+    while (owner + 1 < peers.world && tile_x >= peers.sb_base[owner + 1]) ++owner;
+    const int64_t n0 = peers.starts[owner] + (int64_t)(tile_x - peers.sb_base[owner]) * BN;
+    const int64_t cend = n0 + BN < peers.starts[owner + 1] ? n0 + BN : peers.starts[owner + 1];
+    // symmetric mode: checkerboard over super-blocks (see the header); sb_i = this tile's super-row
+    const int sb_i = peers.sb_base[peers.rank] + (tile_y >> 1), sb_j = tile_x;
+    const bool diagonal = sb_i == sb_j;
+    if (symmetric && !diagonal && ((((sb_i + sb_j) & 1) == 0) != (sb_j > sb_i))) return;
+    const bool mirror = symmetric && !diagonal;
+    int32_t *Dd = peers.slab[peers.rank];                         // may alias Dm: no __restrict__
+    int32_t *Dm = peers.slab[owner];                  // slab that receives the transposed tile
+    const int64_t row_global0 = peers.starts[peers.rank];          // global sample index of slab row 0
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *smem_a = smem;
@@ -66,7 +86,7 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = tile_y * BM, n0 = tile_x * BN;
+    const int m0 = tile_y * BM;
 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmap_a);
@@ -93,7 +113,7 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 tc::mbar_wait(&empty_bar[s], ph ^ 1);
                 tc::mbar_arrive_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
                 tc::tma_load_2d(smem_a + s * A_BYTES, &tmap_a, &full_bar[s], kb * BK, m0);
-                tc::tma_load_2d(smem_b + s * B_BYTES, &tmap_b, &full_bar[s], kb * BK, n0);
+                tc::tma_load_2d(smem_b + s * B_BYTES, &tmap_b, &full_bar[s], kb * BK, (int32_t)n0);
             }
         }
     } else if (warp == 1) {
@@ -119,20 +139,17 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int q = warp & 3;
         const int64_t row = (int64_t)m0 + q * 32 + lane;
         const int32_t s_i = row < R ? srow[ids[row]] : 0;      // issued before the accumulator wait
-        // symmetric mode (ids[r] = r): columns below diag_lo are the mirror image of another tile's
-        // stores and are skipped here; columns from diag_hi on are also stored transposed
-        const int64_t diag_lo = symmetric ? (int64_t)m0 : 0;
-        const int64_t diag_hi = symmetric ? (int64_t)m0 + BM : (int64_t)1 << 62;
         tc::mbar_wait(accum_bar, 0);
         tc::tc_fence_after();
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
-            const int64_t col = (int64_t)n0 + c0;
-            if (col + 32 <= diag_lo || col >= n) continue;     // warp-uniform
+            const int64_t col = n0 + c0;
+            if (col >= cend) continue;                         // warp-uniform
             uint32_t v[32];
             tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             tc::tmem_ld_wait();
-            // distances of this thread's row to samples col .. col+31 (srow is padded to ldd)
+            // distances of this thread's row to samples col .. col+31 (srow is padded to ldd;
+            // col is a multiple of 4)
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
                 const int4 sj = *reinterpret_cast<const int4 *>(srow + col + e);
@@ -144,9 +161,10 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // subtract mode (incremental update): the operands are those of removed columns and
             // their mismatch count is taken off the resident slab
             if (row < R) {
-                int32_t *dst = Dd + row * ldd + col;           // ldd is a multiple of 128: 16-byte aligned
+                int32_t *dst = Dd + row * ldd + col;           // ldd multiple of 128, col multiple of 4: 16-byte aligned
 #pragma unroll
                 for (int e = 0; e < 32; e += 4) {
+                    if (col + e >= cend) break;                // cend is a multiple of 4 or the padded end
                     int4 o = make_int4((int)v[e], (int)v[e + 1], (int)v[e + 2], (int)v[e + 3]);
                     if (subtract) {
                         const int4 old = *reinterpret_cast<const int4 *>(dst + e);
@@ -155,13 +173,12 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     *reinterpret_cast<int4 *>(dst + e) = o;
                 }
             }
-            if (col >= diag_hi && row < R) {
+            if (mirror && row < R) {
+                // transposed copy: row (col + e) of the owner's slab, column = this row's sample
+                int32_t *m = Dm + (col - peers.starts[owner]) * ldd + row_global0 + row;
 #pragma unroll
                 for (int e = 0; e < 32; ++e)
-                    if (col + e < n) {
-                        int32_t *m = Dd + (col + e) * ldd + row;
-                        *m = subtract ? *m - (int32_t)v[e] : (int32_t)v[e];
-                    }
+                    if (col + e < cend) m[e * ldd] = subtract ? m[e * ldd] - (int32_t)v[e] : (int32_t)v[e];
             }
         }
         tc::tc_fence_before();
@@ -174,23 +191,26 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_t K, const int32_t *srow,
-                    const int64_t *d_ids, int64_t R, int64_t n, int32_t *Dd, int64_t ldd, bool symmetric,
-                    bool subtract, cudaStream_t st, int *launches, double *ops) {
+                    const int64_t *d_ids, int64_t R, int64_t n, int64_t ldd, bool symmetric, bool subtract,
+                    const DistPeers &peers, cudaStream_t st, int *launches, double *ops) {
     static bool configured = false;
     if (!configured) {
         FS_CUDA(cudaFuncSetAttribute(tc_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
     }
-    const int tiles_x = (int)ceil_div(n, BN), tiles_y = (int)ceil_div(R, BM);
+    const int tiles_x = peers.sb_base[peers.world], tiles_y = (int)ceil_div(R, BM);
     tc_dist_kernel<<<(unsigned)(tiles_x * tiles_y), THREADS, SMEM_BYTES, st>>>(
-        tmap_a, tmap_b, (int)(K / BK), srow, d_ids, R, n, Dd, ldd, symmetric ? 1 : 0, subtract ? 1 : 0, tiles_y,
-        tiles_x);
+        tmap_a, tmap_b, (int)(K / BK), srow, d_ids, R, n, ldd, symmetric ? 1 : 0, subtract ? 1 : 0, tiles_y, tiles_x,
+        peers);
     FS_CUDA(cudaGetLastError());
     ++*launches;
     if (ops) {
         int64_t tiles = 0;
         for (int by = 0; by < tiles_y; ++by)
-            for (int bx = 0; bx < tiles_x; ++bx) tiles += (!symmetric || bx >= (by >> 1)) ? 1 : 0;
+            for (int bx = 0; bx < tiles_x; ++bx) {
+                const int sb_i = peers.sb_base[peers.rank] + (by >> 1);
+                tiles += (!symmetric || sb_i == bx || ((((sb_i + bx) & 1) == 0) == (bx > sb_i))) ? 1 : 0;
+            }
         *ops += 2.0 * BM * BN * (double)K * (double)tiles;
     }
 }

@@ -32,7 +32,7 @@ extern "C" {
 #define FS_API
 #endif
 
-#define FS_ABI_VERSION 2
+#define FS_ABI_VERSION 3
 /* distinct values tracked per column by fs_dataset_create; a column with more
  * distinct values reports FS_DISTINCT_CAP + 1 */
 #define FS_DISTINCT_CAP 16
@@ -144,6 +144,26 @@ FS_API int fs_score(fs_dataset *ds, int algo, int use_star, int32_t k, const flo
 FS_API int fs_debug_rows(fs_dataset *ds, int algo, int use_star, int32_t k, const float *class_probs,
                   const int64_t *feat_idx, int64_t n_kept, const int64_t *targets, int64_t nt,
                   double *dist_out, double *thresh_out, int8_t *mask_out, double *wsum_out);
+
+/*
+ * Multi-GPU symmetric distances (one process per GPU; optional).  The reference has no
+ * multi-GPU path; target rows are sharded across ranks (fs_score's row range).  D is symmetric,
+ * so with peers configured each rank computes only half of the off-diagonal blocks of its row
+ * shard and stores every computed tile twice -- into its own slab and, transposed, straight into
+ * the slab of the rank that owns those rows (peer stores over NVLink from the GEMM epilogue).
+ *
+ * fs_dataset_peer_slab: allocate this rank's distance slab for `rows` target rows and return its
+ *   CUDA IPC handle (64 bytes) for the other ranks.
+ * fs_dataset_set_peers: row_starts[world + 1] = first internal row of every rank's shard (multiples
+ *   of 4; row_starts[world] = n); ipc_handles = world x 64 bytes (this rank's own entry is ignored);
+ *   raw_ptrs (nullable) = device pointers to use instead of opening handles (ranks emulated inside
+ *   one process, for tests); barrier(ctx) must return only after EVERY rank has called it -- it
+ *   is invoked inside fs_score between the distance kernel and the neighbour selection.
+ *   Every rank must then call fs_score with exactly its own shard and the same arguments.
+ */
+FS_API int fs_dataset_peer_slab(fs_dataset *ds, int64_t rows, void *ipc_handle_out, void **dev_ptr_out);
+FS_API int fs_dataset_set_peers(fs_dataset *ds, int32_t rank, int32_t world, const int64_t *row_starts,
+                         const void *ipc_handles, void *const *raw_ptrs, void (*barrier)(void *), void *barrier_ctx);
 
 /* Internal order: perm_out[r] = original index of internal row r ([n]). */
 FS_API int fs_dataset_row_order(const fs_dataset *ds, int64_t *perm_out);
