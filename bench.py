@@ -471,6 +471,7 @@ def turf_arm(args):
 
     for _ in range(args.warmup):
         score()                          # warm-up: full-width scoring passes (allocations, clocks)
+        score(np.arange(p - p // 10))    # and one pruned pass (buffers of the incremental distance update)
     agg.clear()
     sampler = ClockSampler(local_rank)
     barrier()

@@ -152,6 +152,7 @@ struct DistPeers {
     int64_t starts[kMaxRanks + 1];  // [world + 1] first target row (internal order) of every rank's shard
     int32_t sb_base[kMaxRanks + 1]; // [world + 1] running count of 256-row super-blocks of the shards
     int32_t world, rank;
+    int32_t coarse_shift;           // symmetric mode: log2 of the super-block group size (see tc_dist.cu)
 };
 
 // Working set of one fs_score call: the active columns split by path.
@@ -187,6 +188,7 @@ struct WorkSet {
     int64_t ldt = 0, ldc = 0;
     bool have_codes = false;
     bool have_dist_ops = false;     // U / Wd / srow of the active columns are built
+    int64_t u_lo = 0, u_hi = 0;     // sample rows held by U (the target rows it was built for)
     // distance plan of this call (see DistMode) and, for an incremental update, the reduced
     // one-hot operands of the columns that left the active set since the cached slab was built
     int dist_mode = 0;
@@ -278,7 +280,7 @@ namespace fs {
 // r0 / R / slab_cacheable: the (contiguous) target rows of this call and whether their distance
 // slab fits one chunk -- decides between a full, an incremental and no distance computation
 void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool allow_tensor, bool need_codes,
-                   int64_t r0, int64_t R, bool slab_cacheable, int *launches);
+                   int64_t r0, int64_t R, bool contiguous, bool slab_cacheable, int *launches);
 
 // dist_general.cu: D[r, j] = sum over general columns of the per-feature term
 // between target row r (rows of xa) and sample j (rows of xb).

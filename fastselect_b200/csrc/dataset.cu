@@ -337,8 +337,10 @@ static int plan_dist(fs_dataset *ds, const int64_t *tcol, int64_t pt, int64_t r0
 }
 
 void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool allow_tensor, bool need_codes,
-                   int64_t r0, int64_t R, bool slab_cacheable, int *launches) {
+                   int64_t r0, int64_t R, bool contiguous, bool slab_cacheable, int *launches) {
     WorkSet &ws = ds->ws;
+    // sample rows the target-side distance operand U has to hold
+    const int64_t want_lo = contiguous ? r0 : 0, want_hi = contiguous ? r0 + R : ds->n;
     Trace tr_all("build_workset");
     // cache key: flags + the explicit column list (none when every column is active)
     const bool all = feat_idx == nullptr;
@@ -350,7 +352,7 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
     if (ws.valid && ws.key == key && (ws.have_codes || !need_codes || ws.pt == 0)) {
         // same columns as the last call: the slab is either still there or recomputed in full
         const int mode = plan_dist(ds, ws.p_tcol.ptr, ws.pt, r0, R, slab_cacheable, ws.removed);
-        if (mode == kDistReuse || ws.have_dist_ops || ws.pt == 0) {
+        if (mode == kDistReuse || (ws.have_dist_ops && ws.u_lo <= want_lo && want_hi <= ws.u_hi) || ws.pt == 0) {
             ws.dist_mode = mode == kDistReuse ? kDistReuse : kDistFull;
             return;
         }
@@ -473,6 +475,8 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
         ws.dist_mode = plan_dist(ds, ws.p_tcol.ptr, ws.pt, r0, R, slab_cacheable, ws.removed);
     }
     ws.have_dist_ops = ws.dist_mode == kDistFull;
+    ws.u_lo = want_lo;
+    ws.u_hi = want_hi;
     if (ws.pt > 0) {
         Trace tr("  build_onehot");
         build_onehot(ds, ws, launches);

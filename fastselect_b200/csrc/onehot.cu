@@ -22,11 +22,10 @@ namespace fs {
 void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_t K, const int32_t *srow,
                     const int64_t *d_ids, int64_t R, int64_t n, int64_t ldd, bool symmetric, bool subtract,
                     const DistPeers &peers, cudaStream_t st, int *launches, double *ops);
-int tc_accum_groups(int64_t R, int n_classes);
 int tc_accum_tile_desc_ints();
 int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
                     int64_t R, const int64_t *d_ids, bool contiguous, const RowInfo *rinfo, const uint8_t *codesT,
-                    int64_t ldt, const uint32_t *krow, int64_t K_rows, double *tpartial, int32_t *d_tiles,
+                    int64_t ldt, const uint32_t *krow, int64_t K_rows, DevBuf<double> &tpartial, int32_t *d_tiles,
                     cudaStream_t st, int *launches, const int64_t *h_ids, const int32_t *h_y,
                     const int64_t *h_cls_start, double *ops);
 
@@ -110,7 +109,7 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
     const int32_t *__restrict__ toff, const double *__restrict__ vals, int as_f32, int64_t n, int64_t pt, int64_t K,
     int64_t ldt, int64_t ldc, int8_t *__restrict__ U, int8_t *__restrict__ Wd, int8_t *__restrict__ At,
     uint8_t *__restrict__ codesT, uint8_t *__restrict__ codes, int32_t *__restrict__ srow,
-    uint32_t *__restrict__ krow, int all_ident) {
+    uint32_t *__restrict__ krow, int all_ident, int64_t u_lo, int64_t u_hi) {
     __shared__ __align__(16) uint8_t code_rc[ENC_ROWS][ENC_COLS];       // [sample][column]
     __shared__ __align__(16) uint8_t code_cr[ENC_COLS][ENC_CR_LD];      // [column][sample]
     __shared__ uint8_t kcol[ENC_KMAX];                                  // reduced row -> column in tile
@@ -243,7 +242,8 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
                 expand_v3(cw.x, u.x, u.y, w.x, w.y, cnt);
                 expand_v3(cw.y, u.z, u.w, w.z, w.w, cnt);
                 const int64_t o = (r0 + rr) * K + k0 + 16 * g;
-                *reinterpret_cast<uint4 *>(U + o) = u;
+                // U holds only the rows [u_lo, u_hi) (the target rows of this rank)
+                if (r0 + rr >= u_lo && r0 + rr < u_hi) *reinterpret_cast<uint4 *>(U + o - u_lo * K) = u;
                 *reinterpret_cast<uint4 *>(Wd + o) = w;
             }
             cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
@@ -275,15 +275,16 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
                         }
                     }
                     const int64_t o = (r0 + rr) * K + 4 * (int64_t)w;
+                    const bool in_u = r0 + rr >= u_lo && r0 + rr < u_hi;      // U holds only those rows
                     if (full) {
-                        *reinterpret_cast<uint32_t *>(U + o) = uw;
+                        if (in_u) *reinterpret_cast<uint32_t *>(U + o - u_lo * K) = uw;
                         *reinterpret_cast<uint32_t *>(Wd + o) = ww;
                     } else {
 #pragma unroll
                         for (int b = 0; b < 4; ++b) {
                             const int k = 4 * w + b;
                             if (k >= k0 && k < k1) {
-                                U[o + b] = (int8_t)((uw >> (8 * b)) & 0xffu);
+                                if (in_u) U[o - u_lo * K + b] = (int8_t)((uw >> (8 * b)) & 0xffu);
                                 Wd[o + b] = (int8_t)((ww >> (8 * b)) & 0xffu);
                             }
                         }
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
     const uint8_t *__restrict__ x, int64_t ldx, const int64_t *__restrict__ perm, const int64_t *__restrict__ tcol,
     int64_t n, int64_t pt, int64_t K, int64_t ldt, int64_t ldc, int8_t *__restrict__ U, int8_t *__restrict__ Wd,
     int8_t *__restrict__ At, uint8_t *__restrict__ codesT, uint8_t *__restrict__ codes, int32_t *__restrict__ srow,
-    uint32_t *__restrict__ krow) {
+    uint32_t *__restrict__ krow, int64_t u_lo, int64_t u_hi) {
     __shared__ __align__(16) uint8_t code_rc[ENC_ROWS][ENC_COLS];       // [sample][column]
     __shared__ __align__(16) uint8_t code_cr[ENC_COLS][ENC_CR_LD];      // [column][sample]
     __shared__ int64_t sperm[ENC_ROWS];
@@ -431,7 +432,8 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
                     expand_v3(cw.x, u.x, u.y, w.x, w.y, cnt);
                     expand_v3(cw.y, u.z, u.w, w.z, w.w, cnt);
                     const int64_t o = (r0 + rr) * K + k0 + 16 * g;
-                    *reinterpret_cast<uint4 *>(U + o) = u;
+                    // U holds only the rows [u_lo, u_hi) (the target rows of this rank)
+                    if (r0 + rr >= u_lo && r0 + rr < u_hi) *reinterpret_cast<uint4 *>(U + o - u_lo * K) = u;
                     *reinterpret_cast<uint4 *>(Wd + o) = w;
                 }
                 cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
@@ -448,8 +450,10 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
                         const uint32_t code = code_rc[rr][cc];
                         const uint32_t nl = code != 2u ? 1u : 0u;
                         const int64_t o = (r0 + rr) * K + k0 + 2 * cc;
-                        U[o] = (int8_t)(code == 0u);
-                        U[o + 1] = (int8_t)(code == 1u);
+                        if (r0 + rr >= u_lo && r0 + rr < u_hi) {
+                            U[o - u_lo * K] = (int8_t)(code == 0u);
+                            U[o - u_lo * K + 1] = (int8_t)(code == 1u);
+                        }
                         Wd[o] = (int8_t)((code == 0u) + nl);
                         Wd[o + 1] = (int8_t)((code == 1u) + nl);
                         cnt += (int)nl;
@@ -527,7 +531,7 @@ static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
     if (all_ident && ws.Kr_used == 2 * pr) {
         onehot_encode_v3_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(ds->x), ds->ldx, ds->d_perm.ptr,
                                                       ws.rcol.ptr, n, pr, ws.Kr, ws.ldt, 0, ws.Ur.ptr, ws.Wdr.ptr, nullptr,
-                                                      nullptr, nullptr, ws.srow_r.ptr, nullptr);
+                                                      nullptr, nullptr, ws.srow_r.ptr, nullptr, 0, n);
         FS_CUDA(cudaGetLastError());
         ++*launches;
         return;
@@ -536,7 +540,7 @@ static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
     onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,        \
                                                   ws.rcol.ptr, ws.roff.ptr, ds->d_vals.ptr, as_f32, n, pr, ws.Kr, \
                                                   ws.ldt, 0, ws.Ur.ptr, ws.Wdr.ptr, nullptr, nullptr, nullptr,    \
-                                                  ws.srow_r.ptr, nullptr, all_ident)
+                                                  ws.srow_r.ptr, nullptr, all_ident, 0, n)
     switch (ds->dtype) {
         case FS_U8: FS_ENCODE_R(uint8_t); break;
         case FS_I8: FS_ENCODE_R(int8_t); break;
@@ -560,7 +564,7 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     ws.toff.reserve(pt + 1);
     const bool ops = ws.have_dist_ops;
     if (ops) {
-        ws.U.reserve((size_t)n * ws.K);
+        ws.U.reserve((size_t)(ws.u_hi - ws.u_lo) * ws.K);   // target rows of this call only
         ws.Wd.reserve((size_t)n * ws.K);
         ws.srow.reserve(ws.ldt);   // padded: the distance epilogue reads it in 16-byte vectors
     }
@@ -578,7 +582,8 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     if (ops) FS_CUDA(cudaMemsetAsync(ws.srow.ptr, 0, ws.ldt * sizeof(int32_t), st));
     if (ws.K > ws.K_used) {
         if (ops) {
-            FS_CUDA(cudaMemset2DAsync(ws.U.ptr + ws.K_used, (size_t)ws.K, 0, (size_t)(ws.K - ws.K_used), (size_t)n, st));
+            FS_CUDA(cudaMemset2DAsync(ws.U.ptr + ws.K_used, (size_t)ws.K, 0, (size_t)(ws.K - ws.K_used),
+                                      (size_t)(ws.u_hi - ws.u_lo), st));
             FS_CUDA(cudaMemset2DAsync(ws.Wd.ptr + ws.K_used, (size_t)ws.K, 0, (size_t)(ws.K - ws.K_used), (size_t)n, st));
         }
         FS_CUDA(cudaMemsetAsync(ws.At.ptr + (size_t)ws.K_used * ws.ldt, 0, (size_t)(ws.K - ws.K_used) * ws.ldt, st));
@@ -592,7 +597,7 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
                                                       ws.tcol.ptr, n, pt, ws.K, ws.ldt, ws.ldc, ops ? ws.U.ptr : nullptr,
                                                       ops ? ws.Wd.ptr : nullptr, ws.At.ptr, ws.codesT.ptr,
                                                       ws.have_codes ? ws.codes.ptr : nullptr,
-                                                      ops ? ws.srow.ptr : nullptr, ws.krow.ptr);
+                                                      ops ? ws.srow.ptr : nullptr, ws.krow.ptr, ws.u_lo, ws.u_hi);
         FS_CUDA(cudaGetLastError());
         ++*launches;
         if (ws.dist_mode == kDistIncremental) build_removed(ds, ws, launches);
@@ -604,7 +609,7 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
                                                   ws.ldt, ws.ldc, ops ? ws.U.ptr : nullptr,                      \
                                                   ops ? ws.Wd.ptr : nullptr, ws.At.ptr, ws.codesT.ptr,           \
                                                   ws.have_codes ? ws.codes.ptr : nullptr,                        \
-                                                  ops ? ws.srow.ptr : nullptr, ws.krow.ptr, all_ident)
+                                                  ops ? ws.srow.ptr : nullptr, ws.krow.ptr, all_ident, ws.u_lo, ws.u_hi)
     switch (ds->dtype) {
         case FS_U8: FS_ENCODE(uint8_t); break;
         case FS_I8: FS_ENCODE(int8_t); break;
@@ -631,13 +636,15 @@ void launch_dist_tensor(fs_dataset *ds, const WorkSet &ws, int64_t r0_internal, 
     const int32_t *sop = incr ? ws.srow_r.ptr : ws.srow.ptr;
     const int64_t K = incr ? ws.Kr : ws.K;
     const int8_t *a_rows;
+    const int64_t u_lo = incr ? 0 : ws.u_lo;           // first sample row held by the target-side operand
     if (contiguous) {
-        a_rows = Uop + (size_t)r0_internal * K;
+        a_rows = Uop + (size_t)(r0_internal - u_lo) * K;
     } else {
         DevBuf<int8_t> &g = ds->a_gather;
         g.reserve((size_t)R * K);
         for (int64_t r = 0; r < R; ++r)
-            FS_CUDA(cudaMemcpyAsync(g.ptr + (size_t)r * K, Uop + (size_t)h_row_ids[r] * K, K, cudaMemcpyDeviceToDevice, st));
+            FS_CUDA(cudaMemcpyAsync(g.ptr + (size_t)r * K, Uop + (size_t)(h_row_ids[r] - u_lo) * K, K,
+                                    cudaMemcpyDeviceToDevice, st));
         a_rows = g.ptr;
     }
     // Symmetric mode: the target rows of all ranks together cover every sample, so half of the
@@ -661,6 +668,7 @@ void launch_dist_tensor(fs_dataset *ds, const WorkSet &ws, int64_t r0_internal, 
         peers.starts[1] = ds->n;
         peers.sb_base[0] = 0;
         peers.sb_base[1] = (int32_t)ceil_div(ds->n, 256);
+        peers.coarse_shift = 3;                 // groups of 8 super-blocks = one rasterisation band of 16 tiles
         symmetric = allow && r0_internal == 0 && R == ds->n;
     }
     const CUtensorMap ta = make_tmap_u8_sw128(a_rows, K, R, K, 128);
@@ -753,14 +761,13 @@ void launch_accum_tensor(fs_dataset *ds, const WorkSet &ws, int algo, const int6
         *launches += 2;
         return;
     }
-    ds->tpartial.reserve((size_t)tc_accum_groups(R, ds->n_classes) * ws.K_used);
     ds->tile_desc.reserve(tc_accum_tile_desc_ints());
     // K of this GEMM is the sample index: rows of At and of the masks are n bytes long
     const CUtensorMap tat = make_tmap_u8_sw128(ws.At.ptr, (uint64_t)n, (uint64_t)ws.K, (uint64_t)ws.ldt, 128);
     const CUtensorMap tmh = make_tmap_u8_sw128(ds->maskH.ptr, (uint64_t)n, (uint64_t)R, (uint64_t)ldn, 256);
     const CUtensorMap tmm = make_tmap_u8_sw128(ds->maskM.ptr, (uint64_t)n, (uint64_t)R, (uint64_t)ldn, 256);
     const int parts = launch_tc_accum(tat, tmh, tmm, n, R, d_row_ids, contiguous, rinfo, ws.codesT.ptr, ws.ldt,
-                                      ws.krow.ptr, ws.K_used, ds->tpartial.ptr, ds->tile_desc.ptr, st, launches,
+                                      ws.krow.ptr, ws.K_used, ds->tpartial, ds->tile_desc.ptr, st, launches,
                                       h_row_ids, ds->y_sorted.data(), ds->cls_start.data(), ops);
     reduce_tensor_partials_kernel<<<(unsigned)ceil_div(ws.pt, 256), 256, 0, st>>>(ds->tpartial.ptr, parts, ws.K_used,
                                                                                  ws.toff.ptr, ws.tout.ptr, ws.pt, wsum);

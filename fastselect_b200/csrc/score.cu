@@ -130,7 +130,7 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
     timer.begin(PH_GATHER);
     const auto prep0 = std::chrono::steady_clock::now();
     build_workset(ds, feat_idx, n_kept, allow_tensor, algo == FS_RELIEFF, targets[0], (int64_t)targets.size(),
-                  slab_cacheable, &launches);
+                  contiguous, slab_cacheable, &launches);
     const double ms_prep = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - prep0).count();
     timer.end();
     const WorkSet &ws = ds->ws;
@@ -158,7 +158,7 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
                 ds->dd_valid = false;
                 ds->ws.valid = false;
                 build_workset(ds, feat_idx, n_kept, allow_tensor, algo == FS_RELIEFF, targets[0], (int64_t)targets.size(),
-                              slab_cacheable, &launches);
+                              contiguous, slab_cacheable, &launches);
             }
             ds->dd_valid = false;
         }

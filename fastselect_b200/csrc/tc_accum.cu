@@ -376,17 +376,10 @@ static AccumPlan make_plan(int64_t n, int64_t R, bool contiguous, const int64_t 
     return plan;
 }
 
-// partial vectors written per launch: (tile groups) x (PARTS column parts); an upper bound that
-// does not depend on the class layout (every class adds at most one partial tile)
-int tc_accum_groups(int64_t R, int n_classes) {
-    const int64_t tiles = ceil_div(R, BN) + n_classes;
-    return PARTS * (int)(ceil_div(tiles, GROUP) + ceil_div(tiles, MAX_TILES));
-}
-
 // Returns the number of partial vectors written ([groups x PARTS][K_rows] doubles).
 int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
                     int64_t R, const int64_t *d_ids, bool contiguous, const RowInfo *rinfo, const uint8_t *codesT,
-                    int64_t ldt, const uint32_t *krow, int64_t K_rows, double *tpartial, int32_t *d_tiles,
+                    int64_t ldt, const uint32_t *krow, int64_t K_rows, DevBuf<double> &tpartial, int32_t *d_tiles,
                     cudaStream_t st, int *launches, const int64_t *h_ids, const int32_t *h_y,
                     const int64_t *h_cls_start, double *ops) {
     FS_CUDA(cudaFuncSetAttribute(tc_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -396,13 +389,27 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
     FS_REQUIRE(n < (1LL << 22), FS_ERR_INVALID, "one-hot accumulation supports up to 2^22 samples (got %lld)", (long long)n);
     const AccumPlan plan = make_plan(n, R, contiguous, h_ids, h_y, h_cls_start);
     const int m_blocks = (int)ceil_div(K_rows, BM);
+    // Tile groups.  Work units (128 one-hot rows x one group) are dealt round-robin, so the ~sms
+    // units resident at one time span sms / groups one-hot row blocks, each streaming its own
+    // 128 x n bytes of At again for every tile of the group: keep that footprint within about half
+    // of L2 (else every re-read goes to HBM and the kernel turns DRAM-bound for large n) by
+    // cutting the tiles into more, smaller groups of equal size.
+    auto groups_for = [&](int nt) {
+        const int64_t want = ceil_div((int64_t)sms * BM * n, (int64_t)60 << 20);
+        const int64_t g = std::max<int64_t>(ceil_div(nt, GROUP), std::min<int64_t>(nt, want));
+        return (int)g;
+    };
+    int total_groups = 0;
+    for (size_t t0 = 0; t0 < plan.tiles.size(); t0 += MAX_TILES)
+        total_groups += groups_for((int)std::min<size_t>(MAX_TILES, plan.tiles.size() - t0));
+    tpartial.reserve((size_t)total_groups * PARTS * K_rows);
     int groups_done = 0;
     // at most MAX_TILES tile descriptors per launch
     for (size_t t0 = 0; t0 < plan.tiles.size(); t0 += MAX_TILES) {
         const int nt = (int)std::min<size_t>(MAX_TILES, plan.tiles.size() - t0);
         // equal-sized groups (work units are dealt round-robin: unequal units would unbalance the SMs)
-        const int groups = (int)ceil_div(nt, GROUP);
-        const int group_tiles = (int)ceil_div(nt, groups);
+        const int group_tiles = (int)ceil_div(nt, groups_for(nt));
+        const int groups = (int)ceil_div(nt, group_tiles);
         // pageable source: the copy is staged before cudaMemcpyAsync returns
         FS_CUDA(cudaMemcpyAsync(d_tiles, plan.tiles.data() + t0, nt * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
         const int units = m_blocks * groups;
@@ -410,7 +417,7 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
         tc_accum_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(
             tmap_at, tmap_mh, tmap_mm, (int)ceil_div(n, BK), R, reinterpret_cast<const TileDesc *>(d_tiles), nt,
             groups, group_tiles, m_blocks, d_ids, contiguous ? 1 : 0, rinfo, codesT, ldt, krow, K_rows,
-            tpartial + (size_t)groups_done * PARTS * K_rows);
+            tpartial.ptr + (size_t)groups_done * PARTS * K_rows);
         FS_CUDA(cudaGetLastError());
         ++*launches;
         groups_done += groups;

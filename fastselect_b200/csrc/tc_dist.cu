@@ -44,6 +44,19 @@ constexpr int THREADS = 192;
 constexpr int BAND = 16;        // row blocks per rasterisation band
 }  // namespace
 
+// Symmetric mode: is super-block (sb_i, sb_j) computed on the side that owns rows sb_i?  Exactly
+// one of (i, j) and (j, i) says yes.  Blocks are first grouped 2^coarse_shift x 2^coarse_shift:
+// whole groups alternate (so that the tiles resident at one time are dense and share their
+// operand slabs through L2 -- one GPU uses groups of 8, i.e. one rasterisation band), and inside
+// a group on the diagonal the single super-blocks alternate.  Across GPUs the groups are single
+// super-blocks, which balances the ranks' shares best.
+__host__ __device__ inline bool dist_row_side(int sb_i, int sb_j, int coarse_shift) {
+    if (sb_i == sb_j) return true;
+    const int ci = sb_i >> coarse_shift, cj = sb_j >> coarse_shift;
+    if (ci != cj) return (((ci + cj) & 1) == 0) == (cj > ci);
+    return (((sb_i + sb_j) & 1) == 0) == (sb_j > sb_i);
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                int num_k_blocks, const int32_t *__restrict__ srow, const int64_t *__restrict__ ids, int64_t R,
@@ -71,7 +84,7 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // symmetric mode: checkerboard over super-blocks (see the header); sb_i = this tile's super-row
     const int sb_i = peers.sb_base[peers.rank] + (tile_y >> 1), sb_j = tile_x;
     const bool diagonal = sb_i == sb_j;
-    if (symmetric && !diagonal && ((((sb_i + sb_j) & 1) == 0) != (sb_j > sb_i))) return;
+    if (symmetric && !dist_row_side(sb_i, sb_j, peers.coarse_shift)) return;
     const bool mirror = symmetric && !diagonal;
     int32_t *Dd = peers.slab[peers.rank];                         // may alias Dm: no __restrict__
     int32_t *Dm = peers.slab[owner];                  // slab that receives the transposed tile
@@ -159,26 +172,44 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 v[e + 3] = (uint32_t)(s_i + sj.w - (int32_t)v[e + 3]);
             }
             // subtract mode (incremental update): the operands are those of removed columns and
-            // their mismatch count is taken off the resident slab
+            // their mismatch count is taken off the resident slab.  All loads of a chunk are issued
+            // before the first store (the slab pointers may alias, so the compiler would otherwise
+            // order every load behind the previous store: 32 dependent round trips per chunk).
             if (row < R) {
                 int32_t *dst = Dd + row * ldd + col;           // ldd multiple of 128, col multiple of 4: 16-byte aligned
+                if (subtract) {
+                    int4 old[8];
 #pragma unroll
-                for (int e = 0; e < 32; e += 4) {
-                    if (col + e >= cend) break;                // cend is a multiple of 4 or the padded end
-                    int4 o = make_int4((int)v[e], (int)v[e + 1], (int)v[e + 2], (int)v[e + 3]);
-                    if (subtract) {
-                        const int4 old = *reinterpret_cast<const int4 *>(dst + e);
-                        o = make_int4(old.x - o.x, old.y - o.y, old.z - o.z, old.w - o.w);
-                    }
-                    *reinterpret_cast<int4 *>(dst + e) = o;
+                    for (int e = 0; e < 32; e += 4)
+                        old[e >> 2] = col + e < cend ? *reinterpret_cast<const int4 *>(dst + e) : make_int4(0, 0, 0, 0);
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        if (col + e < cend)                    // cend is a multiple of 4 or the padded end
+                            *reinterpret_cast<int4 *>(dst + e) =
+                                make_int4(old[e >> 2].x - (int)v[e], old[e >> 2].y - (int)v[e + 1],
+                                          old[e >> 2].z - (int)v[e + 2], old[e >> 2].w - (int)v[e + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        if (col + e < cend)
+                            *reinterpret_cast<int4 *>(dst + e) = make_int4((int)v[e], (int)v[e + 1], (int)v[e + 2], (int)v[e + 3]);
                 }
             }
             if (mirror && row < R) {
                 // transposed copy: row (col + e) of the owner's slab, column = this row's sample
                 int32_t *m = Dm + (col - peers.starts[owner]) * ldd + row_global0 + row;
+                if (subtract) {
+                    int32_t old[32];
 #pragma unroll
-                for (int e = 0; e < 32; ++e)
-                    if (col + e < cend) m[e * ldd] = subtract ? m[e * ldd] - (int32_t)v[e] : (int32_t)v[e];
+                    for (int e = 0; e < 32; ++e) old[e] = col + e < cend ? m[e * ldd] : 0;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (col + e < cend) m[e * ldd] = old[e] - (int32_t)v[e];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (col + e < cend) m[e * ldd] = (int32_t)v[e];
+                }
             }
         }
         tc::tc_fence_before();
@@ -209,7 +240,7 @@ void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_
         for (int by = 0; by < tiles_y; ++by)
             for (int bx = 0; bx < tiles_x; ++bx) {
                 const int sb_i = peers.sb_base[peers.rank] + (by >> 1);
-                tiles += (!symmetric || sb_i == bx || ((((sb_i + bx) & 1) == 0) == (bx > sb_i))) ? 1 : 0;
+                tiles += (!symmetric || dist_row_side(sb_i, bx, peers.coarse_shift)) ? 1 : 0;
             }
         *ops += 2.0 * BM * BN * (double)K * (double)tiles;
     }
