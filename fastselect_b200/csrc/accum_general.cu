@@ -13,8 +13,9 @@
 // once per 16 targets; the 16 x 128 coefficient tile of each j-tile is decoded
 // from the int8 codes into shared memory.  float32 products are accumulated in
 // float32 over one 128-sample tile and then folded into a float64 accumulator, so
-// the result is accurate to ~1e-7 relative while the inner loop is 3 FP32
-// instructions per (pair, feature).  Partials are written per (row chunk, feature)
+// the result is accurate to ~1e-7 relative while the inner loop is 2 FP32
+// instructions per (pair, feature) on float32 data (the column's 1/range is applied once
+// to the column total).  Partials are written per (row chunk, feature)
 // and reduced in a fixed order: results are bitwise reproducible.
 #include <algorithm>
 
@@ -33,6 +34,18 @@ __device__ __forceinline__ float term_cont32(float a, float b, float r) {
 __device__ __forceinline__ float term_cont32(double a, double b, float r) {
     return (float)__dmul_rn(fabs(__dsub_rn(a, b)), (double)r);
 }
+
+// Inner-loop term of the accumulation.  float32 data: |a - b| only (FSUB, then one FFMA with
+// the |.| operand modifier) -- the column's 1/range is a common factor of every term of the
+// column and is applied once to the column's total, so the loop is 2 FP32 instructions per
+// (pair, feature) instead of 3.  The reference rounds |a-b|*r per term in float32 and adds in
+// float32 (MultiSURF.py:184-243); either way the sum carries float32 accumulation-order noise
+// of ~1e-7 relative, far inside the 1e-5 tolerance.  float64 data (SURF): the reference's
+// float64 product, rounded to float32 (SURF.py:153-158).
+__device__ __forceinline__ float absdiff32(float a, float b, float) { return fabsf(__fsub_rn(a, b)); }
+__device__ __forceinline__ float absdiff32(double a, double b, float r) { return term_cont32(a, b, r); }
+template <typename T>
+__device__ __forceinline__ double column_scale(float r) { return sizeof(T) == 4 ? (double)r : 1.0; }
 
 template <typename T>
 __global__ void __launch_bounds__(kAccThreads)
@@ -103,7 +116,7 @@ accum_general_kernel(const T *__restrict__ xg, int64_t n, int64_t ld, const floa
                         for (int a = 0; a < kAccRows; ++a) acc[a] += (xi[a] != xj[u]) ? c[a] : 0.0f;
                     } else {
 #pragma unroll
-                        for (int a = 0; a < kAccRows; ++a) acc[a] = fmaf(c[a], term_cont32(xi[a], xj[u], r), acc[a]);
+                        for (int a = 0; a < kAccRows; ++a) acc[a] = fmaf(c[a], absdiff32(xi[a], xj[u], r), acc[a]);
                     }
                 }
             }
@@ -111,7 +124,7 @@ accum_general_kernel(const T *__restrict__ xg, int64_t n, int64_t ld, const floa
             for (int a = 0; a < kAccRows; ++a) total += (double)acc[a];
         }
     }
-    if (live) partial[(int64_t)blockIdx.x * ld + f] = total;
+    if (live) partial[(int64_t)blockIdx.x * ld + f] = cmp ? total : total * column_scale<T>(r);
 }
 
 // ReliefF: per target row at most C*k neighbours; one thread per feature gathers
