@@ -54,7 +54,7 @@ accum_general_kernel(const T *__restrict__ xg, int64_t n, int64_t ld, const floa
                      int64_t ldn, const RowInfo *__restrict__ rinfo, int64_t R, int64_t rows_per_cta,
                      double *__restrict__ partial) {
     constexpr int FT = kChunkBytes / sizeof(T);
-    __shared__ __align__(16) float scoef[kAccJT][kAccRows];
+    __shared__ __align__(16) float scoef[2][kAccJT][kAccRows];
     __shared__ float stab[kAccRows][5];
 
     const int tid = threadIdx.x;
@@ -77,17 +77,33 @@ accum_general_kernel(const T *__restrict__ xg, int64_t n, int64_t ld, const floa
             const int a = tid / 5, q = tid % 5;
             stab[a][q] = a < nr ? (float)rinfo[rb + a].coef[q] : 0.0f;
         }
-        for (int64_t j0 = 0; j0 < n; j0 += kAccJT) {
+        // neighbour codes of a sample tile: thread = (target row a, 16 consecutive samples), one
+        // 16-byte load.  The codes of tile t + 1 are fetched while tile t is being accumulated and
+        // the decoded coefficient tiles are double-buffered, so the global-load latency of the
+        // codes is hidden and one barrier per tile suffices.
+        const int ca = tid >> 3, cchunk = tid & 7;
+        uint4 code = make_uint4(0u, 0u, 0u, 0u);
+        auto fetch_codes = [&](int64_t j0) {
+            if (ca < nr) code = *reinterpret_cast<const uint4 *>(sel + (rb + ca) * ldn + j0 + 16 * cchunk);
+        };
+        __syncthreads();                       // stab
+        fetch_codes(0);
+        int buf = 0;
+        for (int64_t j0 = 0; j0 < n; j0 += kAccJT, buf ^= 1) {
             const int nj = (int)(n - j0 < kAccJT ? n - j0 : kAccJT);
-            __syncthreads();
-            // decode the 16 x 128 coefficient tile (coalesced along j)
-            for (int e = tid; e < kAccRows * kAccJT; e += kAccThreads) {
-                const int a = e / kAccJT, jj = e % kAccJT;
-                float c = 0.0f;
-                if (a < nr && jj < nj) c = stab[a][sel[(rb + a) * ldn + j0 + jj]];
-                scoef[jj][a] = c;
+            // decode 16 coefficients of this thread's row (codes beyond the last sample are padding)
+            {
+                const uint32_t cw[4] = {code.x, code.y, code.z, code.w};
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int jj = 16 * cchunk + q;
+                    uint32_t cd = (cw[q >> 2] >> (8 * (q & 3))) & 0xffu;
+                    cd = cd > 4u ? 0u : cd;             // padding bytes beyond sample n are not codes
+                    scoef[buf][jj][ca] = (ca < nr && jj < nj) ? stab[ca][cd] : 0.0f;
+                }
             }
             __syncthreads();
+            if (j0 + kAccJT < n) fetch_codes(j0 + kAccJT);
             float acc[kAccRows];
 #pragma unroll
             for (int a = 0; a < kAccRows; ++a) acc[a] = 0.0f;
@@ -104,7 +120,7 @@ accum_general_kernel(const T *__restrict__ xg, int64_t n, int64_t ld, const floa
 #pragma unroll
                 for (int u = 0; u < kAhead; ++u) {
                     if (jb + u >= nj) break;
-                    const float4 *cp = reinterpret_cast<const float4 *>(scoef[jb + u]);
+                    const float4 *cp = reinterpret_cast<const float4 *>(scoef[buf][jb + u]);
                     float c[kAccRows];
 #pragma unroll
                     for (int q = 0; q < kAccRows / 4; ++q) {
