@@ -47,6 +47,41 @@ __device__ __forceinline__ float absdiff32(double a, double b, float r) { return
 template <typename T>
 __device__ __forceinline__ double column_scale(float r) { return sizeof(T) == 4 ? (double)r : 1.0; }
 
+// One 128-sample tile of the accumulation for this thread's column: sample values are fetched
+// kAhead rows ahead of their use, the 16 coefficients of a sample come as four 16-byte broadcast
+// loads from shared memory.  FULL: the tile has all kAccJT samples (no bounds checks).
+template <typename T, bool FULL, bool CMP>
+__device__ __forceinline__ void accumulate_tile(const T *__restrict__ xp, int64_t ld, int nj,
+                                                const float (*__restrict__ coef)[kAccRows],
+                                                const T (&xi)[kAccRows], float r, float (&acc)[kAccRows]) {
+    constexpr int kAhead = 8;
+    const int jend = FULL ? kAccJT : nj;
+#pragma unroll 1
+    for (int jb = 0; jb < jend; jb += kAhead, xp += (int64_t)kAhead * ld) {
+        T xj[kAhead];
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) xj[u] = (FULL || jb + u < nj) ? xp[(int64_t)u * ld] : xp[0];
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) {
+            // samples beyond nj have coefficient 0 in the tile: no check needed, the term vanishes
+            const float4 *cp = reinterpret_cast<const float4 *>(coef[jb + u]);
+            float c[kAccRows];
+#pragma unroll
+            for (int q = 0; q < kAccRows / 4; ++q) {
+                const float4 v = cp[q];
+                c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+            }
+            if (CMP) {
+#pragma unroll
+                for (int a = 0; a < kAccRows; ++a) acc[a] += (xi[a] != xj[u]) ? c[a] : 0.0f;
+            } else {
+#pragma unroll
+                for (int a = 0; a < kAccRows; ++a) acc[a] = fmaf(c[a], absdiff32(xi[a], xj[u], r), acc[a]);
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kAccThreads)
 accum_general_kernel(const T *__restrict__ xg, int64_t n, int64_t ld, const float *__restrict__ recip,
@@ -107,34 +142,15 @@ accum_general_kernel(const T *__restrict__ xg, int64_t n, int64_t ld, const floa
             float acc[kAccRows];
 #pragma unroll
             for (int a = 0; a < kAccRows; ++a) acc[a] = 0.0f;
-            // the chunk type is uniform per warp (float32: 32 columns per chunk), so the branch
-            // below does not diverge; sample values are fetched 8 rows ahead of their use
-            constexpr int kAhead = 8;
-            for (int jb = 0; jb < nj; jb += kAhead) {
-                T xj[kAhead];
-#pragma unroll
-                for (int u = 0; u < kAhead; ++u) {
-                    const int jj = jb + u < nj ? jb + u : nj - 1;
-                    xj[u] = xg[(j0 + jj) * ld + fc];
-                }
-#pragma unroll
-                for (int u = 0; u < kAhead; ++u) {
-                    if (jb + u >= nj) break;
-                    const float4 *cp = reinterpret_cast<const float4 *>(scoef[buf][jb + u]);
-                    float c[kAccRows];
-#pragma unroll
-                    for (int q = 0; q < kAccRows / 4; ++q) {
-                        const float4 v = cp[q];
-                        c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
-                    }
-                    if (cmp) {
-#pragma unroll
-                        for (int a = 0; a < kAccRows; ++a) acc[a] += (xi[a] != xj[u]) ? c[a] : 0.0f;
-                    } else {
-#pragma unroll
-                        for (int a = 0; a < kAccRows; ++a) acc[a] = fmaf(c[a], absdiff32(xi[a], xj[u], r), acc[a]);
-                    }
-                }
+            // the chunk type is uniform per warp (float32: 32 columns per chunk), so this branch does
+            // not diverge; full tiles run without any per-sample bounds check
+            const T *xp = xg + j0 * ld + fc;
+            if (nj == kAccJT) {
+                if (cmp) accumulate_tile<T, true, true>(xp, ld, nj, scoef[buf], xi, r, acc);
+                else accumulate_tile<T, true, false>(xp, ld, nj, scoef[buf], xi, r, acc);
+            } else {
+                if (cmp) accumulate_tile<T, false, true>(xp, ld, nj, scoef[buf], xi, r, acc);
+                else accumulate_tile<T, false, false>(xp, ld, nj, scoef[buf], xi, r, acc);
             }
 #pragma unroll
             for (int a = 0; a < kAccRows; ++a) total += (double)acc[a];
