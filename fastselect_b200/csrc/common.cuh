@@ -251,7 +251,6 @@ struct fs_dataset {
     bool peers_on = false;
     int32_t *peer_slab = nullptr;
     size_t peer_slab_count = 0;
-    std::vector<void *> peer_mapped;         // cudaIpcOpenMemHandle results (to close)
     void (*barrier_fn)(void *) = nullptr;
     void *barrier_ctx = nullptr;
     bool last_dist_exchanged = false;        // the last distance launch stored into peer slabs

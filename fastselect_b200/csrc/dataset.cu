@@ -4,6 +4,7 @@
 // of the reference's fit (MultiSURF.py:409-425, SURF.py:347-365, ReliefF.py:366-391)
 // and TuRF's X[:, active] copy (TuRF.py:110).
 #include <algorithm>
+#include <array>
 #include <cstring>
 #include <mutex>
 #include <numeric>
@@ -70,6 +71,61 @@ void pinned_give(void *ptr, size_t bytes) {
         return;
     }
     g_pinned_free.push_back(PinnedBlock{ptr, bytes});
+}
+
+// Process-wide caches of the multi-GPU distance slabs: allocating an IPC-exportable slab and
+// opening the peers' handles cost milliseconds, and every fit opens a new data set.  A slab
+// returns to the free list when its data set is destroyed (it keeps its IPC handle, so the peers'
+// mappings stay valid for the next fit); opened peer mappings are kept until the process exits.
+namespace {
+struct SlabEntry {
+    int device;
+    int32_t *ptr;
+    size_t count;
+    bool in_use;
+};
+std::mutex g_slab_mu;
+std::vector<SlabEntry> g_slabs;
+std::vector<std::pair<std::array<char, 64>, void *>> g_ipc_open;
+}  // namespace
+
+static int32_t *slab_take(int device, size_t count, size_t *got) {
+    std::lock_guard<std::mutex> lk(g_slab_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_slabs.size(); ++i)
+        if (!g_slabs[i].in_use && g_slabs[i].device == device && g_slabs[i].count >= count &&
+            (best < 0 || g_slabs[i].count < g_slabs[best].count))
+            best = i;
+    if (best < 0) {
+        int32_t *p = nullptr;
+        // plain cudaMalloc: stream-ordered pool memory cannot be exported through CUDA IPC
+        FS_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(int32_t)));
+        g_slabs.push_back(SlabEntry{device, p, count, false});
+        best = (int)g_slabs.size() - 1;
+    }
+    g_slabs[best].in_use = true;
+    *got = g_slabs[best].count;
+    return g_slabs[best].ptr;
+}
+
+static void slab_give(int32_t *ptr) {
+    std::lock_guard<std::mutex> lk(g_slab_mu);
+    for (auto &e : g_slabs)
+        if (e.ptr == ptr) e.in_use = false;
+}
+
+static void *ipc_open_cached(const char *handle_bytes) {
+    std::lock_guard<std::mutex> lk(g_slab_mu);
+    std::array<char, 64> key;
+    memcpy(key.data(), handle_bytes, 64);
+    for (auto &kv : g_ipc_open)
+        if (kv.first == key) return kv.second;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_bytes, sizeof(h));
+    void *p = nullptr;
+    FS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    g_ipc_open.emplace_back(key, p);
+    return p;
 }
 
 // keep freed blocks in the device's default memory pool (no trimming at synchronisation)
@@ -645,11 +701,9 @@ int fs_dataset_peer_slab(fs_dataset *ds, int64_t rows, void *ipc_handle_out, voi
         const size_t count = (size_t)round_up(std::max<int64_t>(rows, 1), 128) * (size_t)round_up(ds->n, 128);
         if (ds->peer_slab == nullptr || ds->peer_slab_count < count) {
             FS_REQUIRE(!ds->peers_on, FS_ERR_STATE, "fs_dataset_peer_slab: peers already configured");
-            if (ds->peer_slab) cudaFree(ds->peer_slab);
+            if (ds->peer_slab) slab_give(ds->peer_slab);
             ds->peer_slab = nullptr;
-            // plain cudaMalloc: stream-ordered pool memory cannot be exported through CUDA IPC
-            FS_CUDA(cudaMalloc(reinterpret_cast<void **>(&ds->peer_slab), count * sizeof(int32_t)));
-            ds->peer_slab_count = count;
+            ds->peer_slab = slab_take(ds->device, count, &ds->peer_slab_count);
         }
         if (ipc_handle_out) {
             cudaIpcMemHandle_t h;
@@ -690,8 +744,6 @@ int fs_dataset_set_peers(fs_dataset *ds, int32_t rank, int32_t world, const int6
         FS_REQUIRE((size_t)round_up(std::max<int64_t>(pr.starts[rank + 1] - pr.starts[rank], 1), 128) *
                            (size_t)round_up(ds->n, 128) <= ds->peer_slab_count,
                    FS_ERR_INVALID, "fs_dataset_set_peers: slab smaller than this rank's shard");
-        for (void *m : ds->peer_mapped) cudaIpcCloseMemHandle(m);
-        ds->peer_mapped.clear();
         ds->peers_on = false;
         for (int r = 0; r < world; ++r) {
             if (r == rank) {
@@ -699,12 +751,7 @@ int fs_dataset_set_peers(fs_dataset *ds, int32_t rank, int32_t world, const int6
             } else if (raw_ptrs) {
                 pr.slab[r] = static_cast<int32_t *>(raw_ptrs[r]);
             } else {
-                cudaIpcMemHandle_t h;
-                memcpy(&h, static_cast<const char *>(ipc_handles) + (size_t)r * sizeof(h), sizeof(h));
-                void *p = nullptr;
-                FS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-                ds->peer_mapped.push_back(p);
-                pr.slab[r] = static_cast<int32_t *>(p);
+                pr.slab[r] = static_cast<int32_t *>(ipc_open_cached(static_cast<const char *>(ipc_handles) + (size_t)r * 64));
             }
         }
         ds->peers = pr;
@@ -722,8 +769,7 @@ int fs_dataset_destroy(fs_dataset *ds) {
     if (!ds) return FS_OK;
     cudaSetDevice(ds->device);
     cudaStreamSynchronize(ds->stream);
-    for (void *m : ds->peer_mapped) cudaIpcCloseMemHandle(m);
-    if (ds->peer_slab) cudaFree(ds->peer_slab);
+    if (ds->peer_slab) slab_give(ds->peer_slab);
     alloc_stream() = ds->stream;
     delete ds;
     return FS_OK;
