@@ -103,6 +103,17 @@ __device__ __forceinline__ void expand_v3(uint32_t cw, uint32_t &u0, uint32_t &u
     w1 = __byte_perm(a0, a1, 0x7362);
 }
 
+// At is stored as e2m1 (FP4) nibbles, two samples per byte (low nibble = even sample), for the
+// tcgen05 kind::mxf4 accumulation GEMM: 1.0 is the nibble 0x2.  pack_fp4_flags turns four 0/1
+// flag bytes (samples s..s+3) into two bytes of nibbles.
+__device__ __forceinline__ uint32_t pack_fp4_flags(uint32_t e) {
+    const uint32_t t = (e << 1) | (e >> 3);          // byte 0: b0<<1 | b1<<5,  byte 2: b2<<1 | b3<<5
+    return __byte_perm(t, 0u, 0x4420);               // (t.b0, t.b2, 0, 0)
+}
+__device__ __forceinline__ uint2 pack_fp4_flags16(uint32_t e0, uint32_t e1, uint32_t e2, uint32_t e3) {
+    return make_uint2(pack_fp4_flags(e0) | (pack_fp4_flags(e1) << 16), pack_fp4_flags(e2) | (pack_fp4_flags(e3) << 16));
+}
+
 template <typename Tin>
 __global__ void __launch_bounds__(256) onehot_encode_kernel(
     const Tin *__restrict__ x, int64_t ldx, const int64_t *__restrict__ perm, const int64_t *__restrict__ tcol,
@@ -312,8 +323,9 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
             e1.z = w.z & 0x01010101u; e0.z = ((w.z >> 1) & 0x01010101u) ^ 0x01010101u ^ e1.z;
             e1.w = w.w & 0x01010101u; e0.w = ((w.w >> 1) & 0x01010101u) ^ 0x01010101u ^ e1.w;
             const int64_t o = r0 + 16 * seg;                                  // r0, ldt multiples of 128: aligned
-            *reinterpret_cast<uint4 *>(At + (int64_t)(k0 + 2 * c) * ldt + o) = e0;
-            *reinterpret_cast<uint4 *>(At + (int64_t)(k0 + 2 * c + 1) * ldt + o) = e1;
+            const int64_t lda = ldt >> 1;                                     // At: two samples per byte
+            *reinterpret_cast<uint2 *>(At + (int64_t)(k0 + 2 * c) * lda + (o >> 1)) = pack_fp4_flags16(e0.x, e0.y, e0.z, e0.w);
+            *reinterpret_cast<uint2 *>(At + (int64_t)(k0 + 2 * c + 1) * lda + (o >> 1)) = pack_fp4_flags16(e1.x, e1.y, e1.z, e1.w);
             *reinterpret_cast<uint4 *>(codesT + (c0 + c) * ldt + o) = w;
         }
     } else {
@@ -327,13 +339,22 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
             o.y = __vcmpeq4(src[1], val) & 0x01010101u;
             o.z = __vcmpeq4(src[2], val) & 0x01010101u;
             o.w = __vcmpeq4(src[3], val) & 0x01010101u;
-            int8_t *dst = At + (int64_t)(k0 + kk) * ldt + r0 + 16 * seg;     // r0, ldt multiples of 128: aligned
+            // two samples per byte (FP4 nibbles); r0, ldt multiples of 128: aligned
+            int8_t *dst = At + (int64_t)(k0 + kk) * (ldt >> 1) + ((r0 + 16 * seg) >> 1);
+            const uint2 pk = pack_fp4_flags16(o.x, o.y, o.z, o.w);
             if (16 * seg + 16 <= nrows) {
-                *reinterpret_cast<uint4 *>(dst) = o;
+                *reinterpret_cast<uint2 *>(dst) = pk;
             } else {
-                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-                for (int b = 0; b < 16; ++b)
-                    if (16 * seg + b < nrows) dst[b] = (int8_t)((ow[b >> 2] >> (8 * (b & 3))) & 0xffu);
+                // ragged last row tile: flags of samples beyond nrows are zero (their codes are 0 in
+                // shared memory but may match value 0: mask them), whole bytes only where a sample lives
+                const uint32_t pw[2] = {pk.x, pk.y};
+                for (int b = 0; b < 8; ++b) {
+                    const int s0 = 16 * seg + 2 * b;
+                    if (s0 >= nrows) break;
+                    uint32_t byte = (pw[b >> 2] >> (8 * (b & 3))) & 0xffu;
+                    if (s0 + 1 >= nrows) byte &= 0x0fu;
+                    dst[b] = (int8_t)byte;
+                }
             }
         }
         for (int item = tid; item < ncols * 8; item += 256) {
@@ -476,18 +497,22 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
             e1.z = w.z & 0x01010101u; e0.z = ((w.z >> 1) & 0x01010101u) ^ 0x01010101u ^ e1.z;
             e1.w = w.w & 0x01010101u; e0.w = ((w.w >> 1) & 0x01010101u) ^ 0x01010101u ^ e1.w;
             const int64_t o = r0 + 16 * seg;                                  // r0, ldt multiples of 128: aligned
-            int8_t *a0 = At + (k0 + 2 * cc) * ldt + o, *a1 = a0 + ldt;
+            const int64_t lda = ldt >> 1;                                     // At: two samples per byte (FP4 nibbles)
+            int8_t *a0 = At + (k0 + 2 * cc) * lda + (o >> 1), *a1 = a0 + lda;
             uint8_t *ct = codesT + (c0 + cc) * ldt + o;
             if (16 * seg + 16 <= nrows) {
-                *reinterpret_cast<uint4 *>(a0) = e0;
-                *reinterpret_cast<uint4 *>(a1) = e1;
+                *reinterpret_cast<uint2 *>(a0) = pack_fp4_flags16(e0.x, e0.y, e0.z, e0.w);
+                *reinterpret_cast<uint2 *>(a1) = pack_fp4_flags16(e1.x, e1.y, e1.z, e1.w);
                 *reinterpret_cast<uint4 *>(ct) = w;
             } else {
-                for (int b = 0; b < 16 && 16 * seg + b < nrows; ++b) {
-                    const uint32_t code = code_cr[cc][16 * seg + b];
-                    a0[b] = (int8_t)(code == 0u);
-                    a1[b] = (int8_t)(code == 1u);
-                    ct[b] = (uint8_t)code;
+                for (int b = 0; b < 16 && 16 * seg + b < nrows; b += 2) {
+                    const uint32_t ca = code_cr[cc][16 * seg + b];
+                    const bool two = 16 * seg + b + 1 < nrows;
+                    const uint32_t cb = two ? code_cr[cc][16 * seg + b + 1] : 3u;     // 3 matches no value
+                    a0[b >> 1] = (int8_t)((ca == 0u ? 0x02u : 0u) | (cb == 0u ? 0x20u : 0u));
+                    a1[b >> 1] = (int8_t)((ca == 1u ? 0x02u : 0u) | (cb == 1u ? 0x20u : 0u));
+                    ct[b] = (uint8_t)ca;
+                    if (two) ct[b + 1] = (uint8_t)cb;
                 }
             }
         }
@@ -568,7 +593,7 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
         ws.Wd.reserve((size_t)n * ws.K);
         ws.srow.reserve(ws.ldt);   // padded: the distance epilogue reads it in 16-byte vectors
     }
-    ws.At.reserve((size_t)ws.K * ws.ldt);
+    ws.At.reserve((size_t)ws.K * (ws.ldt / 2));          // FP4 nibbles: two samples per byte
     ws.codesT.reserve((size_t)pt * ws.ldt + 512);   // slack: the accumulation epilogue reads whole 128-byte runs
     if (ws.have_codes) ws.codes.reserve((size_t)n * ws.ldc);
     ws.krow.reserve(ws.K);
@@ -586,7 +611,7 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
                                       (size_t)(ws.u_hi - ws.u_lo), st));
             FS_CUDA(cudaMemset2DAsync(ws.Wd.ptr + ws.K_used, (size_t)ws.K, 0, (size_t)(ws.K - ws.K_used), (size_t)n, st));
         }
-        FS_CUDA(cudaMemsetAsync(ws.At.ptr + (size_t)ws.K_used * ws.ldt, 0, (size_t)(ws.K - ws.K_used) * ws.ldt, st));
+        FS_CUDA(cudaMemsetAsync(ws.At.ptr + (size_t)ws.K_used * (ws.ldt / 2), 0, (size_t)(ws.K - ws.K_used) * (ws.ldt / 2), st));
     }
     const unsigned grid = (unsigned)(ceil_div(pt, ENC_COLS) * ceil_div(n, ENC_ROWS));
     const int as_f32 = (ds->arith == FS_ARITH_F32 && ds->dtype == FS_F64) ? 1 : 0;
@@ -762,10 +787,11 @@ void launch_accum_tensor(fs_dataset *ds, const WorkSet &ws, int algo, const int6
         return;
     }
     ds->tile_desc.reserve(tc_accum_tile_desc_ints());
-    // K of this GEMM is the sample index: rows of At and of the masks are n bytes long
-    const CUtensorMap tat = make_tmap_u8_sw128(ws.At.ptr, (uint64_t)n, (uint64_t)ws.K, (uint64_t)ws.ldt, 128);
-    const CUtensorMap tmh = make_tmap_u8_sw128(ds->maskH.ptr, (uint64_t)n, (uint64_t)R, (uint64_t)ldn, 256);
-    const CUtensorMap tmm = make_tmap_u8_sw128(ds->maskM.ptr, (uint64_t)n, (uint64_t)R, (uint64_t)ldn, 256);
+    // K of this GEMM is the sample index; At and the masks hold FP4 nibbles: rows of (n + 1) / 2 bytes
+    const uint64_t row_bytes = (uint64_t)((n + 1) / 2);
+    const CUtensorMap tat = make_tmap_u8_sw128(ws.At.ptr, row_bytes, (uint64_t)ws.K, (uint64_t)(ws.ldt / 2), 128);
+    const CUtensorMap tmh = make_tmap_u8_sw128(ds->maskH.ptr, row_bytes, (uint64_t)R, (uint64_t)(ldn / 2), 240);
+    const CUtensorMap tmm = make_tmap_u8_sw128(ds->maskM.ptr, row_bytes, (uint64_t)R, (uint64_t)(ldn / 2), 240);
     const int parts = launch_tc_accum(tat, tmh, tmm, n, R, d_row_ids, contiguous, rinfo, ws.codesT.ptr, ws.ldt,
                                       ws.krow.ptr, ws.K_used, ds->tpartial, ds->tile_desc.ptr, st, launches,
                                       h_row_ids, ds->y_sorted.data(), ds->cls_start.data(), ops);

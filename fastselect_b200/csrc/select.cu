@@ -120,29 +120,39 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(const double *__r
     const double thresh = s_thresh;
     const int32_t yi = y[self];
     int nh = 0, nm = 0, nfh = 0, nfm = 0;
-    for (int64_t j = tid; j < n; j += 256) {
-        int code = FS_MASK_NONE;
-        if (j != self) {
-            double d = load_d(Dc, Dd, base + j);
-            if (ALGO == FS_SURF) d = (double)(float)d;
-            const bool hit = (y[j] == yi);
-            if (d < thresh) {
-                code = hit ? FS_MASK_NEAR_HIT : FS_MASK_NEAR_MISS;
-            } else if (use_star) {
-                if (!hit) code = FS_MASK_FAR_MISS;
-                else if (ALGO == FS_SURF) code = FS_MASK_FAR_HIT;
+    // two samples per thread and step: the signed masks of the tensor-core accumulation
+    // (c_ij = -aH*mH + aM*mM, mH/mM in {-1, 0, 1}) are stored as e2m1 (FP4) nibbles, two samples per
+    // byte, low nibble = even sample: +1 -> 0x2, -1 -> 0xA.  Row pitch ldn / 2 bytes.
+    for (int64_t j0 = 2 * (int64_t)tid; j0 < n; j0 += 512) {
+        uint32_t bh = 0, bm = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t j = j0 + h;
+            if (j >= n) break;
+            int code = FS_MASK_NONE;
+            if (j != self) {
+                double d = load_d(Dc, Dd, base + j);
+                if (ALGO == FS_SURF) d = (double)(float)d;
+                const bool hit = (y[j] == yi);
+                if (d < thresh) {
+                    code = hit ? FS_MASK_NEAR_HIT : FS_MASK_NEAR_MISS;
+                } else if (use_star) {
+                    if (!hit) code = FS_MASK_FAR_MISS;
+                    else if (ALGO == FS_SURF) code = FS_MASK_FAR_HIT;
+                }
             }
+            sel[base + j] = (int8_t)code;
+            bh |= (code == FS_MASK_NEAR_HIT ? 0x2u : code == FS_MASK_FAR_HIT ? 0xAu : 0u) << (4 * h);
+            bm |= (code == FS_MASK_NEAR_MISS ? 0x2u : code == FS_MASK_FAR_MISS ? 0xAu : 0u) << (4 * h);
+            nh += (code == FS_MASK_NEAR_HIT);
+            nm += (code == FS_MASK_NEAR_MISS);
+            nfm += (code == FS_MASK_FAR_MISS);
+            nfh += (code == FS_MASK_FAR_HIT);
         }
-        sel[base + j] = (int8_t)code;
         if (mask_h) {
-            // signed masks of the tensor-core accumulation: c_ij = -aH*mH + aM*mM
-            mask_h[base + j] = (int8_t)((code == FS_MASK_NEAR_HIT) - (code == FS_MASK_FAR_HIT));
-            mask_m[base + j] = (int8_t)((code == FS_MASK_NEAR_MISS) - (code == FS_MASK_FAR_MISS));
+            mask_h[(base >> 1) + (j0 >> 1)] = (int8_t)bh;
+            mask_m[(base >> 1) + (j0 >> 1)] = (int8_t)bm;
         }
-        nh += (code == FS_MASK_NEAR_HIT);
-        nm += (code == FS_MASK_NEAR_MISS);
-        nfm += (code == FS_MASK_FAR_MISS);
-        nfh += (code == FS_MASK_FAR_HIT);
     }
     nh = block_sum(nh, si);
     nm = block_sum(nm, si);

@@ -45,24 +45,26 @@ namespace fs {
 
 namespace {
 constexpr int BM = 128;   // one-hot rows per work unit
-constexpr int BN = 256;   // target rows per tile
-constexpr int BK = 128;   // samples (bytes) per K block
+constexpr int BN = 240;   // target rows per tile (2 accumulators x 240 + 8 scale-factor columns <= 512 TMEM columns)
+constexpr int BK = 128;   // bytes of K per block ...
+constexpr int KS = 256;   // ... = 256 samples (FP4 nibbles)
 constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK;                  // 16 KB
-constexpr int B_BYTES = BN * BK;                  // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 48 KB
+constexpr int B_BYTES = BN * BK;                  // 30 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 46 KB (a multiple of 1024: swizzle-atom aligned)
 constexpr int GROUP = 8;                          // target tiles per work unit
 constexpr int MAX_TILES = 256;                    // tile descriptors per launch (staged in shared memory)
-constexpr int CONST_BYTES = 2 * BN * 16;          // [2][BN] x {int2 coefficient limbs; int rs; int pad}
+constexpr int CONST_BYTES = 2 * 256 * 16;         // [2][BN padded to 256] x {int2 coefficient limbs; int rs; int pad}
 constexpr int DESC_BYTES = MAX_TILES * 32;
 constexpr int BAR_BYTES = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + CONST_BYTES + DESC_BYTES;
-constexpr int EPI_WARPS = 16;            // epilogue warps: 4 per TMEM lane quarter, one column quarter each
+constexpr int EPI_WARPS = 12;            // epilogue warps: 3 per TMEM lane quarter, one column part each
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = 64 + EPI_THREADS; // TMA warp, MMA warp, epilogue warps
-constexpr int HALF = BN / (EPI_WARPS / 4); // target columns per epilogue thread
+constexpr int HALF = BN / (EPI_WARPS / 4); // 80 target columns per epilogue thread
 constexpr int PARTS = EPI_WARPS / 4;      // column parts = partial vectors per (group, one-hot row)
-constexpr int TMEM_COLS = 512;                    // 2 accumulator buffers x 256 columns
+constexpr int TMEM_COLS = 512;            // 2 accumulator buffers x 240 columns + scale factors
+constexpr int SF_COL = 2 * BN;            // 8 columns of UE8M0 1.0 (0x7f) for both operands' block scales
 
 // A tile of target rows and the K blocks (of 128 samples) its two masks can be non-zero in:
 // hit mask: blocks [hb0, hb1); miss mask: blocks [0, ib0) and [ib1, num_k_blocks).
@@ -72,6 +74,7 @@ struct __align__(16) TileDesc {
     int32_t pad0, pad1;
 };
 static_assert(sizeof(TileDesc) == 32, "TileDesc layout");
+static_assert(STAGE_BYTES % 1024 == 0 && HALF % 16 == 0 && SF_COL + 8 <= TMEM_COLS, "tile shape");
 
 // Fixed-point image of a per-target coefficient c (|c| <= 1): C = round(c * 2^52) split into a
 // signed high limb and a 26-bit low limb, so that c * t for an integer t is accumulated EXACTLY
@@ -129,6 +132,14 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // block scale factors of both operands: UE8M0 1.0 everywhere (8 columns cover M = 128 and N <= 256)
+    if (warp >= 2 && warp < 6) {
+        for (int c = 0; c < 8; ++c) tc::tmem_st_32x1(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + SF_COL + c, 0x7f7f7f7fu);
+        tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -170,7 +181,7 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                 for (int t = g * group_tiles; t < tile_end; ++t) {
                     const TileDesc d = s_tiles[t];
                     // a partial tile (class tail) only needs N = its row count rounded up to 16
-                    const uint32_t idesc = tc::make_idesc_i8(BM, ((d.rows + 15) >> 4) << 4);
+                    const uint32_t idesc = tc::make_idesc_mxf4(BM, ((d.rows + 15) >> 4) << 4);
                     for (int phase = 0; phase < 2; ++phase) {
                         const int nblk = phase == 0 ? d.hb1 - d.hb0 : d.ib0 + (num_k_blocks - d.ib1);
                         if (nblk == 0) continue;                          // mask is all zero: nothing to add
@@ -192,7 +203,8 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                             const uint64_t db = tc::make_smem_desc_sw128(sa + A_BYTES);
 #pragma unroll
                             for (int k = 0; k < BK / 32; ++k) {
-                                tc::mma_i8(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, have);
+                                tc::mma_mxf4(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, tmem_base + SF_COL,
+                                             tmem_base + SF_COL, have);
                                 have = 1;
                             }
                             tc::tc_commit(&empty_bar[s]);
@@ -273,8 +285,8 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                     ++item;
                     // per-target constants: c = -aH (hit phase) or +aM (miss phase) as fixed-point
                     // limbs; rs = mask row sum
-                    int2 *s_c = reinterpret_cast<int2 *>(s_const + buf * BN * 16);
-                    int32_t *s_rs = reinterpret_cast<int32_t *>(s_const + buf * BN * 16 + BN * 8);
+                    int2 *s_c = reinterpret_cast<int2 *>(s_const + buf * 256 * 16);
+                    int32_t *s_rs = reinterpret_cast<int32_t *>(s_const + buf * 256 * 16 + 256 * 8);
                     if (ethread < BN) {
                         double c = 0.0;
                         int rs = 0;
@@ -291,20 +303,21 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                     tc::tc_fence_after();
                     const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * HALF);
 #pragma unroll
-                    for (int c0 = 0; c0 < HALF; c0 += 32) {
-                        uint32_t v[32];
-                        tc::tmem_ld_32x32(tacc + c0, v);
+                    for (int c0 = 0; c0 < HALF; c0 += 16) {
+                        uint32_t v[16];                    // FP32 accumulators holding exact integers
+                        tc::tmem_ld_32x16(tacc + c0, v);
                         tc::tmem_ld_wait();
                         const int4 *cc = reinterpret_cast<const int4 *>(s_c + half * HALF + c0);
                         const int4 *rr = reinterpret_cast<const int4 *>(s_rs + half * HALF + c0);
 #pragma unroll
-                        for (int e = 0; e < 32; e += 4) {
+                        for (int e = 0; e < 16; e += 4) {
                             const uint32_t w = oh[(c0 + e) >> 2];
                             const uint32_t own = __vcmpeq4(w, own4), lst = __vcmpeq4(w, last4);
                             const int4 rs4 = rr[e >> 2];
                             const int4 ca = cc[e >> 1], cb = cc[(e >> 1) + 1];   // (Chi, Clo) of two targets each
                             // t = own ? rs - G : (last ? G : 0)
-                            const int g0 = (int)v[e], g1 = (int)v[e + 1], g2 = (int)v[e + 2], g3 = (int)v[e + 3];
+                            const int g0 = tc::f32_to_int_exact(v[e]), g1 = tc::f32_to_int_exact(v[e + 1]);
+                            const int g2 = tc::f32_to_int_exact(v[e + 2]), g3 = tc::f32_to_int_exact(v[e + 3]);
                             const int t0 = (own & 0x000000ffu) ? rs4.x - g0 : ((lst & 0x000000ffu) ? g0 : 0);
                             const int t1 = (own & 0x0000ff00u) ? rs4.y - g1 : ((lst & 0x0000ff00u) ? g1 : 0);
                             const int t2 = (own & 0x00ff0000u) ? rs4.z - g2 : ((lst & 0x00ff0000u) ? g2 : 0);
@@ -343,7 +356,7 @@ struct AccumPlan {
 static AccumPlan make_plan(int64_t n, int64_t R, bool contiguous, const int64_t *h_ids, const int32_t *h_y,
                            const int64_t *h_cls_start) {
     AccumPlan plan;
-    const int nkb = (int)ceil_div(n, BK);
+    const int nkb = (int)ceil_div(n, KS);
     auto add = [&](int64_t row0, int64_t rows, int64_t hs, int64_t he, bool mixed) {
         TileDesc d{};
         d.row0 = (int32_t)row0;
@@ -351,11 +364,11 @@ static AccumPlan make_plan(int64_t n, int64_t R, bool contiguous, const int64_t 
         if (mixed) {
             d.hb0 = 0; d.hb1 = nkb; d.ib0 = nkb; d.ib1 = nkb;      // both masks over every block
         } else {
-            d.hb0 = (int32_t)(hs / BK);
-            d.hb1 = (int32_t)ceil_div(he, BK);
+            d.hb0 = (int32_t)(hs / KS);
+            d.hb1 = (int32_t)ceil_div(he, KS);
             // blocks entirely inside [hs, he) hold no misses of this class
-            d.ib0 = (int32_t)ceil_div(hs, BK);
-            d.ib1 = he == n ? nkb : (int32_t)(he / BK);
+            d.ib0 = (int32_t)ceil_div(hs, KS);
+            d.ib1 = he == n ? nkb : (int32_t)(he / KS);
             if (d.ib1 < d.ib0) d.ib1 = d.ib0;
         }
         plan.blocks += (double)((d.hb1 - d.hb0) + d.ib0 + (nkb - d.ib1)) * (double)(((rows + 15) >> 4) << 4) / BN;
@@ -395,7 +408,7 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
     // of L2 (else every re-read goes to HBM and the kernel turns DRAM-bound for large n) by
     // cutting the tiles into more, smaller groups of equal size.
     auto groups_for = [&](int nt) {
-        const int64_t want = ceil_div((int64_t)sms * BM * n, (int64_t)60 << 20);
+        const int64_t want = ceil_div((int64_t)sms * BM * (n / 2), (int64_t)60 << 20);   // At rows are n / 2 bytes
         const int64_t g = std::max<int64_t>(ceil_div(nt, GROUP), std::min<int64_t>(nt, want));
         return (int)g;
     };
@@ -415,14 +428,14 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
         const int units = m_blocks * groups;
         const int grid = units < sms ? units : sms;
         tc_accum_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(
-            tmap_at, tmap_mh, tmap_mm, (int)ceil_div(n, BK), R, reinterpret_cast<const TileDesc *>(d_tiles), nt,
+            tmap_at, tmap_mh, tmap_mm, (int)ceil_div(n, KS), R, reinterpret_cast<const TileDesc *>(d_tiles), nt,
             groups, group_tiles, m_blocks, d_ids, contiguous ? 1 : 0, rinfo, codesT, ldt, krow, K_rows,
             tpartial.ptr + (size_t)groups_done * PARTS * K_rows);
         FS_CUDA(cudaGetLastError());
         ++*launches;
         groups_done += groups;
     }
-    if (ops) *ops += 2.0 * BM * BN * BK * plan.blocks * (double)m_blocks;
+    if (ops) *ops += 2.0 * BM * BN * KS * plan.blocks * (double)m_blocks;
     return PARTS * groups_done;
 }
 
