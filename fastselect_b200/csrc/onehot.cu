@@ -103,6 +103,18 @@ __device__ __forceinline__ void expand_v3(uint32_t cw, uint32_t &u0, uint32_t &u
     w1 = __byte_perm(a0, a1, 0x7362);
 }
 
+// FP4 (e2m1 nibble) images of 4 genotype codes: one byte per column -- low nibble = row v = 0,
+// high nibble = row v = 1.  U: [c = v] -> 1.0 = 0x2.  Wd: [c = v] + [c != last] in {0, 1, 2} ->
+// 0x0 / 0x2 / 0x4, i.e. the bytes 0x24 (code 0), 0x42 (code 1), 0x00 (code 2).
+__device__ __forceinline__ void expand_v3_fp4(uint32_t cw, uint32_t &u, uint32_t &w, int &cnt) {
+    const uint32_t e1 = cw & 0x01010101u, e2 = (cw >> 1) & 0x01010101u;
+    const uint32_t ne = e2 ^ 0x01010101u;             // [code != last]
+    const uint32_t e0 = ne ^ e1;                      // [code == 0]
+    cnt += __popc(ne);
+    u = (e0 << 1) | (e1 << 5);
+    w = (e0 << 2) | (e0 << 5) | (e1 << 1) | (e1 << 6);
+}
+
 // At is stored as e2m1 (FP4) nibbles, two samples per byte (low nibble = even sample), for the
 // tcgen05 kind::mxf4 accumulation GEMM: 1.0 is the nibble 0x2.  pack_fp4_flags turns four 0/1
 // flag bytes (samples s..s+3) into two bytes of nibbles.
@@ -238,34 +250,37 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
     // ---- step 2: U[r, k0..k1), Wd[r, k0..k1), s[r]
     // fast path (every column of the tile has 3 values and k0 is 16-byte aligned, i.e. 0/1/2
     // genotypes): 8 codes -> 16 bytes of U and of Wd, built with shifts
-    const bool v3 = __syncthreads_and((tid >= ncols) || clast[tid < ncols ? tid : 0] == 2) && (k0 & 15) == 0 &&
-                    (ncols & 7) == 0;
+    const bool v3 = __syncthreads_and((tid >= ncols) || clast[tid < ncols ? tid : 0] == 2) && (k0 & 31) == 0 &&
+                    (ncols & 15) == 0;
     if (U == nullptr) {
         // distance operands not wanted (the slab is updated incrementally from other columns)
     } else if (v3) {
-        const int ngroups = ncols >> 3;
-        for (int item = tid; item < ENC_ROWS * 8; item += 256) {      // uniform trip count (shuffles below)
-            const int rr = item >> 3, g = item & 7;
+        // 16 columns per item: 16 code bytes -> 16 bytes of U and of Wd (one byte per column)
+        const int ngroups = ncols >> 4;
+        for (int item = tid; item < ENC_ROWS * 4; item += 256) {      // uniform trip count (shuffles below)
+            const int rr = item >> 2, g = item & 3;
             int cnt = 0;
             if (rr < nrows && g < ngroups) {
-                const uint2 cw = *reinterpret_cast<const uint2 *>(&code_rc[rr][8 * g]);
+                const uint4 cw = *reinterpret_cast<const uint4 *>(&code_rc[rr][16 * g]);
                 uint4 u, w;
-                expand_v3(cw.x, u.x, u.y, w.x, w.y, cnt);
-                expand_v3(cw.y, u.z, u.w, w.z, w.w, cnt);
-                const int64_t o = (r0 + rr) * K + k0 + 16 * g;
+                expand_v3_fp4(cw.x, u.x, w.x, cnt);
+                expand_v3_fp4(cw.y, u.y, w.y, cnt);
+                expand_v3_fp4(cw.z, u.z, w.z, cnt);
+                expand_v3_fp4(cw.w, u.w, w.w, cnt);
+                const int64_t o = (r0 + rr) * K + (k0 >> 1) + 16 * g;      // K = row pitch in bytes
                 // U holds only the rows [u_lo, u_hi) (the target rows of this rank)
                 if (r0 + rr >= u_lo && r0 + rr < u_hi) *reinterpret_cast<uint4 *>(U + o - u_lo * K) = u;
                 *reinterpret_cast<uint4 *>(Wd + o) = w;
             }
             cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
             cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
-            cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
             if (g == 0 && rr < nrows && cnt) atomicAdd(&srow[r0 + rr], cnt);
         }
     } else {
-        // general path: 32-bit words where the whole word belongs to this tile, single bytes at
-        // the unaligned edges (a neighbouring tile owns the rest of that word)
-        const int w0 = k0 >> 2, w1 = (k1 + 3) >> 2;               // word range covering [k0, k1)
+        // general path: nibbles k0..k1 of the row; 32-bit words (8 nibbles) that belong to this tile
+        // entirely are stored, the words at the unaligned edges are OR-ed in (the operands were
+        // cleared by the host; a neighbouring tile owns the other nibbles of such a word)
+        const int w0 = k0 >> 3, w1 = (k1 + 7) >> 3;               // word range covering [k0, k1)
         for (int rr = tid >> 5; rr < ENC_ROWS; rr += 8) {          // uniform trip count
             int cnt = 0;
             if (rr < nrows) {
@@ -273,32 +288,26 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
                     uint32_t uw = 0, ww = 0;
                     bool full = true;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const int k = 4 * w + b;
+                    for (int b = 0; b < 8; ++b) {
+                        const int k = 8 * w + b;
                         if (k >= k0 && k < k1) {
                             const int col = kcol[k - k0];
                             const uint32_t code = code_rc[rr][col];
                             const uint32_t on = code == kval[k - k0] ? 1u : 0u;
-                            uw |= on << (8 * b);
-                            ww |= (on + (code != clast[col] ? 1u : 0u)) << (8 * b);
+                            uw |= (on << 1) << (4 * b);                                        // 1.0 = 0x2
+                            ww |= ((on + (code != clast[col] ? 1u : 0u)) << 1) << (4 * b);      // 0 / 1.0 / 2.0 = 0x0 / 0x2 / 0x4
                         } else {
                             full = false;
                         }
                     }
-                    const int64_t o = (r0 + rr) * K + 4 * (int64_t)w;
+                    const int64_t o = (r0 + rr) * K + 4 * (int64_t)w;         // K = row pitch in bytes
                     const bool in_u = r0 + rr >= u_lo && r0 + rr < u_hi;      // U holds only those rows
                     if (full) {
                         if (in_u) *reinterpret_cast<uint32_t *>(U + o - u_lo * K) = uw;
                         *reinterpret_cast<uint32_t *>(Wd + o) = ww;
                     } else {
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const int k = 4 * w + b;
-                            if (k >= k0 && k < k1) {
-                                if (in_u) U[o - u_lo * K + b] = (int8_t)((uw >> (8 * b)) & 0xffu);
-                                Wd[o + b] = (int8_t)((ww >> (8 * b)) & 0xffu);
-                            }
-                        }
+                        if (in_u && uw) atomicOr(reinterpret_cast<unsigned int *>(U + o - u_lo * K), uw);
+                        if (ww) atomicOr(reinterpret_cast<unsigned int *>(Wd + o), ww);
                     }
                 }
                 for (int c = lane; c < ncols; c += 32) cnt += code_rc[rr][c] != clast[c] ? 1 : 0;
@@ -441,43 +450,41 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
     __syncthreads();
     // ---- step 2: U, Wd (16 bytes per 8 codes) and the per-sample counts s
     if (U != nullptr) {
-        if ((ncols & 7) == 0) {
-            const int ngroups = ncols >> 3;
+        if ((ncols & 15) == 0) {
+            // 16 columns per item: 16 code bytes -> 16 bytes of U and of Wd (one byte per column)
+            const int ngroups = ncols >> 4;
 #pragma unroll
-            for (int it = 0; it < ENC_ROWS * 8 / 256; ++it) {
-                const int item = tid + 256 * it, rr = item >> 3, g = item & 7;
+            for (int it = 0; it < ENC_ROWS * 4 / 256; ++it) {
+                const int item = tid + 256 * it, rr = item >> 2, g = item & 3;
                 int cnt = 0;
                 if (rr < nrows && g < ngroups) {
-                    const uint2 cw = *reinterpret_cast<const uint2 *>(&code_rc[rr][8 * g]);
+                    const uint4 cw = *reinterpret_cast<const uint4 *>(&code_rc[rr][16 * g]);
                     uint4 u, w;
-                    expand_v3(cw.x, u.x, u.y, w.x, w.y, cnt);
-                    expand_v3(cw.y, u.z, u.w, w.z, w.w, cnt);
-                    const int64_t o = (r0 + rr) * K + k0 + 16 * g;
+                    expand_v3_fp4(cw.x, u.x, w.x, cnt);
+                    expand_v3_fp4(cw.y, u.y, w.y, cnt);
+                    expand_v3_fp4(cw.z, u.z, w.z, cnt);
+                    expand_v3_fp4(cw.w, u.w, w.w, cnt);
+                    const int64_t o = (r0 + rr) * K + c0 + 16 * g;       // K = row pitch in bytes; k0 / 2 = c0
                     // U holds only the rows [u_lo, u_hi) (the target rows of this rank)
                     if (r0 + rr >= u_lo && r0 + rr < u_hi) *reinterpret_cast<uint4 *>(U + o - u_lo * K) = u;
                     *reinterpret_cast<uint4 *>(Wd + o) = w;
                 }
                 cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
                 cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
-                cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
                 if (g == 0 && rr < nrows && cnt) atomicAdd(&srow[r0 + rr], cnt);
             }
         } else {
-            // ragged last column tile: one (sample, column) pair per step
+            // ragged last column tile: one (sample, column) byte per step
             for (int rr = tid >> 5; rr < ENC_ROWS; rr += 8) {
                 int cnt = 0;
                 if (rr < nrows)
                     for (int cc = tid & 31; cc < ncols; cc += 32) {
                         const uint32_t code = code_rc[rr][cc];
-                        const uint32_t nl = code != 2u ? 1u : 0u;
-                        const int64_t o = (r0 + rr) * K + k0 + 2 * cc;
-                        if (r0 + rr >= u_lo && r0 + rr < u_hi) {
-                            U[o - u_lo * K] = (int8_t)(code == 0u);
-                            U[o - u_lo * K + 1] = (int8_t)(code == 1u);
-                        }
-                        Wd[o] = (int8_t)((code == 0u) + nl);
-                        Wd[o + 1] = (int8_t)((code == 1u) + nl);
-                        cnt += (int)nl;
+                        const int64_t o = (r0 + rr) * K + c0 + cc;
+                        if (r0 + rr >= u_lo && r0 + rr < u_hi)
+                            U[o - u_lo * K] = (int8_t)(code == 0u ? 0x02u : code == 1u ? 0x20u : 0u);
+                        Wd[o] = (int8_t)(code == 0u ? 0x24u : code == 1u ? 0x42u : 0u);
+                        cnt += code != 2u ? 1 : 0;
                     }
 #pragma unroll
                 for (int o = 16; o >= 1; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -536,26 +543,32 @@ static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
     }
     ws.p_roff.ptr[pr] = (int32_t)K;
     ws.Kr_used = K;
-    ws.Kr = round_up(K, 128);
+    ws.Kr = round_up(K, 256);                 // elements (FP4 nibbles); rows are Kr / 2 bytes
     ws.rcol.reserve(pr);
     ws.roff.reserve(pr + 1);
-    ws.Ur.reserve((size_t)n * ws.Kr);
-    ws.Wdr.reserve((size_t)n * ws.Kr);
+    const size_t Kb = (size_t)ws.Kr / 2;
+    ws.Ur.reserve((size_t)n * Kb);
+    ws.Wdr.reserve((size_t)n * Kb);
     ws.srow_r.reserve(ws.ldt);
     cudaStream_t st = ds->stream;
     FS_CUDA(cudaMemcpyAsync(ws.rcol.ptr, ws.p_rcol.ptr, pr * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     FS_CUDA(cudaMemcpyAsync(ws.roff.ptr, ws.p_roff.ptr, (pr + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     FS_CUDA(cudaMemsetAsync(ws.srow_r.ptr, 0, ws.ldt * sizeof(int32_t), st));
-    if (ws.Kr > ws.Kr_used) {
-        FS_CUDA(cudaMemset2DAsync(ws.Ur.ptr + ws.Kr_used, (size_t)ws.Kr, 0, (size_t)(ws.Kr - ws.Kr_used), (size_t)n, st));
-        FS_CUDA(cudaMemset2DAsync(ws.Wdr.ptr + ws.Kr_used, (size_t)ws.Kr, 0, (size_t)(ws.Kr - ws.Kr_used), (size_t)n, st));
+    const int all_ident = (ident & kColIdent) ? 1 : 0;
+    const bool lean = all_ident && ws.Kr_used == 2 * pr;
+    if (!lean) {
+        // general encoder ORs partial words in: clear everything
+        FS_CUDA(cudaMemsetAsync(ws.Ur.ptr, 0, (size_t)n * Kb, st));
+        FS_CUDA(cudaMemsetAsync(ws.Wdr.ptr, 0, (size_t)n * Kb, st));
+    } else if (ws.Kr > ws.Kr_used) {
+        FS_CUDA(cudaMemset2DAsync(ws.Ur.ptr + ws.Kr_used / 2, Kb, 0, (size_t)(ws.Kr - ws.Kr_used) / 2, (size_t)n, st));
+        FS_CUDA(cudaMemset2DAsync(ws.Wdr.ptr + ws.Kr_used / 2, Kb, 0, (size_t)(ws.Kr - ws.Kr_used) / 2, (size_t)n, st));
     }
     const unsigned grid = (unsigned)(ceil_div(pr, ENC_COLS) * ceil_div(n, ENC_ROWS));
     const int as_f32 = (ds->arith == FS_ARITH_F32 && ds->dtype == FS_F64) ? 1 : 0;
-    const int all_ident = (ident & kColIdent) ? 1 : 0;
-    if (all_ident && ws.Kr_used == 2 * pr) {
+    if (lean) {
         onehot_encode_v3_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(ds->x), ds->ldx, ds->d_perm.ptr,
-                                                      ws.rcol.ptr, n, pr, ws.Kr, ws.ldt, 0, ws.Ur.ptr, ws.Wdr.ptr, nullptr,
+                                                      ws.rcol.ptr, n, pr, (int64_t)Kb, ws.ldt, 0, ws.Ur.ptr, ws.Wdr.ptr, nullptr,
                                                       nullptr, nullptr, ws.srow_r.ptr, nullptr, 0, n);
         FS_CUDA(cudaGetLastError());
         ++*launches;
@@ -563,7 +576,7 @@ static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
     }
 #define FS_ENCODE_R(T)                                                                                            \
     onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,        \
-                                                  ws.rcol.ptr, ws.roff.ptr, ds->d_vals.ptr, as_f32, n, pr, ws.Kr, \
+                                                  ws.rcol.ptr, ws.roff.ptr, ds->d_vals.ptr, as_f32, n, pr, (int64_t)Kb, \
                                                   ws.ldt, 0, ws.Ur.ptr, ws.Wdr.ptr, nullptr, nullptr, nullptr,    \
                                                   ws.srow_r.ptr, nullptr, all_ident, 0, n)
     switch (ds->dtype) {
@@ -580,7 +593,7 @@ static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
 void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     const int64_t n = ds->n, pt = ws.pt;
     // tcol / tout / toff, K_used and all_ident were filled by build_workset (pinned staging)
-    ws.K = round_up(ws.K_used, 128);
+    ws.K = round_up(ws.K_used, 256);          // elements (FP4 nibbles); U / Wd rows are K / 2 bytes
     ws.ldt = round_up(n, 128);
     ws.ldc = round_up(pt, 16);
     FS_REQUIRE(pt < (1LL << 24), FS_ERR_INVALID, "too many one-hot columns (%lld)", (long long)pt);
@@ -589,8 +602,8 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     ws.toff.reserve(pt + 1);
     const bool ops = ws.have_dist_ops;
     if (ops) {
-        ws.U.reserve((size_t)(ws.u_hi - ws.u_lo) * ws.K);   // target rows of this call only
-        ws.Wd.reserve((size_t)n * ws.K);
+        ws.U.reserve((size_t)(ws.u_hi - ws.u_lo) * (ws.K / 2));   // target rows of this call only
+        ws.Wd.reserve((size_t)n * (ws.K / 2));
         ws.srow.reserve(ws.ldt);   // padded: the distance epilogue reads it in 16-byte vectors
     }
     ws.At.reserve((size_t)ws.K * (ws.ldt / 2));          // FP4 nibbles: two samples per byte
@@ -605,21 +618,25 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     // padding (reduced rows K_used..K) has to be cleared.  Sample padding of the feature-major
     // rows (columns n..ldt) is never read (the TMA maps are n bytes wide).
     if (ops) FS_CUDA(cudaMemsetAsync(ws.srow.ptr, 0, ws.ldt * sizeof(int32_t), st));
-    if (ws.K > ws.K_used) {
-        if (ops) {
-            FS_CUDA(cudaMemset2DAsync(ws.U.ptr + ws.K_used, (size_t)ws.K, 0, (size_t)(ws.K - ws.K_used),
-                                      (size_t)(ws.u_hi - ws.u_lo), st));
-            FS_CUDA(cudaMemset2DAsync(ws.Wd.ptr + ws.K_used, (size_t)ws.K, 0, (size_t)(ws.K - ws.K_used), (size_t)n, st));
-        }
-        FS_CUDA(cudaMemsetAsync(ws.At.ptr + (size_t)ws.K_used * (ws.ldt / 2), 0, (size_t)(ws.K - ws.K_used) * (ws.ldt / 2), st));
+    const size_t Kb = (size_t)ws.K / 2;
+    const bool lean = ws.all_ident && ws.K_used == 2 * pt;
+    if (ops && !lean) {
+        // the general encoder ORs the words at unaligned tile edges in: clear the operands first
+        FS_CUDA(cudaMemsetAsync(ws.U.ptr, 0, (size_t)(ws.u_hi - ws.u_lo) * Kb, st));
+        FS_CUDA(cudaMemsetAsync(ws.Wd.ptr, 0, (size_t)n * Kb, st));
+    } else if (ops && ws.K > ws.K_used) {
+        FS_CUDA(cudaMemset2DAsync(ws.U.ptr + ws.K_used / 2, Kb, 0, (size_t)(ws.K - ws.K_used) / 2, (size_t)(ws.u_hi - ws.u_lo), st));
+        FS_CUDA(cudaMemset2DAsync(ws.Wd.ptr + ws.K_used / 2, Kb, 0, (size_t)(ws.K - ws.K_used) / 2, (size_t)n, st));
     }
+    if (ws.K > ws.K_used)
+        FS_CUDA(cudaMemsetAsync(ws.At.ptr + (size_t)ws.K_used * (ws.ldt / 2), 0, (size_t)(ws.K - ws.K_used) * (ws.ldt / 2), st));
     const unsigned grid = (unsigned)(ceil_div(pt, ENC_COLS) * ceil_div(n, ENC_ROWS));
     const int as_f32 = (ds->arith == FS_ARITH_F32 && ds->dtype == FS_F64) ? 1 : 0;
     const int all_ident = ws.all_ident ? 1 : 0;
-    if (ws.all_ident && ws.K_used == 2 * pt) {
+    if (lean) {
         // every active column holds exactly the byte values 0/1/2: lean kernel
         onehot_encode_v3_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(ds->x), ds->ldx, ds->d_perm.ptr,
-                                                      ws.tcol.ptr, n, pt, ws.K, ws.ldt, ws.ldc, ops ? ws.U.ptr : nullptr,
+                                                      ws.tcol.ptr, n, pt, (int64_t)Kb, ws.ldt, ws.ldc, ops ? ws.U.ptr : nullptr,
                                                       ops ? ws.Wd.ptr : nullptr, ws.At.ptr, ws.codesT.ptr,
                                                       ws.have_codes ? ws.codes.ptr : nullptr,
                                                       ops ? ws.srow.ptr : nullptr, ws.krow.ptr, ws.u_lo, ws.u_hi);
@@ -630,7 +647,7 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     }
 #define FS_ENCODE(T)                                                                                             \
     onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,       \
-                                                  ws.tcol.ptr, ws.toff.ptr, ds->d_vals.ptr, as_f32, n, pt, ws.K, \
+                                                  ws.tcol.ptr, ws.toff.ptr, ds->d_vals.ptr, as_f32, n, pt, (int64_t)Kb, \
                                                   ws.ldt, ws.ldc, ops ? ws.U.ptr : nullptr,                      \
                                                   ops ? ws.Wd.ptr : nullptr, ws.At.ptr, ws.codesT.ptr,           \
                                                   ws.have_codes ? ws.codes.ptr : nullptr,                        \
@@ -659,7 +676,9 @@ void launch_dist_tensor(fs_dataset *ds, const WorkSet &ws, int64_t r0_internal, 
     const bool incr = ws.dist_mode == kDistIncremental;
     const int8_t *Uop = incr ? ws.Ur.ptr : ws.U.ptr, *Wop = incr ? ws.Wdr.ptr : ws.Wd.ptr;
     const int32_t *sop = incr ? ws.srow_r.ptr : ws.srow.ptr;
-    const int64_t K = incr ? ws.Kr : ws.K;
+    const int64_t K = (incr ? ws.Kr : ws.K) / 2;        // operand row bytes (FP4 nibbles)
+    // every column adds at most 2 to an FP32 accumulator: exact while the sums stay below 2^24
+    FS_REQUIRE(2 * ws.pt < (1LL << 24), FS_ERR_INVALID, "too many one-hot columns for exact FP32 accumulation (%lld)", (long long)ws.pt);
     const int8_t *a_rows;
     const int64_t u_lo = incr ? 0 : ws.u_lo;           // first sample row held by the target-side operand
     if (contiguous) {

@@ -5,12 +5,14 @@
 //     d_ij = sum_f [x_if != x_jf] = s_i + s_j - sum_k U[i,k] * Wd[j,k],
 // where U / Wd are the reduced one-hot images of the discrete columns (onehot.cu: V_f - 1
 // int8 columns per feature, K = sum_f (V_f - 1)) and s_i counts the columns in which sample
-// i does not carry its column's last value.  The contraction is an int8 GEMM U * Wd^T with
-// int32 accumulation, so the distances are exact integers.
+// i does not carry its column's last value.  The contraction is a GEMM U * Wd^T over operands
+// stored as e2m1 (FP4) nibbles -- entries 0/1 and 0/1/2 -- with unit UE8M0 block scales and FP32
+// accumulation (tcgen05 kind::mxf4, twice the int8 rate): every product and every partial sum is a
+// small integer, so the FP32 accumulators are exact up to 2^24 and the distances are exact.
 //
 // Kernel: one CTA per 128 x 256 tile of D.  Warp 0 streams 128-byte-wide K slabs of
 // both operands with TMA (128B swizzle) through a 4-stage mbarrier ring; one elected
-// thread of warp 1 issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=256, K=32) into
+// thread of warp 1 issues tcgen05.mma.cta_group::1.kind::mxf4 (M=128, N=256, K=64) into
 // a 256-column TMEM accumulator; warps 2-5 read the accumulator back with
 // tcgen05.ld (32 lanes x 32 columns per instruction), form s_i + s_j - acc and store
 // int32 rows (each thread writes whole 128-byte lines).
@@ -25,7 +27,7 @@
 // for another rank it is a peer store over NVLink into that rank's slab, mapped through CUDA
 // IPC).  The exchange is fused into the GEMM epilogue; a cross-rank barrier before the
 // neighbour selection is all that follows.
-// Tensor-pipe bound: 4 int-ops per (sample pair, feature) for 3-valued genotypes, half of
+// Tensor-pipe bound: 4 ops per (sample pair, feature) for 3-valued genotypes, half of
 // that in symmetric mode.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -41,6 +43,8 @@ constexpr int A_BYTES = BM * BK;   // 16 KB
 constexpr int B_BYTES = BN * BK;   // 32 KB
 constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 512;  // 256 accumulator columns + 8 scale-factor columns, rounded up to a power of two
+constexpr int SF_COL = BN;      // 8 columns of UE8M0 1.0 (0x7f): block scales of both operands
 constexpr int BAND = 16;        // row blocks per rasterisation band
 }  // namespace
 
@@ -111,11 +115,19 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc::mbar_init(accum_bar, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc<BN>(tmem_slot);
+    if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp >= 2) {
+        // block scale factors: 1.0 everywhere (warps 2..5 cover the four TMEM lane quarters)
+        for (int c = 0; c < 8; ++c) tc::tmem_st_32x1(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + SF_COL + c, 0x7f7f7f7fu);
+        tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -132,7 +144,7 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            constexpr uint32_t idesc = tc::make_idesc_i8(BM, BN);
+            constexpr uint32_t idesc = tc::make_idesc_mxf4(BM, BN);
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
@@ -142,7 +154,8 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const uint64_t db = tc::make_smem_desc_sw128(tc::smem_u32(smem_b + s * B_BYTES));
 #pragma unroll
                 for (int k = 0; k < BK / 32; ++k)   // +32 bytes of K = +2 in the (addr >> 4) field
-                    tc::mma_i8(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    tc::mma_mxf4(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, tmem_base + SF_COL,
+                                 tmem_base + SF_COL, (kb | k) != 0);
                 tc::tc_commit(&empty_bar[s]);       // frees the smem stage when these MMAs retire
             }
             tc::tc_commit(accum_bar);               // accumulator complete
@@ -166,10 +179,10 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
                 const int4 sj = *reinterpret_cast<const int4 *>(srow + col + e);
-                v[e] = (uint32_t)(s_i + sj.x - (int32_t)v[e]);
-                v[e + 1] = (uint32_t)(s_i + sj.y - (int32_t)v[e + 1]);
-                v[e + 2] = (uint32_t)(s_i + sj.z - (int32_t)v[e + 2]);
-                v[e + 3] = (uint32_t)(s_i + sj.w - (int32_t)v[e + 3]);
+                v[e] = (uint32_t)(s_i + sj.x - __float2int_rn(__uint_as_float(v[e])));
+                v[e + 1] = (uint32_t)(s_i + sj.y - __float2int_rn(__uint_as_float(v[e + 1])));
+                v[e + 2] = (uint32_t)(s_i + sj.z - __float2int_rn(__uint_as_float(v[e + 2])));
+                v[e + 3] = (uint32_t)(s_i + sj.w - __float2int_rn(__uint_as_float(v[e + 3])));
             }
             // subtract mode (incremental update): the operands are those of removed columns and
             // their mismatch count is taken off the resident slab.  All loads of a chunk are issued
@@ -217,7 +230,7 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         tc::tc_fence_after();
-        tc::tmem_dealloc<BN>(tmem_base);
+        tc::tmem_dealloc<TMEM_COLS>(tmem_base);
     }
 }
 
@@ -242,7 +255,7 @@ void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_
                 const int sb_i = peers.sb_base[peers.rank] + (by >> 1);
                 tiles += (!symmetric || dist_row_side(sb_i, bx, peers.coarse_shift)) ? 1 : 0;
             }
-        *ops += 2.0 * BM * BN * (double)K * (double)tiles;
+        *ops += 2.0 * BM * BN * (2.0 * (double)K) * (double)tiles;      // K is the operand row length in bytes
     }
 }
 
