@@ -384,25 +384,30 @@ def own_arm(args):
     peak_src = ("2 x measured %s bf16 (MEASURED_PEAKS.json)" % ("burst" if at_max else "sustained")) if peaks \
         else "2 x fallback bf16 (%s)" % ("1.59 PF burst" if at_max else "1.4 PF sustained")
     hbm = peaks.get("hbm_gbs", 6650.0)
-    int8_peak = 2.0 * bf16
+    # both one-hot GEMMs run on tcgen05 kind::mxf4 (e2m1 operands, FP32 accumulation): dense FP4 is
+    # nominally 4 x bf16 on B200; MEASURED_PEAKS.json has no FP4 entry, so the denominator is
+    # 4 x the measured cuBLAS bf16 figure
+    fp4_peak = 4.0 * bf16
+    peak_src = peak_src.replace("2 x", "4 x")
     traffic = load_traffic(args.workload if world == 1 else None)
     kernels = {}
     for ph, key in (("ms_dist_tensor", "ops_dist_tensor"), ("ms_accum_tensor", "ops_accum_tensor")):
         if phases[ph] > 0:
-            # int8 operations actually issued to the tensor pipe (fs_stats), not the 6/u of SURVEY 8d:
+            # operations actually issued to the tensor pipe (fs_stats), not the 6/u of SURVEY 8d:
             # the reduced one-hot operands need 2 MAC per (pair, 3-valued feature) and symmetric tiles half of that
             ex = agg.get(key, 0.0) / steps / (phases[ph] / 1e3) / 1e12
-            kernels[ph] = {"bound": "tensor", "achieved": ex, "peak": int8_peak, "unit": "TOP/s int8",
-                           "frac": ex / int8_peak, "survey_algorithmic_rate": 6.0 * u_rank / (phases[ph] / 1e3) / 1e12,
+            kernels[ph] = {"bound": "tensor", "achieved": ex, "peak": fp4_peak, "unit": "TOP/s fp4 (e2m1, exact integers)",
+                           "frac": ex / fp4_peak, "survey_algorithmic_rate": 6.0 * u_rank / (phases[ph] / 1e3) / 1e12,
                            "traffic": traffic.get(ph)}
     if phases["ms_gather"] > 0 and agg.get("onehot_k", 0) > 0:
         kk = agg["onehot_k"] / steps
         pt = agg["n_tensor_cols"] / steps
-        # encode: raw columns read once; U, Wd, At (3 x n x K) and codesT (n x pt) written once
-        byts = n * pt * w["x"].itemsize + 3.0 * n * kk + n * pt
+        # encode: raw columns read once; U (this rank's rows), Wd, At as FP4 nibbles (K / 2 bytes per
+        # sample each) and codesT (n x pt) written once
+        byts = n * pt * w["x"].itemsize + (rows + 2.0 * n) * kk / 2.0 + n * pt
         gbs = byts / (phases["ms_gather"] / 1e3) / 1e9
         kernels["ms_gather"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                                "traffic": traffic.get("ms_gather")}
+                                "traffic": traffic.get("ms_gather"), "note": "time includes the host-side working-set preparation (ms_host_prep)"}
     if top.endswith("tensor"):
         roof = dict(kernels[top], kernel=top, peak_source=peak_src)
     else:
@@ -419,7 +424,7 @@ def own_arm(args):
     cpu = cpu_baseline(w) if world == 1 else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
-            "vs_baseline": None, "dtype": "u8 one-hot / int32 accum (genotype), f32 terms + f64 accum (continuous)",
+            "vs_baseline": None, "dtype": "e2m1 (FP4) one-hot / exact FP32 accum (genotype), f32 terms + f64 accum (continuous)",
             "data": "synthetic",
             "config": {"workload": w["desc"], "n": n, "p": p, "algo": w["algo"] + ("*" if w["star"] else ""),
                        "rows_per_gpu": rows, "sharding": f"target rows x{world}, one NCCL allreduce" + (", symmetric distances via NVLink peer stores" if sess_peers else ""),
@@ -539,18 +544,18 @@ def turf_arm(args):
                                                       "ms_reduce", "ms_total", "ms_host_prep")}
     at_max = False                       # second-scale steps: sustained peak
     bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
-    int8_peak = 2.0 * bf16
+    fp4_peak = 4.0 * bf16                # kind::mxf4: nominally 4 x bf16; no measured FP4 figure in MEASURED_PEAKS.json
     kernels = {}
     for ph, key in (("ms_dist_tensor", "ops_dist_tensor"), ("ms_accum_tensor", "ops_accum_tensor")):
         ex = agg.get(key, 0.0) / steps / (phases[ph] / 1e3) / 1e12
-        kernels[ph] = {"bound": "tensor", "achieved": ex, "peak": int8_peak, "unit": "TOP/s int8", "frac": ex / int8_peak,
+        kernels[ph] = {"bound": "tensor", "achieved": ex, "peak": fp4_peak, "unit": "TOP/s fp4 (e2m1, exact integers)", "frac": ex / fp4_peak,
                        "traffic": None}
     top = max(kernels, key=lambda q: phases[q])
     roof = dict(kernels[top], kernel=top,
-                peak_source="2 x measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "2 x fallback 1.4 PF")
+                peak_source="4 x measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "4 x fallback 1.4 PF")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u8 one-hot / int32 accum (genotype)", "data": "synthetic",
+            "dtype": "e2m1 (FP4) one-hot / exact FP32 accum (genotype)", "data": "synthetic",
             "config": {"workload": w["desc"], "n": n, "p": p, "algo": "TuRF(MultiSURF)", "scoring_passes": len(sizes),
                        "sum_p_t": int(sum(sizes)), "sharding": f"target rows x{world}, one NCCL allreduce per pass",
                        "l2": "inputs larger than L2 (no flush needed)",
