@@ -2,14 +2,15 @@
 // tensor maps, and the host side of the tcgen05 distance / accumulation kernels.
 //
 // K0 "encode" of the design: every active discrete column f with 2 <= V_f <= FS_DISTINCT_CAP
-// distinct values becomes V_f - 1 reduced one-hot int8 rows/columns (only equality matters,
-// MultiSURF.py:184-185, so any injective value coding is exact):
-//   U, Wd [n, K]   sample-major (one-hot index contiguous)  -> the two operands of the distance GEMM
-//   At    [K, ldt] feature-major (sample index contiguous)   -> M operand of the accumulation GEMM
+// distinct values becomes V_f - 1 reduced one-hot rows/columns (only equality matters,
+// MultiSURF.py:184-185, so any injective value coding is exact), stored as e2m1 (FP4) nibbles --
+// two entries per byte -- for the tcgen05 kind::mxf4 GEMMs:
+//   U, Wd [n, K/2 bytes]   sample-major (one-hot index contiguous)  -> the two operands of the distance GEMM
+//   At    [K, ldt/2 bytes] feature-major (sample index contiguous)   -> M operand of the accumulation GEMM
 //   codesT [pt, ldt] feature-major value codes               -> accumulation epilogue
 //   codes  [n, ldc]  sample-major value codes                -> ReliefF's sparse neighbour gather (only then)
 // Samples are in the data set's class-sorted internal order.  HBM-bound streaming kernel:
-// reads n*pt elements once, writes 3*n*K + n*pt bytes.
+// reads n*pt elements once, writes 1.5*n*K + n*pt bytes.
 #include <algorithm>
 
 #include <cuda.h>
@@ -82,26 +83,13 @@ CUtensorMap make_tmap_u8_sw128(const void *base, uint64_t row_bytes, uint64_t ro
 // Tile: 128 samples x 64 columns per CTA.  Step 1 reads x and keeps the value codes in
 // shared memory in both orientations; step 2 emits the U / Wd rows (one-hot index
 // contiguous) and the per-sample counts s; step 3 the At and codesT rows (sample index
-// contiguous).  All global stores are 16-byte vectors on the 0/1/2 fast path, and every
-// byte of the tile's footprint is written exactly once (no memset of the operands).
+// contiguous).  On the 0/1/2 fast path all global stores are 8- or 16-byte vectors and every
+// byte of the tile's footprint is written exactly once (no memset of the operands); the general
+// path ORs the words at unaligned tile edges into operands the host cleared.
 constexpr int ENC_ROWS = 128;
 constexpr int ENC_COLS = 64;
 constexpr int ENC_CR_LD = ENC_ROWS + 4;                       // conflict-free transposed stores
 constexpr int ENC_KMAX = ENC_COLS * (FS_DISTINCT_CAP - 1);
-
-// 4 genotype codes (one per byte, each 0/1/2) -> 8 bytes of U, 8 bytes of Wd, count of codes != 2.
-// Byte-parallel: e_v = [code == v] per byte from the two low bits of each code.
-__device__ __forceinline__ void expand_v3(uint32_t cw, uint32_t &u0, uint32_t &u1, uint32_t &w0, uint32_t &w1, int &cnt) {
-    const uint32_t e1 = cw & 0x01010101u, e2 = (cw >> 1) & 0x01010101u;
-    const uint32_t ne = e2 ^ 0x01010101u;             // [code != last]
-    const uint32_t e0 = ne ^ e1;                      // [code == 0]
-    cnt += __popc(ne);
-    u0 = __byte_perm(e0, e1, 0x5140);                 // (e0.b0, e1.b0, e0.b1, e1.b1)
-    u1 = __byte_perm(e0, e1, 0x7362);
-    const uint32_t a0 = e0 + ne, a1 = e1 + ne;        // no carries: every byte <= 2
-    w0 = __byte_perm(a0, a1, 0x5140);
-    w1 = __byte_perm(a0, a1, 0x7362);
-}
 
 // FP4 (e2m1 nibble) images of 4 genotype codes: one byte per column -- low nibble = row v = 0,
 // high nibble = row v = 1.  U: [c = v] -> 1.0 = 0x2.  Wd: [c = v] + [c != last] in {0, 1, 2} ->

@@ -1,6 +1,6 @@
 // tc_accum.cu -- per-feature hit/miss weight accumulation for discrete columns as a
-// (neighbour mask) x (one-hot) int8 GEMM on the 5th-gen tensor cores, with a fused
-// select / scale / reduce epilogue.
+// (neighbour mask) x (one-hot) GEMM on the 5th-gen tensor cores (FP4 operands, exact integer
+// results), with a fused select / scale / reduce epilogue.
 //
 // Replaces the discrete branch of the reference's accumulation loops and their
 // normalisation (MultiSURF.py:218-251, SURF.py:165-195).  For a discrete feature f with
@@ -14,28 +14,33 @@
 //     W_i[f] = sum_{v<last} [c_if = v] * k_i (rs_i - G[(f,v), i])  +  [c_if = last] * k_i * sum_{v<last} G[(f,v), i]
 // for each of the two masks (k_i = -aH_i or +aM_i).  The thread that owns one-hot row (f,v)
 // therefore adds k_i (rs_i - G) for targets whose code is v and k_i G for targets whose
-// code is the last one: no exchange between rows.  All counts are exact integers; the
-// per-target scaling and the reduction over targets are done in float64.
+// code is the last one: no exchange between rows.
+//
+// Arithmetic.  At holds 0/1 and the masks -1/0/1, both exact in e2m1, so the GEMM runs on
+// tcgen05 kind::mxf4 (unit UE8M0 block scales, FP32 accumulators): the sums are integers below
+// 2^22 and therefore exact in FP32 (probed on B200, tools/mxf4_probe.cu) at twice the int8 MMA
+// rate.  The per-target scaling k_i * t is accumulated exactly as well: k_i is a 52-bit
+// fixed-point number in two 26-bit limbs, t an integer, the sums two int64 -- no float64
+// instruction in the inner loop (FP64 and the tensor pipe did not overlap on B200).
 //
 // Kernel: persistent, one CTA per SM.  A work unit is 128 one-hot rows (UMMA M = TMEM
-// lanes) x a group of up to 8 tiles of <= 256 target rows (UMMA N); units are dealt
+// lanes) x a group of tiles of <= 240 target rows (UMMA N); units are dealt
 // round-robin and the TMA / MMA / epilogue pipelines run across unit boundaries without
 // draining.  Tiles never straddle a class boundary (host-built descriptors, staged in
 // shared memory).  Each tile is processed as two work items, "hit" and "miss", one mask
-// and one 256-column TMEM accumulator each (double-buffered, so the epilogue of one item
-// overlaps the MMAs of the next).  Warp 0: TMA producer (At tile +
-// mask tile per K block of 128 samples, 128B swizzle, 4-stage mbarrier ring); warp 1:
-// one thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=256, K=32); warps 2-17
-// (lane quarter x column quarter): epilogue -- tcgen05.ld the accumulator, test the target's
-// own value code (codesT), scale, and add into float64 registers per one-hot row;
-// the reduction over a tile's targets is a loop over TMEM columns inside one thread.
-// The epilogue is the critical path next to the MMAs: int32 -> float64 goes through an
-// exact bit trick (2^52 + 2^31 + x, one DADD) instead of I2F.F64, which saturated the XU pipe.
+// and one 240-column TMEM accumulator each (double-buffered, so the epilogue of one item
+// overlaps the MMAs of the next; 8 more TMEM columns hold the scale factors).  Warp 0: TMA
+// producer (At tile + mask tile per K block of 256 samples = 128 bytes, 128B swizzle, 4-stage
+// mbarrier ring); warp 1: one thread issues tcgen05.mma.cta_group::1.kind::mxf4 (M=128,
+// N<=240, K=64); warps 2-13 (lane quarter x column third): epilogue -- tcgen05.ld the
+// accumulator, test the target's own value code (codesT), scale, and add into the fixed-point
+// sums of its one-hot row; the reduction over a tile's targets is a loop over TMEM columns
+// inside one thread.
 // Samples are class-sorted, so for a class-homogeneous target tile the hit mask is
 // non-zero only in the K blocks of the tile's own class and the miss mask only outside:
 // the other K blocks are skipped, which keeps the MMA work at 2 MAC per (pair, feature)
-// for 3-valued genotypes.  Partials are written per (tile group, one-hot row) and reduced
-// in a fixed order.
+// for 3-valued genotypes.  Partials are written per (tile group, column part, one-hot row) and
+// reduced in a fixed order.
 #include <algorithm>
 
 #include "common.cuh"
@@ -80,8 +85,9 @@ static_assert(STAGE_BYTES % 1024 == 0 && HALF % 16 == 0 && SF_COL + 8 <= TMEM_CO
 // signed high limb and a 26-bit low limb, so that c * t for an integer t is accumulated EXACTLY
 // in two int64 sums (sum t*Chi, sum t*Clo) with integer multiply-adds.  No float64 instruction
 // is left in the epilogue's inner loop: on B200 DADD/DFMA and the tensor pipe could not be kept
-// busy at the same time (ncu: math-pipe throttle on every FP64 instruction while the MMA issuer
-// waited for the epilogue; FP64 time and MMA time added up instead of overlapping).
+// busy at the same time (ncu on the earlier float64 epilogue: math-pipe throttle on every FP64
+// instruction while the MMA issuer waited for the epilogue; FP64 time and MMA time added up
+// instead of overlapping).
 constexpr int kCoefBits = 52, kLimbBits = 26;
 __device__ __forceinline__ int2 coef_limbs(double c) {
     const long long C = __double2ll_rn(c * 4503599627370496.0);       // 2^52

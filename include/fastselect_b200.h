@@ -62,7 +62,7 @@ enum { FS_MASK_NONE = 0, FS_MASK_NEAR_HIT = 1, FS_MASK_NEAR_MISS = 2, FS_MASK_FA
 typedef struct fs_stats {
     float ms_total;          /* whole fs_score call on the device */
     float ms_gather;         /* column compaction / one-hot encode of the active columns */
-    float ms_dist_tensor;    /* one-hot int8 tcgen05 distance kernel(s) */
+    float ms_dist_tensor;    /* one-hot tcgen05 (FP4 kind::mxf4, exact) distance kernel(s) */
     float ms_dist_general;   /* CUDA-core distance kernel(s) (continuous / wide discrete) */
     float ms_select;         /* row statistics, thresholds / top-k, neighbour masks */
     float ms_accum_tensor;   /* mask x one-hot tcgen05 accumulation kernel(s) */
@@ -74,7 +74,7 @@ typedef struct fs_stats {
     int64_t n_general_cols;  /* active columns on the CUDA-core path */
     int64_t onehot_k;        /* contraction length of the one-hot operands (sum of V_f - 1, padded) */
     int64_t pairs_selected;  /* neighbour pairs with a non-zero coefficient */
-    double ops_dist_tensor;  /* int8 operations (2 per MAC) issued to the tensor pipe by the distance kernel(s) */
+    double ops_dist_tensor;  /* operations (2 per MAC) issued to the tensor pipe by the distance kernel(s) */
     double ops_accum_tensor; /* same, accumulation kernel(s) */
     double ms_host_prep;     /* host wall time spent preparing the working set (inside ms_gather) */
 } fs_stats;

@@ -10,16 +10,7 @@
 
 using namespace fs::tc;
 
-__device__ __forceinline__ void mma_mxf4(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t sfa, uint32_t sfb, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(d),
-        "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
-}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) { tmem_st_32x1(taddr, v); }
 
 constexpr int BM = 128, BN = 256;
 // mode 0: mxf4, mode 1: i8
