@@ -268,7 +268,7 @@ struct fs_dataset {
     fs::DevBuf<int32_t> tile_desc; // target-tile descriptors of the accumulation kernel
     fs::DevBuf<int8_t> maskH, maskM;
     fs::DevBuf<int8_t> a_gather;  // gathered one-hot target rows (fs_debug_rows)
-    fs::DevBuf<int32_t> tie_flag, tie_order;   // ReliefF reference tie order (select.cu)
+    fs::DevBuf<int32_t> tie_flag, tie_order, tie_list;   // ReliefF reference tie order (select.cu)
     fs::DevBuf<float> tie_keys;
     fs::DevBuf<unsigned long long> counters;
 };

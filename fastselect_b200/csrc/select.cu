@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) relieff_select_kernel(
     const int64_t *__restrict__ row_ids, const int32_t *__restrict__ y, const int64_t *__restrict__ cls_start,
     int n_classes, int k, const float *__restrict__ class_probs, int8_t *__restrict__ sel,
     RowInfo *__restrict__ rinfo, int32_t *__restrict__ nbr_idx, double *__restrict__ nbr_w,
-    int32_t *__restrict__ nbr_cnt, int nbr_cap, int32_t *__restrict__ tie_flag) {
+    int32_t *__restrict__ nbr_cnt, int nbr_cap, int32_t *__restrict__ tie_flag, int32_t *__restrict__ tie_list) {
     __shared__ int hist[256];
     __shared__ int warp_tot[8];
     __shared__ unsigned s_prefix;
@@ -255,7 +255,11 @@ __global__ void __launch_bounds__(256) relieff_select_kernel(
                 const unsigned prefix = s_prefix;
                 for (int64_t j = s0 + tid; j < s1; j += 256) {
                     const unsigned key = key_of(j);
-                    if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+                    // warp-aggregated histogram update: distances of one row share their leading
+                    // bytes, so most lanes hit the same bin (one shared atomic per distinct bin)
+                    const unsigned bin = (key & mask) == prefix ? (key >> shift) & 255u : 0xffffffffu;
+                    const unsigned peers = __match_any_sync(__activemask(), bin);
+                    if (bin != 0xffffffffu && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
                 }
                 __syncthreads();
                 if (tid == 0) {
@@ -304,7 +308,11 @@ __global__ void __launch_bounds__(256) relieff_select_kernel(
         slot_base = slot;
     }
     if (tid == 0) {
-        if (tie_flag) tie_flag[r] = ambiguous ? 1 : 0;
+        if (tie_flag) {
+            tie_flag[r] = ambiguous ? 1 : 0;
+            // compacted list of the rows that need the reference's tie order: [0] = count
+            if (ambiguous) tie_list[1 + atomicAdd(&tie_list[0], 1)] = (int32_t)r;
+        }
         nbr_cnt[r] = slot_base < nbr_cap ? slot_base : nbr_cap;
         RowInfo ri;
         ri.thresh = 0.0;
@@ -378,6 +386,104 @@ __device__ void numba_argsort_f32(const float *A, int32_t *R, int64_t n) {
     }
 }
 
+// The same quicksort on (key, index) pairs held in shared memory: the reference permutes an
+// index array R and compares A[R[i]]; moving the pairs themselves performs exactly the same
+// swaps.  Keys are non-negative float32 distances (and +inf), whose order is that of their bit
+// patterns; only the key half is compared, so equal distances stay ties.
+__device__ __forceinline__ uint32_t pkey(const uint2 *P, int64_t i) { return P[i].x; }
+__device__ __forceinline__ void pswap(uint2 *P, int64_t a, int64_t b) {
+    const uint2 t = P[a]; P[a] = P[b]; P[b] = t;
+}
+__device__ void numba_argsort_pairs(uint2 *P, int64_t n) {
+    if (n < 2) return;
+    int32_t stack_lo[100], stack_hi[100];
+    int sp = 1;
+    stack_lo[0] = 0; stack_hi[0] = (int32_t)(n - 1);
+    while (sp > 0) {
+        --sp;
+        int64_t low = stack_lo[sp], high = stack_hi[sp];
+        while (high - low >= 15) {
+            const int64_t mid = (low + high) >> 1;
+            if (pkey(P, mid) < pkey(P, low)) pswap(P, low, mid);
+            if (pkey(P, high) < pkey(P, mid)) pswap(P, high, mid);
+            if (pkey(P, mid) < pkey(P, low)) pswap(P, low, mid);
+            const uint32_t pivot = pkey(P, mid);
+            pswap(P, high, mid);
+            int64_t i = low, j = high - 1;
+            for (;;) {
+                while (i < high && pkey(P, i) < pivot) ++i;
+                while (j >= low && pivot < pkey(P, j)) --j;
+                if (i >= j) break;
+                pswap(P, i, j);
+                ++i; --j;
+            }
+            pswap(P, i, high);
+            if (high - i > i - low) {
+                if (high > i) { stack_lo[sp] = (int32_t)(i + 1); stack_hi[sp] = (int32_t)high; ++sp; }
+                high = i - 1;
+            } else {
+                if (i > low) { stack_lo[sp] = (int32_t)low; stack_hi[sp] = (int32_t)(i - 1); ++sp; }
+                low = i + 1;
+            }
+        }
+        for (int64_t i = low + 1; i <= high; ++i) {
+            const uint2 kv = P[i];
+            int64_t j = i;
+            while (j > low && kv.x < P[j - 1].x) { P[j] = P[j - 1]; --j; }
+            P[j] = kv;
+        }
+    }
+}
+
+// One CTA per ambiguous row (compacted list): the row's float32 distances are staged in shared
+// memory by all threads, one thread replays the quicksort there (shared-memory latency instead of
+// a dependent global access per comparison) and re-selects exactly as ReliefF.py:164-175.
+__global__ void __launch_bounds__(256) relieff_ties_smem_kernel(
+    const double *__restrict__ Dc, const int32_t *__restrict__ Dd, int64_t ldn, int64_t n,
+    const int64_t *__restrict__ row_ids, const int32_t *__restrict__ y, const int64_t *__restrict__ inv_perm,
+    int n_classes, int k, const float *__restrict__ class_probs, const int32_t *__restrict__ tie_list,
+    int8_t *__restrict__ sel, int32_t *__restrict__ nbr_idx, double *__restrict__ nbr_w,
+    int32_t *__restrict__ nbr_cnt, int nbr_cap) {
+    extern __shared__ __align__(16) unsigned char ties_smem[];
+    uint2 *P = reinterpret_cast<uint2 *>(ties_smem);
+    if ((int)blockIdx.x >= tie_list[0]) return;
+    const int64_t r = tie_list[1 + blockIdx.x];
+    const int64_t self = row_ids[r];
+    const int64_t base = r * ldn;
+    for (int64_t o = threadIdx.x; o < n; o += blockDim.x) {
+        const int64_t j = inv_perm[o];
+        const float d = j == self ? __int_as_float(0x7f800000) : (float)load_d(Dc, Dd, base + j);   // ReliefF.py:146-155
+        P[o] = make_uint2(__float_as_uint(d), (uint32_t)o);
+    }
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) sel[base + j] = FS_MASK_NONE;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    numba_argsort_pairs(P, n);
+    const int ci = y[self];
+    double denom = 1.0 - (double)class_probs[ci];
+    if (denom == 0.0) denom = 1.0;
+    int found[kMaxTieClasses];
+    for (int c = 0; c < n_classes; ++c) found[c] = 0;
+    int slot = 0, filled = 0;
+    for (int64_t q = 0; q < n && filled < n_classes; ++q) {
+        const int64_t j = inv_perm[P[q].y];
+        const int c = y[j];
+        if (found[c] >= k) continue;
+        if (++found[c] == k) ++filled;
+        sel[base + j] = c == ci ? FS_MASK_NEAR_HIT : FS_MASK_NEAR_MISS;
+        if (slot < nbr_cap) {
+            nbr_idx[r * nbr_cap + slot] = (int32_t)j;
+            nbr_w[r * nbr_cap + slot] = c == ci ? -1.0 : ((double)class_probs[c] / denom) / (double)k;
+        }
+        ++slot;
+    }
+    const double wh = found[ci] > 0 ? -1.0 / (double)found[ci] : 0.0;   // ReliefF.py:211-212
+    const int m = slot < nbr_cap ? slot : nbr_cap;
+    for (int e = 0; e < m; ++e)
+        if (nbr_w[r * nbr_cap + e] == -1.0) nbr_w[r * nbr_cap + e] = wh;
+    nbr_cnt[r] = m;
+}
+
 __global__ void __launch_bounds__(32) relieff_ties_kernel(
     const double *__restrict__ Dc, const int32_t *__restrict__ Dd, int64_t ldn, int64_t n,
     const int64_t *__restrict__ row_ids, const int32_t *__restrict__ y, const int64_t *__restrict__ inv_perm,
@@ -445,18 +551,34 @@ void launch_select(fs_dataset *ds, int algo, int use_star, int32_t k, const int6
         // reference tie order unless FS_B200_RELIEFF_TIES=index (ties then go by sample index)
         const char *env = getenv("FS_B200_RELIEFF_TIES");
         const bool emulate = !(env && env[0] == 'i') && ds->n_classes <= kMaxTieClasses;
-        if (emulate) ds->tie_flag.reserve(R);
+        if (emulate) {
+            ds->tie_flag.reserve(R);
+            ds->tie_list.reserve(R + 1);
+            FS_CUDA(cudaMemsetAsync(ds->tie_list.ptr, 0, sizeof(int32_t), st));
+        }
         relieff_select_kernel<<<grid, 256, 0, st>>>(Dc, Dd, ldn, ds->n, row_ids, ds->d_y.ptr, ds->d_cls_start.ptr,
                                                     ds->n_classes, k, class_probs, sel, rinfo, nbr_idx, nbr_w,
-                                                    nbr_cnt, nbr_cap, emulate ? ds->tie_flag.ptr : nullptr);
+                                                    nbr_cnt, nbr_cap, emulate ? ds->tie_flag.ptr : nullptr,
+                                                    emulate ? ds->tie_list.ptr : nullptr);
         if (emulate) {
             FS_CUDA(cudaGetLastError());
             ++*launches;
-            ds->tie_keys.reserve((size_t)R * ds->n);
-            ds->tie_order.reserve((size_t)R * ds->n);
-            relieff_ties_kernel<<<(unsigned)ceil_div(R, 32), 32, 0, st>>>(
-                Dc, Dd, ldn, ds->n, row_ids, ds->d_y.ptr, ds->d_inv_perm.ptr, ds->n_classes, k, class_probs,
-                ds->tie_flag.ptr, ds->tie_keys.ptr, ds->tie_order.ptr, sel, nbr_idx, nbr_w, nbr_cnt, nbr_cap, R);
+            const size_t pair_bytes = (size_t)ds->n * sizeof(uint2);
+            if (pair_bytes <= 200 * 1024) {
+                // the row fits in shared memory: one CTA per ambiguous row of the compacted list
+                // (CTAs beyond the list's length exit at once; no host round trip for the count)
+                FS_CUDA(cudaFuncSetAttribute(relieff_ties_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)pair_bytes));
+                relieff_ties_smem_kernel<<<grid, 256, pair_bytes, st>>>(
+                    Dc, Dd, ldn, ds->n, row_ids, ds->d_y.ptr, ds->d_inv_perm.ptr, ds->n_classes, k, class_probs,
+                    ds->tie_list.ptr, sel, nbr_idx, nbr_w, nbr_cnt, nbr_cap);
+            } else {
+                ds->tie_keys.reserve((size_t)R * ds->n);
+                ds->tie_order.reserve((size_t)R * ds->n);
+                relieff_ties_kernel<<<(unsigned)ceil_div(R, 32), 32, 0, st>>>(
+                    Dc, Dd, ldn, ds->n, row_ids, ds->d_y.ptr, ds->d_inv_perm.ptr, ds->n_classes, k, class_probs,
+                    ds->tie_flag.ptr, ds->tie_keys.ptr, ds->tie_order.ptr, sel, nbr_idx, nbr_w, nbr_cnt, nbr_cap, R);
+            }
         }
     }
     FS_CUDA(cudaGetLastError());
