@@ -225,3 +225,29 @@ def test_turf_selection_equals_argsort_prefix():
         s = rs.randint(0, 5, n).astype(np.float32) if trial % 2 else rs.standard_normal(n).astype(np.float32)
         k = rs.randint(1, n + 1)
         assert set(TuRF._worst(s, k).tolist()) == set(np.argsort(s)[:k].tolist())
+
+
+def test_aligned_shards_partition_every_row_once():
+    """shard_rows(align=4): the multi-GPU symmetric distance kernel wants shard starts that are
+    multiples of 4; the shards must still cover every row exactly once."""
+    from fastselect_b200._shard import shard_starts
+
+    for n in (5, 61, 4000, 5656, 11312):
+        for w in (1, 2, 3, 8):
+            starts = shard_starts(n, w, align=4)
+            assert starts[0] == 0 and starts[-1] == n and len(starts) == w + 1
+            assert all(a <= b for a, b in zip(starts, starts[1:]))
+            assert all(s % 4 == 0 for s in starts[:-1])
+            assert [shard_rows(n, w, r, 4) for r in range(w)] == list(zip(starts, starts[1:]))
+
+
+def test_top_features_equal_the_reference_expression():
+    """_ReliefBase._top == np.argsort(scores)[::-1][:k] (MultiSURF.py:443), ties included."""
+    from fastselect_b200._relief import _ReliefBase
+
+    rs = np.random.RandomState(1)
+    for trial in range(300):
+        p = rs.randint(9, 400)
+        k = rs.randint(1, max(2, p // 8))
+        s = (rs.randint(0, 50, p) / 7).astype(np.float32) if trial % 2 else rs.standard_normal(p).astype(np.float32)
+        assert np.array_equal(_ReliefBase._top(s, k), np.argsort(s)[::-1][:k])
