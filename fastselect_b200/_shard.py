@@ -69,6 +69,8 @@ def setup_peers(ds, n: int, align: int = 4) -> bool:
     if dist.get_backend() != "nccl" or world > 16:
         return False
     starts = shard_starts(n, world, align)
+    if any(a == b for a, b in zip(starts, starts[1:])):
+        return False        # a rank without rows would skip the barrier inside fs_score
     ok = torch.ones(1, dtype=torch.int32, device="cuda")
     handles = torch.zeros(world * 64, dtype=torch.uint8, device="cuda")
     try:

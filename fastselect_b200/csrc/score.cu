@@ -141,9 +141,15 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
     // shard (multi-GPU symmetric mode), else the data set's own buffer
     int32_t *Dd = nullptr;
     if (ws.pt > 0) {
+        // every rank must take the same decision (the barrier inside the pipeline has to match):
+        // the single-chunk condition is evaluated for the LARGEST shard, not for this rank's own
+        int64_t max_shard = 0;
+        for (int q = 0; ds->peers_on && q < ds->peers.world; ++q)
+            max_shard = std::max<int64_t>(max_shard, ds->peers.starts[q + 1] - ds->peers.starts[q]);
         const bool my_shard = ds->peers_on && contiguous && dbg == nullptr &&
                               targets[0] == ds->peers.starts[ds->peers.rank] &&
                               (int64_t)targets.size() == ds->peers.starts[ds->peers.rank + 1] - ds->peers.starts[ds->peers.rank] &&
+                              round_up(max_shard, 128) <= chunk_rows(ws.pg > 0, ws.pt > 0, ldn, algo) &&
                               (size_t)Rmax * ldn <= ds->peer_slab_count && Rmax >= (int64_t)targets.size();
         if (my_shard) {
             Dd = ds->peer_slab;
