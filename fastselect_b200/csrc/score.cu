@@ -124,8 +124,11 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
     const int64_t ldn = round_up(n, 128);
     // the one-hot distance slab of a contiguous target range that fits one chunk is kept between
     // calls: TuRF's next iteration subtracts the removed columns instead of recomputing it
-    const bool slab_cacheable = contiguous && dbg == nullptr &&
-                                round_up((int64_t)targets.size(), 128) <= chunk_rows(true, true, ldn, algo);
+    // (with peers configured the decision is taken for the largest shard, so that all ranks agree)
+    int64_t cache_rows = (int64_t)targets.size();
+    for (int q = 0; ds->peers_on && q < ds->peers.world; ++q)
+        cache_rows = std::max<int64_t>(cache_rows, ds->peers.starts[q + 1] - ds->peers.starts[q]);
+    const bool slab_cacheable = contiguous && dbg == nullptr && round_up(cache_rows, 128) <= chunk_rows(true, true, ldn, algo);
     if (!slab_cacheable) ds->dd_valid = false;
     timer.begin(PH_GATHER);
     const auto prep0 = std::chrono::steady_clock::now();
