@@ -190,7 +190,7 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------- #
 # CPU baseline (oracle port on a bounded sample)
 # --------------------------------------------------------------------------- #
-def cpu_sample(w, n_s=1000, p_s=4000):
+def cpu_sample(w, n_s=2000, p_s=5000):
     n_s, p_s = min(n_s, w["n"], w["x"].shape[0]), min(p_s, w["p"])
     return w["x"][:n_s, :p_s], w["y"][:n_s], n_s, p_s
 
@@ -232,7 +232,7 @@ def reference_arm(args):
 
     R.build()
     R.set_threads(os.cpu_count() or 1)
-    w = make_workload(args.workload, 1, "weak", args.n, args.p, rows=1000)
+    w = make_workload(args.workload, 1, "weak", args.n, args.p, rows=2000)
     xs, ys, n_s, p_s = cpu_sample(w)
     for _ in range(args.warmup):
         run_cpu_port(w, xs[:200], ys[:200])
