@@ -266,6 +266,7 @@ struct fs_dataset {
     fs::DevBuf<char> xa_gather;   // gathered target rows (fs_debug_rows)
     fs::DevBuf<double> tpartial;  // tensor-path accumulation partials
     fs::DevBuf<int32_t> tile_desc; // target-tile descriptors of the accumulation kernel
+    fs::DevBuf<int32_t> tile_consts; // per-(tile, phase, target) coefficient limbs and mask row sums
     fs::DevBuf<int8_t> maskH, maskM;
     fs::DevBuf<int8_t> a_gather;  // gathered one-hot target rows (fs_debug_rows)
     fs::DevBuf<int32_t> tie_flag, tie_order, tie_list;   // ReliefF reference tie order (select.cu)

@@ -59,10 +59,9 @@ constexpr int B_BYTES = BN * BK;                  // 30 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 46 KB (a multiple of 1024: swizzle-atom aligned)
 constexpr int GROUP = 8;                          // target tiles per work unit
 constexpr int MAX_TILES = 256;                    // tile descriptors per launch (staged in shared memory)
-constexpr int CONST_BYTES = 2 * 256 * 16;         // [2][BN padded to 256] x {int2 coefficient limbs; int rs; int pad}
 constexpr int DESC_BYTES = MAX_TILES * 32;
 constexpr int BAR_BYTES = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + CONST_BYTES + DESC_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES + DESC_BYTES;
 constexpr int EPI_WARPS = 12;            // epilogue warps: 3 per TMEM lane quarter, one column part each
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = 64 + EPI_THREADS; // TMA warp, MMA warp, epilogue warps
@@ -95,13 +94,35 @@ __device__ __forceinline__ int2 coef_limbs(double c) {
 }
 }  // namespace
 
+// Per-target constants of every work item, laid out per (tile, phase) with a stride of 256
+// targets: limbs[.] = fixed-point (Chi, Clo) of the item's coefficient (-aH for the hit phase,
+// +aM for the miss phase), rsum[.] = the mask's row sum.  Targets beyond the tile's rows get
+// zeros.  Written once per launch so that the accumulation epilogue reads them with uniform
+// (broadcast) loads instead of staging them through shared memory behind a barrier per item.
+__global__ void __launch_bounds__(256) accum_consts_kernel(const TileDesc *__restrict__ tiles, int num_tiles,
+                                                           const RowInfo *__restrict__ rinfo, int2 *__restrict__ limbs,
+                                                           int32_t *__restrict__ rsum) {
+    const int t = blockIdx.x >> 1, phase = blockIdx.x & 1, e = threadIdx.x;
+    if (t >= num_tiles) return;
+    const TileDesc d = tiles[t];
+    double c = 0.0;
+    int rs = 0;
+    if (e < d.rows) {
+        const RowInfo ri = rinfo[d.row0 + e];
+        c = phase == 0 ? ri.coef[FS_MASK_NEAR_HIT] : ri.coef[FS_MASK_NEAR_MISS];
+        rs = phase == 0 ? ri.n_hit - ri.n_far_hit : ri.n_miss - ri.n_far_miss;
+    }
+    limbs[(size_t)blockIdx.x * 256 + e] = coef_limbs(c);
+    rsum[(size_t)blockIdx.x * 256 + e] = rs;
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_constant__ CUtensorMap tmap_mh,
                 const __grid_constant__ CUtensorMap tmap_mm, int num_k_blocks, int64_t R,
                 const TileDesc *__restrict__ tiles, int num_tiles, int groups, int group_tiles, int m_blocks,
-                const int64_t *__restrict__ ids, int contiguous, const RowInfo *__restrict__ rinfo,
-                const uint8_t *__restrict__ codesT, int64_t ldt, const uint32_t *__restrict__ krow, int64_t K_rows,
-                double *__restrict__ tpartial) {
+                const int64_t *__restrict__ ids, int contiguous, const int2 *__restrict__ limbs,
+                const int32_t *__restrict__ rsum, const uint8_t *__restrict__ codesT, int64_t ldt,
+                const uint32_t *__restrict__ krow, int64_t K_rows, double *__restrict__ tpartial) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // pointer arithmetic only (no integer round trip), so the compiler keeps the shared address space
     unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -111,14 +132,14 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
     uint64_t *tempty_bar = tfull_bar + 2;         // [2] accumulator buffer drained
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
     // per-target constants of the work item being drained: [2][BN] x {double c; int rs}
-    unsigned char *s_const = smem + STAGES * STAGE_BYTES + BAR_BYTES;
-    const TileDesc *s_tiles = reinterpret_cast<const TileDesc *>(s_const + CONST_BYTES);
+    unsigned char *s_desc = smem + STAGES * STAGE_BYTES + BAR_BYTES;
+    const TileDesc *s_tiles = reinterpret_cast<const TileDesc *>(s_desc);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int units = m_blocks * groups;
 
     for (int i = threadIdx.x; i < num_tiles * 2; i += THREADS)
-        reinterpret_cast<uint4 *>(s_const + CONST_BYTES)[i] = reinterpret_cast<const uint4 *>(tiles)[i];
+        reinterpret_cast<uint4 *>(s_desc)[i] = reinterpret_cast<const uint4 *>(tiles)[i];
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmap_at);
         tc::prefetch_tmap(&tmap_mh);
@@ -289,22 +310,9 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                     const int buf = item & 1;
                     const uint32_t tph = (item >> 1) & 1;
                     ++item;
-                    // per-target constants: c = -aH (hit phase) or +aM (miss phase) as fixed-point
-                    // limbs; rs = mask row sum
-                    int2 *s_c = reinterpret_cast<int2 *>(s_const + buf * 256 * 16);
-                    int32_t *s_rs = reinterpret_cast<int32_t *>(s_const + buf * 256 * 16 + 256 * 8);
-                    if (ethread < BN) {
-                        double c = 0.0;
-                        int rs = 0;
-                        if (ethread < d.rows) {
-                            const RowInfo ri = rinfo[d.row0 + ethread];
-                            c = phase == 0 ? ri.coef[FS_MASK_NEAR_HIT] : ri.coef[FS_MASK_NEAR_MISS];
-                            rs = phase == 0 ? ri.n_hit - ri.n_far_hit : ri.n_miss - ri.n_far_miss;
-                        }
-                        s_c[ethread] = coef_limbs(c);
-                        s_rs[ethread] = rs;
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                    // per-target constants of this work item (accum_consts_kernel): uniform loads
+                    const int2 *s_c = limbs + ((size_t)t * 2 + phase) * 256;
+                    const int32_t *s_rs = rsum + ((size_t)t * 2 + phase) * 256;
                     tc::mbar_wait(&tfull_bar[buf], tph);
                     tc::tc_fence_after();
                     const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * HALF);
@@ -319,8 +327,8 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                         for (int e = 0; e < 16; e += 4) {
                             const uint32_t w = oh[(c0 + e) >> 2];
                             const uint32_t own = __vcmpeq4(w, own4), lst = __vcmpeq4(w, last4);
-                            const int4 rs4 = rr[e >> 2];
-                            const int4 ca = cc[e >> 1], cb = cc[(e >> 1) + 1];   // (Chi, Clo) of two targets each
+                            const int4 rs4 = __ldg(rr + (e >> 2));
+                            const int4 ca = __ldg(cc + (e >> 1)), cb = __ldg(cc + (e >> 1) + 1);   // (Chi, Clo) of two targets each
                             // t = own ? rs - G : (last ? G : 0)
                             const int g0 = tc::f32_to_int_exact(v[e]), g1 = tc::f32_to_int_exact(v[e + 1]);
                             const int g2 = tc::f32_to_int_exact(v[e + 2]), g3 = tc::f32_to_int_exact(v[e + 3]);
@@ -399,7 +407,7 @@ static AccumPlan make_plan(int64_t n, int64_t R, bool contiguous, const int64_t 
 int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
                     int64_t R, const int64_t *d_ids, bool contiguous, const RowInfo *rinfo, const uint8_t *codesT,
                     int64_t ldt, const uint32_t *krow, int64_t K_rows, DevBuf<double> &tpartial, int32_t *d_tiles,
-                    cudaStream_t st, int *launches, const int64_t *h_ids, const int32_t *h_y,
+                    DevBuf<int32_t> &consts, cudaStream_t st, int *launches, const int64_t *h_ids, const int32_t *h_y,
                     const int64_t *h_cls_start, double *ops) {
     FS_CUDA(cudaFuncSetAttribute(tc_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int dev = 0, sms = 0;
@@ -431,11 +439,17 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
         const int groups = (int)ceil_div(nt, group_tiles);
         // pageable source: the copy is staged before cudaMemcpyAsync returns
         FS_CUDA(cudaMemcpyAsync(d_tiles, plan.tiles.data() + t0, nt * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
+        // per-item constants: [nt x 2 phases x 256] (Chi, Clo) pairs, then as many row sums
+        consts.reserve((size_t)nt * 2 * 256 * 3);
+        int2 *limbs = reinterpret_cast<int2 *>(consts.ptr);
+        int32_t *rsum = consts.ptr + (size_t)nt * 2 * 256 * 2;
+        accum_consts_kernel<<<2 * nt, 256, 0, st>>>(reinterpret_cast<const TileDesc *>(d_tiles), nt, rinfo, limbs, rsum);
+        ++*launches;
         const int units = m_blocks * groups;
         const int grid = units < sms ? units : sms;
         tc_accum_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(
             tmap_at, tmap_mh, tmap_mm, (int)ceil_div(n, KS), R, reinterpret_cast<const TileDesc *>(d_tiles), nt,
-            groups, group_tiles, m_blocks, d_ids, contiguous ? 1 : 0, rinfo, codesT, ldt, krow, K_rows,
+            groups, group_tiles, m_blocks, d_ids, contiguous ? 1 : 0, limbs, rsum, codesT, ldt, krow, K_rows,
             tpartial.ptr + (size_t)groups_done * PARTS * K_rows);
         FS_CUDA(cudaGetLastError());
         ++*launches;
