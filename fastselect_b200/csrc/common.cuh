@@ -177,7 +177,8 @@ struct WorkSet {
     DevBuf<int64_t> tcol, tout;     // [pt]
     DevBuf<int32_t> toff;           // [pt+1] first reduced one-hot row of each column
     PinnedBuf<int64_t> p_tcol, p_tout;   // host copies of tcol / tout / toff (pinned staging)
-    PinnedBuf<int32_t> p_toff;
+    PinnedBuf<int32_t> p_toff, p_tpos;
+    DevBuf<int32_t> tpos;           // [pt] codesT row of each active column when the resident codesT is reused
     DevBuf<int8_t> U;               // [n, K]    sample-major, U[i,(f,v)] = [code == v]            (target side of the distance GEMM)
     DevBuf<int8_t> Wd;              // [n, K]    sample-major, U + [code != last]                 (sample side of the distance GEMM)
     DevBuf<int8_t> At;              // [K, ldt]  feature-major reduced one-hot (sample index contiguous)
@@ -235,6 +236,9 @@ struct fs_dataset {
     std::vector<uint8_t> is_discrete;
     std::vector<float> recip;
     std::vector<uint8_t> col_info;           // kCol* flags per column
+    // resident codesT (ws.codesT): row of each original column in it (-1: none); see build_onehot
+    std::vector<int32_t> ct_pos;
+    bool ct_valid = false;
     // per-call scratch, kept between calls (TuRF re-scores the same data set)
     fs::WorkSet ws;
     fs::DevBuf<double> Dc;        // [R, ldn] continuous/general distance part

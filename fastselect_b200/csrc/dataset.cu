@@ -682,6 +682,7 @@ int fs_dataset_set_features(fs_dataset *ds, const uint8_t *is_discrete, const fl
     ds->have_features = true;
     ds->ws.valid = false;
     ds->dd_valid = false;
+    ds->ct_valid = false;
     return FS_OK;
 }
 

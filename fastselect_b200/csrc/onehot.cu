@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
     const int32_t *__restrict__ toff, const double *__restrict__ vals, int as_f32, int64_t n, int64_t pt, int64_t K,
     int64_t ldt, int64_t ldc, int8_t *__restrict__ U, int8_t *__restrict__ Wd, int8_t *__restrict__ At,
     uint8_t *__restrict__ codesT, uint8_t *__restrict__ codes, int32_t *__restrict__ srow,
-    uint32_t *__restrict__ krow, int all_ident, int64_t u_lo, int64_t u_hi) {
+    uint32_t *__restrict__ krow, int all_ident, int64_t u_lo, int64_t u_hi, const int32_t *__restrict__ tpos) {
     __shared__ __align__(16) uint8_t code_rc[ENC_ROWS][ENC_COLS];       // [sample][column]
     __shared__ __align__(16) uint8_t code_cr[ENC_COLS][ENC_CR_LD];      // [column][sample]
     __shared__ uint8_t kcol[ENC_KMAX];                                  // reduced row -> column in tile
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
                     kcol[off - k0 + q] = (uint8_t)c;
                     kval[off - k0 + q] = (uint8_t)q;
                     if (tile_y == 0 && krow)
-                        krow[off + q] = (uint32_t)(c0 + c) | ((uint32_t)q << 24) | ((uint32_t)(V - 1) << 28);
+                        krow[off + q] = (uint32_t)(tpos ? tpos[c0 + c] : (int32_t)(c0 + c)) | ((uint32_t)q << 24) | ((uint32_t)(V - 1) << 28);
                 }
             }
         }
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
             const int64_t lda = ldt >> 1;                                     // At: two samples per byte
             *reinterpret_cast<uint2 *>(At + (int64_t)(k0 + 2 * c) * lda + (o >> 1)) = pack_fp4_flags16(e0.x, e0.y, e0.z, e0.w);
             *reinterpret_cast<uint2 *>(At + (int64_t)(k0 + 2 * c + 1) * lda + (o >> 1)) = pack_fp4_flags16(e1.x, e1.y, e1.z, e1.w);
-            *reinterpret_cast<uint4 *>(codesT + (c0 + c) * ldt + o) = w;
+            if (codesT) *reinterpret_cast<uint4 *>(codesT + (c0 + c) * ldt + o) = w;
         }
     } else {
         const int nk = k1 - k0;
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
                 }
             }
         }
-        for (int item = tid; item < ncols * 8; item += 256) {
+        for (int item = tid; codesT != nullptr && item < ncols * 8; item += 256) {
             const int c = item >> 3, seg = item & 7;
             const uint32_t *src = reinterpret_cast<const uint32_t *>(&code_cr[c][16 * seg]);
             const uint4 o = make_uint4(src[0], src[1], src[2], src[3]);
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
     const uint8_t *__restrict__ x, int64_t ldx, const int64_t *__restrict__ perm, const int64_t *__restrict__ tcol,
     int64_t n, int64_t pt, int64_t K, int64_t ldt, int64_t ldc, int8_t *__restrict__ U, int8_t *__restrict__ Wd,
     int8_t *__restrict__ At, uint8_t *__restrict__ codesT, uint8_t *__restrict__ codes, int32_t *__restrict__ srow,
-    uint32_t *__restrict__ krow, int64_t u_lo, int64_t u_hi) {
+    uint32_t *__restrict__ krow, int64_t u_lo, int64_t u_hi, const int32_t *__restrict__ tpos) {
     __shared__ __align__(16) uint8_t code_rc[ENC_ROWS][ENC_COLS];       // [sample][column]
     __shared__ __align__(16) uint8_t code_cr[ENC_COLS][ENC_CR_LD];      // [column][sample]
     __shared__ int64_t sperm[ENC_ROWS];
@@ -395,12 +395,21 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
     const int c = tid & (ENC_COLS - 1);
     const int64_t f = c < ncols ? tcol[c0 + c] : 0, f0 = tcol[c0];
     if (tile_y == 0 && krow && tid < ncols) {
-        krow[k0 + 2 * tid] = (uint32_t)(c0 + tid) | (2u << 28);
-        krow[k0 + 2 * tid + 1] = (uint32_t)(c0 + tid) | (1u << 24) | (2u << 28);
+        const uint32_t crow = (uint32_t)(tpos ? tpos[c0 + tid] : (int32_t)(c0 + tid));   // codesT row of this column
+        krow[k0 + 2 * tid] = crow | (2u << 28);
+        krow[k0 + 2 * tid + 1] = crow | (1u << 24) | (2u << 28);
     }
     // ---- step 1: codes (= values) into shared memory, both orientations
     const bool fast1 = __syncthreads_and(ncols == ENC_COLS && f == f0 + c && (ldx & 15) == 0 &&
                                          ((reinterpret_cast<uintptr_t>(x) + f0) & 15) == 0);
+    // second choice: the tile's columns lie within kSpan bytes of x (16-byte aligned base)
+    constexpr int kSpan = 256, kSpanRows = 32;
+    __shared__ __align__(16) uint8_t raw[kSpanRows][kSpan];
+    const int64_t fbase = f0 & ~(int64_t)15;
+    const int64_t flast = tcol[c0 + ncols - 1];
+    const bool span_ok = __syncthreads_and(!fast1 && (ldx & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                                           flast - fbase < kSpan && (c >= ncols || (f >= fbase && f <= flast)));
+    const int span_chunks = (int)((flast - fbase) >> 4) + 1;          // 16-byte chunks that hold a wanted column
     if (fast1) {
         // the tile's 64 columns are 64 consecutive, 16-byte aligned bytes of every row of x
 #pragma unroll
@@ -415,6 +424,28 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
             const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
             for (int b = 0; b < 16; ++b) code_cr[16 * ch + b][rr] = (uint8_t)(qw[b >> 2] >> (8 * (b & 3)));
+        }
+    } else if (span_ok) {
+        // gathered columns whose span in x is short (TuRF's early iterations: ascending columns with
+        // a few gaps): the span [fbase, fbase + kSpan) of 32 rows at a time is staged in shared memory
+        // with coalesced 16-byte loads, and every thread picks its column's bytes from there
+        for (int rb = 0; rb < ENC_ROWS; rb += kSpanRows) {
+            for (int item = tid; item < kSpanRows * span_chunks; item += 256) {
+                const int rr = rb + item / span_chunks, ch = item % span_chunks;
+                uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                if (rr < nrows && fbase + 16 * ch < ldx) q = *reinterpret_cast<const uint4 *>(x + sperm[rr] * ldx + fbase + 16 * ch);
+                *reinterpret_cast<uint4 *>(&raw[rr - rb][16 * ch]) = q;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < kSpanRows / 4; ++u) {
+                const int rl = (tid >> 6) + 4 * u, rr = rb + rl;
+                const uint8_t xv = (c < ncols && rr < nrows) ? raw[rl][(int)(f - fbase)] : (uint8_t)0;
+                if (codes && c < ncols && rr < nrows) codes[(r0 + rr) * ldc + c0 + c] = xv;
+                code_rc[rr][c] = xv;
+                code_cr[c][rr] = xv;
+            }
+            __syncthreads();
         }
     } else {
         // gathered columns (TuRF iterations): one column per thread, 8 loads in flight
@@ -494,11 +525,11 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
             const int64_t o = r0 + 16 * seg;                                  // r0, ldt multiples of 128: aligned
             const int64_t lda = ldt >> 1;                                     // At: two samples per byte (FP4 nibbles)
             int8_t *a0 = At + (k0 + 2 * cc) * lda + (o >> 1), *a1 = a0 + lda;
-            uint8_t *ct = codesT + (c0 + cc) * ldt + o;
+            uint8_t *ct = codesT ? codesT + (c0 + cc) * ldt + o : nullptr;
             if (16 * seg + 16 <= nrows) {
                 *reinterpret_cast<uint2 *>(a0) = pack_fp4_flags16(e0.x, e0.y, e0.z, e0.w);
                 *reinterpret_cast<uint2 *>(a1) = pack_fp4_flags16(e1.x, e1.y, e1.z, e1.w);
-                *reinterpret_cast<uint4 *>(ct) = w;
+                if (ct) *reinterpret_cast<uint4 *>(ct) = w;
             } else {
                 for (int b = 0; b < 16 && 16 * seg + b < nrows; b += 2) {
                     const uint32_t ca = code_cr[cc][16 * seg + b];
@@ -506,8 +537,10 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
                     const uint32_t cb = two ? code_cr[cc][16 * seg + b + 1] : 3u;     // 3 matches no value
                     a0[b >> 1] = (int8_t)((ca == 0u ? 0x02u : 0u) | (cb == 0u ? 0x20u : 0u));
                     a1[b >> 1] = (int8_t)((ca == 1u ? 0x02u : 0u) | (cb == 1u ? 0x20u : 0u));
-                    ct[b] = (uint8_t)ca;
-                    if (two) ct[b + 1] = (uint8_t)cb;
+                    if (ct) {
+                        ct[b] = (uint8_t)ca;
+                        if (two) ct[b + 1] = (uint8_t)cb;
+                    }
                 }
             }
         }
@@ -557,7 +590,7 @@ static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
     if (lean) {
         onehot_encode_v3_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(ds->x), ds->ldx, ds->d_perm.ptr,
                                                       ws.rcol.ptr, n, pr, (int64_t)Kb, ws.ldt, 0, ws.Ur.ptr, ws.Wdr.ptr, nullptr,
-                                                      nullptr, nullptr, ws.srow_r.ptr, nullptr, 0, n);
+                                                      nullptr, nullptr, ws.srow_r.ptr, nullptr, 0, n, nullptr);
         FS_CUDA(cudaGetLastError());
         ++*launches;
         return;
@@ -566,7 +599,7 @@ static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
     onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,        \
                                                   ws.rcol.ptr, ws.roff.ptr, ds->d_vals.ptr, as_f32, n, pr, (int64_t)Kb, \
                                                   ws.ldt, 0, ws.Ur.ptr, ws.Wdr.ptr, nullptr, nullptr, nullptr,    \
-                                                  ws.srow_r.ptr, nullptr, all_ident, 0, n)
+                                                  ws.srow_r.ptr, nullptr, all_ident, 0, n, nullptr)
     switch (ds->dtype) {
         case FS_U8: FS_ENCODE_R(uint8_t); break;
         case FS_I8: FS_ENCODE_R(int8_t); break;
@@ -595,13 +628,28 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
         ws.srow.reserve(ws.ldt);   // padded: the distance epilogue reads it in 16-byte vectors
     }
     ws.At.reserve((size_t)ws.K * (ws.ldt / 2));          // FP4 nibbles: two samples per byte
-    ws.codesT.reserve((size_t)pt * ws.ldt + 512);   // slack: the accumulation epilogue reads whole 128-byte runs
+    // codesT (value codes, feature-major) depends on a column only, not on which other columns are
+    // active: when every active column already has a row in the resident codesT of an earlier, wider
+    // encode (TuRF iterations), that table is kept and the one-hot rows point into it (krow)
+    bool reuse_ct = ds->ct_valid;
+    for (int64_t c = 0; c < pt && reuse_ct; ++c) reuse_ct = ds->ct_pos[ws.p_tcol.ptr[c]] >= 0;
+    if (reuse_ct) {
+        ws.p_tpos.reserve(pt);
+        for (int64_t c = 0; c < pt; ++c) ws.p_tpos.ptr[c] = ds->ct_pos[ws.p_tcol.ptr[c]];
+        ws.tpos.reserve(pt);
+    } else {
+        ws.codesT.reserve((size_t)pt * ws.ldt + 512);   // slack: the accumulation epilogue reads whole 128-byte runs
+        ds->ct_pos.assign(ds->p, -1);
+        for (int64_t c = 0; c < pt; ++c) ds->ct_pos[ws.p_tcol.ptr[c]] = (int32_t)c;
+        ds->ct_valid = true;
+    }
     if (ws.have_codes) ws.codes.reserve((size_t)n * ws.ldc);
     ws.krow.reserve(ws.K);
     cudaStream_t st = ds->stream;
     FS_CUDA(cudaMemcpyAsync(ws.tcol.ptr, ws.p_tcol.ptr, pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     FS_CUDA(cudaMemcpyAsync(ws.tout.ptr, ws.p_tout.ptr, pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     FS_CUDA(cudaMemcpyAsync(ws.toff.ptr, ws.p_toff.ptr, (pt + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (reuse_ct) FS_CUDA(cudaMemcpyAsync(ws.tpos.ptr, ws.p_tpos.ptr, pt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     // the encode kernel writes every used byte of U, Wd, At and codesT exactly once; only the K
     // padding (reduced rows K_used..K) has to be cleared.  Sample padding of the feature-major
     // rows (columns n..ldt) is never read (the TMA maps are n bytes wide).
@@ -625,9 +673,10 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
         // every active column holds exactly the byte values 0/1/2: lean kernel
         onehot_encode_v3_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(ds->x), ds->ldx, ds->d_perm.ptr,
                                                       ws.tcol.ptr, n, pt, (int64_t)Kb, ws.ldt, ws.ldc, ops ? ws.U.ptr : nullptr,
-                                                      ops ? ws.Wd.ptr : nullptr, ws.At.ptr, ws.codesT.ptr,
+                                                      ops ? ws.Wd.ptr : nullptr, ws.At.ptr, reuse_ct ? nullptr : ws.codesT.ptr,
                                                       ws.have_codes ? ws.codes.ptr : nullptr,
-                                                      ops ? ws.srow.ptr : nullptr, ws.krow.ptr, ws.u_lo, ws.u_hi);
+                                                      ops ? ws.srow.ptr : nullptr, ws.krow.ptr, ws.u_lo, ws.u_hi,
+                                                      reuse_ct ? ws.tpos.ptr : nullptr);
         FS_CUDA(cudaGetLastError());
         ++*launches;
         if (ws.dist_mode == kDistIncremental) build_removed(ds, ws, launches);
@@ -637,9 +686,11 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,       \
                                                   ws.tcol.ptr, ws.toff.ptr, ds->d_vals.ptr, as_f32, n, pt, (int64_t)Kb, \
                                                   ws.ldt, ws.ldc, ops ? ws.U.ptr : nullptr,                      \
-                                                  ops ? ws.Wd.ptr : nullptr, ws.At.ptr, ws.codesT.ptr,           \
+                                                  ops ? ws.Wd.ptr : nullptr, ws.At.ptr,                          \
+                                                  reuse_ct ? nullptr : ws.codesT.ptr,                            \
                                                   ws.have_codes ? ws.codes.ptr : nullptr,                        \
-                                                  ops ? ws.srow.ptr : nullptr, ws.krow.ptr, all_ident, ws.u_lo, ws.u_hi)
+                                                  ops ? ws.srow.ptr : nullptr, ws.krow.ptr, all_ident, ws.u_lo, ws.u_hi, \
+                                                  reuse_ct ? ws.tpos.ptr : nullptr)
     switch (ds->dtype) {
         case FS_U8: FS_ENCODE(uint8_t); break;
         case FS_I8: FS_ENCODE(int8_t); break;
