@@ -251,3 +251,19 @@ def test_top_features_equal_the_reference_expression():
         k = rs.randint(1, max(2, p // 8))
         s = (rs.randint(0, 50, p) / 7).astype(np.float32) if trial % 2 else rs.standard_normal(p).astype(np.float32)
         assert np.array_equal(_ReliefBase._top(s, k), np.argsort(s)[::-1][:k])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the oracle port on the host cores) prints one JSON line with the
+    keys the driver reads; tiny workload so that the CPU suite stays fast."""
+    import json
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--n", "300",
+                          "--p", "400", "--steps", "1", "--warmup", "1"], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "multisurf_fit_pair_features_per_s"
+    assert line["unit"] == "sample-pair*features/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and line["vs_baseline"] is None
