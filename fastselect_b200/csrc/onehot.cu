@@ -430,8 +430,10 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
         // a few gaps): the span [fbase, fbase + kSpan) of 32 rows at a time is staged in shared memory
         // with coalesced 16-byte loads, and every thread picks its column's bytes from there
         for (int rb = 0; rb < ENC_ROWS; rb += kSpanRows) {
-            for (int item = tid; item < kSpanRows * span_chunks; item += 256) {
-                const int rr = rb + item / span_chunks, ch = item % span_chunks;
+            // fixed 16-chunk indexing (no division by the run-time chunk count); chunks past the span idle
+            for (int item = tid; item < kSpanRows * (kSpan / 16); item += 256) {
+                const int rr = rb + (item >> 4), ch = item & 15;
+                if (ch >= span_chunks) continue;
                 uint4 q = make_uint4(0u, 0u, 0u, 0u);
                 if (rr < nrows && fbase + 16 * ch < ldx) q = *reinterpret_cast<const uint4 *>(x + sperm[rr] * ldx + fbase + 16 * ch);
                 *reinterpret_cast<uint4 *>(&raw[rr - rb][16 * ch]) = q;
