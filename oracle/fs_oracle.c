@@ -570,3 +570,133 @@ FSO_API int fso_relieff_targets(const float *x, int64_t n, int64_t p, const int3
     free(rows);
     return 0;
 }
+
+/* ======================================================================== */
+/* feature x feature joint-count tables and the     */
+/* two statistics the reference derives from them.                           */
+/*   mutual information  -- mutual_information.py:26-46 (_mi_pair_cpu) and   */
+/*                          :49-63 (_batch_mi_cpu: relevance + redundancy)   */
+/*   symmetrical uncertainty -- CFS.py:26-77 (_entropy, _mutual_information, */
+/*                          _symmetrical_uncertainty) and :81-104            */
+/* The count tables are integers and restated exactly.  The statistics are   */
+/* restated in float64.  The reference computes MI in float64 too (numba     */
+/* fastmath only reassociates: golden vectors agree to 1e-15); its SU path   */
+/* keeps the probabilities and log2 terms in float32 (numba types p, p_xy,   */
+/* p_x, p_y as float32 arrays), which puts +-1e-7 of rounding noise on values */
+/* in [0, 1] -- the golden tests allow 1e-6 absolute for SU.                 */
+/* x is row-major [n, p] non-negative codes; states that never occur add 0.  */
+/* ------------------------------------------------------------------------ */
+#define FSO_MAX_STATES 64
+
+/* table[a * kb + b] = #{i : xa[i] = a, xb[i] = b}  (mutual_information.py:31-33, CFS.py:51-53) */
+FSO_API int fso_joint_counts(const int32_t *xa, const int32_t *xb, int64_t n, int32_t ka, int32_t kb,
+                             int64_t *table) {
+    if (n < 1 || ka < 1 || kb < 1 || ka > FSO_MAX_STATES || kb > FSO_MAX_STATES) return -1;
+    memset(table, 0, (size_t)ka * (size_t)kb * sizeof(int64_t));
+    for (int64_t i = 0; i < n; ++i) {
+        if (xa[i] < 0 || xa[i] >= ka || xb[i] < 0 || xb[i] >= kb) return -1;
+        table[(int64_t)xa[i] * kb + xb[i]] += 1;
+    }
+    return 0;
+}
+
+/* mutual_information.py:35-46 on an integer count table */
+static double mi_from_table(const int64_t *t, int ka, int kb, int64_t n, double log_base) {
+    double p1[FSO_MAX_STATES], p2[FSO_MAX_STATES];
+    for (int a = 0; a < ka; ++a) p1[a] = 0.0;
+    for (int b = 0; b < kb; ++b) p2[b] = 0.0;
+    for (int a = 0; a < ka; ++a)
+        for (int b = 0; b < kb; ++b) {
+            const double pxy = (double)t[a * kb + b] / (double)n;      /* :35 table /= n */
+            p1[a] += pxy;                                              /* :36 */
+            p2[b] += pxy;                                              /* :37 */
+        }
+    double mi = 0.0;
+    const double eps = 1e-12;
+    for (int a = 0; a < ka; ++a)
+        for (int b = 0; b < kb; ++b) {
+            const double pxy = (double)t[a * kb + b] / (double)n;
+            if (pxy > eps) mi += pxy * log(pxy / (p1[a] * p2[b] + eps));   /* :44-45 */
+        }
+    return mi / log_base;                                                  /* :46 */
+}
+
+static double entropy_counts(const int64_t *c, int k, int64_t n) {          /* CFS.py:26-41 */
+    double e = 0.0;
+    for (int s = 0; s < k; ++s) {
+        const double pr = (double)c[s] / (double)n;
+        if (pr > 1e-12) e -= pr * log2(pr);
+    }
+    return e;
+}
+
+/* CFS.py:44-77 on an integer count table */
+static double su_from_table(const int64_t *t, int ka, int kb, int64_t n) {
+    int64_t ca[FSO_MAX_STATES], cb[FSO_MAX_STATES];
+    double pa[FSO_MAX_STATES], pb[FSO_MAX_STATES];
+    for (int a = 0; a < ka; ++a) { ca[a] = 0; pa[a] = 0.0; }
+    for (int b = 0; b < kb; ++b) { cb[b] = 0; pb[b] = 0.0; }
+    for (int a = 0; a < ka; ++a)
+        for (int b = 0; b < kb; ++b) {
+            ca[a] += t[a * kb + b];
+            cb[b] += t[a * kb + b];
+            const double pxy = (double)t[a * kb + b] / (double)n;
+            pa[a] += pxy;                                                   /* :56 */
+            pb[b] += pxy;                                                   /* :57 */
+        }
+    const double hx = entropy_counts(ca, ka, n), hy = entropy_counts(cb, kb, n);
+    if (hx + hy < 1e-12) return 0.0;                                        /* :73-74 */
+    double mi = 0.0;
+    for (int a = 0; a < ka; ++a)
+        for (int b = 0; b < kb; ++b) {
+            const double pxy = (double)t[a * kb + b] / (double)n;
+            if (pxy > 1e-12 && pa[a] > 1e-12 && pb[b] > 1e-12) mi += pxy * log2(pxy / (pa[a] * pb[b]));   /* :62-63 */
+        }
+    return 2.0 * mi / (hx + hy);                                            /* :77 */
+}
+
+/* columns of x (and y as column p) as contiguous int32 vectors + their state counts */
+static int32_t *columns_of(const int32_t *x, int64_t n, int64_t p, const int32_t *y, int32_t *k_out) {
+    int32_t *cols = malloc((size_t)(p + 1) * n * sizeof(int32_t));
+    if (!cols) return NULL;
+    for (int64_t f = 0; f <= p; ++f) {
+        int32_t mx = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            const int32_t v = f < p ? x[i * p + f] : y[i];
+            if (v < 0 || v >= FSO_MAX_STATES) { free(cols); return NULL; }
+            cols[f * n + i] = v;
+            mx = v > mx ? v : mx;
+        }
+        k_out[f] = mx + 1;                     /* mutual_information.py:28-29: k = max + 1 */
+    }
+    return cols;
+}
+
+/* kind 0: MI (relevance / redundancy in units of log_base), kind 1: SU (r_cf / r_ff).
+ * vec_out[p] = statistic(feature f, y); mat_out[p*p] symmetric with a zero diagonal
+ * (mutual_information.py:52-63, CFS.py:87-104).  mat_out may be NULL. */
+FSO_API int fso_joint_matrices(const int32_t *x, int64_t n, int64_t p, const int32_t *y, int kind,
+                               double log_base, double *vec_out, double *mat_out) {
+    if (n < 1 || p < 1 || (kind != 0 && kind != 1)) return -1;
+    int32_t *k = malloc((size_t)(p + 1) * sizeof(int32_t));
+    if (!k) return -2;
+    int32_t *cols = columns_of(x, n, p, y, k);
+    if (!cols) { free(k); return -1; }
+    if (mat_out) memset(mat_out, 0, (size_t)p * p * sizeof(double));
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t f = 0; f < p; ++f) {
+        int64_t t[FSO_MAX_STATES * FSO_MAX_STATES];
+        fso_joint_counts(cols + f * n, cols + p * n, n, k[f], k[p], t);
+        vec_out[f] = kind == 0 ? mi_from_table(t, k[f], k[p], n, log_base) : su_from_table(t, k[f], k[p], n);
+        if (!mat_out) continue;
+        for (int64_t g = f + 1; g < p; ++g) {
+            fso_joint_counts(cols + f * n, cols + g * n, n, k[f], k[g], t);
+            const double v = kind == 0 ? mi_from_table(t, k[f], k[g], n, log_base) : su_from_table(t, k[f], k[g], n);
+            mat_out[f * p + g] = v;
+            mat_out[g * p + f] = v;
+        }
+    }
+    free(cols);
+    free(k);
+    return 0;
+}

@@ -244,3 +244,49 @@ def fit_relieff(x, y, discrete_limit=10, n_neighbors=3, tie_mode=0):
     if class_probs.size < 2:  # ReliefF.py:351-356
         return np.zeros(x32.shape[1], np.float32), isd
     return relieff_scores(x32, y_enc, recip, isd, n_neighbors, class_probs, tie_mode), isd
+
+
+# --------------------------------------------------------------------------- #
+# joint-count tables, mutual information, symmetrical uncertainty
+# --------------------------------------------------------------------------- #
+def joint_counts(xa, xb, ka=None, kb=None):
+    """Contingency table of two code vectors (mutual_information.py:31-33, CFS.py:51-53): int64 [ka, kb]."""
+    xa = np.ascontiguousarray(xa, np.int32)
+    xb = np.ascontiguousarray(xb, np.int32)
+    ka = int(xa.max()) + 1 if ka is None else int(ka)
+    kb = int(xb.max()) + 1 if kb is None else int(kb)
+    table = np.empty((ka, kb), np.int64)
+    _check(lib().fso_joint_counts(_p(xa, C.c_int32), _p(xb, C.c_int32), C.c_int64(xa.size), C.c_int32(ka),
+                                  C.c_int32(kb), _p(table, C.c_int64)), "fso_joint_counts")
+    return table
+
+
+def _joint_matrices(x_codes, y_codes, kind, log_base, want_matrix):
+    x_codes = np.ascontiguousarray(x_codes, np.int32)
+    y_codes = np.ascontiguousarray(y_codes, np.int32)
+    n, p = x_codes.shape
+    vec = np.empty(p, np.float64)
+    mat = np.empty((p, p), np.float64) if want_matrix else None
+    _check(lib().fso_joint_matrices(_p(x_codes, C.c_int32), C.c_int64(n), C.c_int64(p), _p(y_codes, C.c_int32),
+                                    C.c_int(kind), C.c_double(log_base), _p(vec, C.c_double), _p(mat, C.c_double)),
+           "fso_joint_matrices")
+    return vec, mat
+
+
+def mi_matrices(x_codes, y_codes, unit="bit", want_matrix=True):
+    """``calculate_mi_matrices`` (mutual_information.py:158-196, CPU path :49-63): (relevance [p], redundancy
+    [p, p]) of non-negative integer codes."""
+    return _joint_matrices(x_codes, y_codes, 0, np.log(2.0) if unit == "bit" else 1.0, want_matrix)
+
+
+def su_matrices(x_codes, y_codes, want_matrix=True):
+    """``_precompute_correlations_cpu`` (CFS.py:81-104) in float64: (r_cf [p], r_ff [p, p])."""
+    return _joint_matrices(x_codes, y_codes, 1, 1.0, want_matrix)
+
+
+def mrmr_codes(x, y):
+    """mRMR.fit's value coding (mRMR.py:90-92): index into the sorted union of all values of X and y."""
+    x = np.asarray(x)
+    y = np.asarray(y)
+    u = np.unique(np.concatenate([np.unique(x), np.unique(y)]))
+    return np.searchsorted(u, x).astype(np.int32), np.searchsorted(u, y).astype(np.int32), u
