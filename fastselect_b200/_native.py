@@ -13,8 +13,9 @@ import numpy as np
 FS_RELIEFF, FS_SURF, FS_MULTISURF = 0, 1, 2
 FS_U8, FS_I8, FS_F32, FS_F64 = 0, 1, 2, 3
 FS_ARITH_F32, FS_ARITH_F64 = 0, 1
+FS_JOINT_MI, FS_JOINT_SU = 0, 1
 FS_DISTINCT_CAP = 16
-FS_ABI_VERSION = 3
+FS_ABI_VERSION = 4
 
 _DTYPES = {np.dtype(np.uint8): FS_U8, np.dtype(np.int8): FS_I8,
            np.dtype(np.float32): FS_F32, np.dtype(np.float64): FS_F64}
@@ -66,6 +67,8 @@ def load():
     lib.fs_debug_rows.argtypes = [vp, C.c_int, C.c_int, i32, vp, vp, i64, vp, i64, vp, vp, vp, vp]
     lib.fs_dataset_peer_slab.argtypes = [vp, i64, vp, C.POINTER(vp)]
     lib.fs_dataset_set_peers.argtypes = [vp, i32, i32, vp, vp, vp, BARRIER_FN, vp]
+    lib.fs_joint_matrix.argtypes = [vp, C.c_int, C.c_double, vp, i64, i64, i64, vp, C.c_int, C.POINTER(FsStats)]
+    lib.fs_joint_tables.argtypes = [vp, vp, i64, vp, i64, vp]
     if lib.fs_abi_version() != FS_ABI_VERSION:
         raise RuntimeError(f"fastselect_b200: {LIB_PATH} has ABI version {lib.fs_abi_version()}, "
                            f"this package needs {FS_ABI_VERSION}; rebuild it (make -C fastselect_b200/csrc)")
@@ -220,6 +223,46 @@ class Dataset:
         if rc != 0:
             _raise(rc, "fs_score")
         return (out, stats.as_dict()) if want_stats else out
+
+    def joint_matrix(self, kind, log_base=1.0, feat_idx=None, pos_begin=0, pos_end=None, out_device_ptr=None,
+                     want_stats=False):
+        """Pairwise statistic (FS_JOINT_MI / FS_JOINT_SU) of the discrete columns ``feat_idx``: the
+        float64 ``[n_kept, n_kept]`` matrix restricted to the pairs whose smaller position lies in
+        ``[pos_begin, pos_end)`` (see include/fastselect_b200.h)."""
+        if feat_idx is not None:
+            feat_idx = np.ascontiguousarray(feat_idx, np.int64)
+            n_kept = feat_idx.size
+        else:
+            n_kept = self.p
+        pos_end = n_kept if pos_end is None else pos_end
+        stats = FsStats() if want_stats else None
+        out = None
+        if out_device_ptr is None:
+            out = np.empty((n_kept, n_kept), np.float64)
+            dst, on_dev = _ptr(out), 0
+        else:
+            dst, on_dev = C.c_void_p(out_device_ptr), 1
+        rc = load().fs_joint_matrix(self._h, int(kind), float(log_base), _ptr(feat_idx), n_kept, int(pos_begin),
+                                    int(pos_end), dst, on_dev, C.byref(stats) if stats is not None else None)
+        if rc != 0:
+            _raise(rc, "fs_joint_matrix")
+        return (out, stats.as_dict()) if want_stats else out
+
+    def joint_tables(self, pairs, feat_idx=None):
+        """Exact contingency tables of ``pairs`` (``[m, 2]`` positions in ``feat_idx``): int64
+        ``[m, 16, 16]``, entry ``[q, va, vb]`` counting the samples with the va-th smallest value of
+        the first column and the vb-th smallest value of the second."""
+        pairs = np.ascontiguousarray(pairs, np.int64).reshape(-1, 2)
+        if feat_idx is not None:
+            feat_idx = np.ascontiguousarray(feat_idx, np.int64)
+            n_kept = feat_idx.size
+        else:
+            n_kept = self.p
+        out = np.empty((pairs.shape[0], 16, 16), np.int64)
+        rc = load().fs_joint_tables(self._h, _ptr(feat_idx), n_kept, _ptr(pairs), pairs.shape[0], _ptr(out))
+        if rc != 0:
+            _raise(rc, "fs_joint_tables")
+        return out
 
     def debug_rows(self, algo, targets, use_star=False, k=0, class_probs=None, feat_idx=None):
         targets = np.ascontiguousarray(targets, np.int64)

@@ -33,6 +33,23 @@ def shard_starts(n: int, world_size: int, align: int = 1) -> list[int]:
     return [shard_rows(n, world_size, r, align)[0] for r in range(world_size)] + [n]
 
 
+def shard_triangle(q: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Row range ``[lo, hi)`` of rank ``rank`` when the strict upper triangle of a ``q x q`` pair
+    matrix is split into ``world_size`` contiguous row bands of (nearly) equal pair count: row c
+    holds ``q - 1 - c`` pairs (the joint-count path computes the pairs (c, g), g > c, of its rows)."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    work = np.arange(q - 1, -1, -1, dtype=np.int64)              # pairs in row c
+    cum = np.concatenate([[0], np.cumsum(work)])                 # pairs above row c
+    total = int(cum[-1])
+    cuts = [int(np.searchsorted(cum, total * r / world_size, side="left")) for r in range(world_size)] + [q]
+    cuts[0] = 0
+    cuts = [min(max(c, 0), q) for c in cuts]
+    for r in range(1, world_size + 1):                           # monotone
+        cuts[r] = max(cuts[r], cuts[r - 1])
+    return cuts[rank], cuts[rank + 1]
+
+
 def dist_info() -> tuple[int, int]:
     """(rank, world_size) of the initialised torch.distributed group, else (0, 1)."""
     try:
@@ -122,3 +139,27 @@ def score_sharded(n: int, n_kept: int, score_rows, device_buffers: bool, align: 
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)   # one NCCL allreduce over NVLink per fit
         return buf.cpu().numpy()
     return allreduce_sum_numpy(score_rows(lo, hi, None))
+
+
+def joint_sharded(q: int, compute_band, device_buffers: bool):
+    """Run ``compute_band(lo, hi, out_device_ptr)`` on this rank's row band of the ``q x q`` pair
+    matrix (:func:`shard_triangle`) and return the allreduced float64 matrix.  A band's matrix is
+    zero outside its own pairs, so the sum over ranks is the full matrix.
+
+    ``compute_band`` returns a float64 ``[q, q]`` numpy array when ``out_device_ptr`` is None and
+    writes the device buffer otherwise (fastselect_b200._native.Dataset.joint_matrix)."""
+    rank, world = dist_info()
+    if world == 1:
+        return compute_band(0, q, None)
+    import torch
+    import torch.distributed as dist
+
+    lo, hi = shard_triangle(q, world, rank)
+    if device_buffers:
+        buf = torch.empty((q, q), dtype=torch.float64, device="cuda")
+        compute_band(lo, hi, buf.data_ptr())
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)       # one NCCL allreduce over NVLink per matrix
+        return buf.cpu().numpy()
+    t = torch.from_numpy(np.ascontiguousarray(compute_band(lo, hi, None), np.float64))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.numpy()

@@ -276,6 +276,15 @@ struct fs_dataset {
     fs::DevBuf<int32_t> tie_flag, tie_order, tie_list;   // ReliefF reference tie order (select.cu)
     fs::DevBuf<float> tie_keys;
     fs::DevBuf<unsigned long long> counters;
+    // joint-count path (joint.cu)
+    bool no_dist_ops = false;     // build_workset: skip the distance operands (U / Wd / srow)
+    fs::DevBuf<double> joint_out;       // [n_kept, n_kept]
+    fs::DevBuf<int32_t> joint_marg;     // [K] marginal counts of the reduced one-hot rows
+    fs::DevBuf<int32_t> joint_zero;     // zeros: the s_i / s_j vector of the reused distance kernel
+    fs::DevBuf<int64_t> joint_ids;      // zeros: its row-id vector
+    fs::DevBuf<int32_t> joint_slab;     // [band rows, ldd] negated reduced joint counts of one band
+    fs::DevBuf<int32_t> joint_start;    // [n_kept + 1] first reduced row of every position
+    fs::DevBuf<int64_t> joint_pairs, joint_tables;
 };
 
 namespace fs {

@@ -408,7 +408,8 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
     if (ws.valid && ws.key == key && (ws.have_codes || !need_codes || ws.pt == 0)) {
         // same columns as the last call: the slab is either still there or recomputed in full
         const int mode = plan_dist(ds, ws.p_tcol.ptr, ws.pt, r0, R, slab_cacheable, ws.removed);
-        if (mode == kDistReuse || (ws.have_dist_ops && ws.u_lo <= want_lo && want_hi <= ws.u_hi) || ws.pt == 0) {
+        if (mode == kDistReuse || (ws.have_dist_ops && ws.u_lo <= want_lo && want_hi <= ws.u_hi) || ws.pt == 0 ||
+            ds->no_dist_ops) {               // joint-count path: only At is needed, and it is always built
             ws.dist_mode = mode == kDistReuse ? kDistReuse : kDistFull;
             return;
         }
@@ -530,7 +531,7 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
         Trace tr("  plan_dist");
         ws.dist_mode = plan_dist(ds, ws.p_tcol.ptr, ws.pt, r0, R, slab_cacheable, ws.removed);
     }
-    ws.have_dist_ops = ws.dist_mode == kDistFull;
+    ws.have_dist_ops = ws.dist_mode == kDistFull && !ds->no_dist_ops;
     ws.u_lo = want_lo;
     ws.u_hi = want_hi;
     if (ws.pt > 0) {

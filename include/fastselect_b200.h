@@ -32,7 +32,7 @@ extern "C" {
 #define FS_API
 #endif
 
-#define FS_ABI_VERSION 3
+#define FS_ABI_VERSION 4
 /* distinct values tracked per column by fs_dataset_create; a column with more
  * distinct values reports FS_DISTINCT_CAP + 1 */
 #define FS_DISTINCT_CAP 16
@@ -164,6 +164,39 @@ FS_API int fs_debug_rows(fs_dataset *ds, int algo, int use_star, int32_t k, cons
 FS_API int fs_dataset_peer_slab(fs_dataset *ds, int64_t rows, void *ipc_handle_out, void **dev_ptr_out);
 FS_API int fs_dataset_set_peers(fs_dataset *ds, int32_t rank, int32_t world, const int64_t *row_starts,
                          const void *ipc_handles, void *const *raw_ptrs, void (*barrier)(void *), void *barrier_ctx);
+
+/*
+ * Joint-count path: pairwise statistics of DISCRETE columns from their
+ * contingency tables.  The tables of all column pairs are one GEMM over the samples between the
+ * reduced one-hot rows of the columns (the operand the accumulation kernel already uses), run on
+ * the tensor cores with exact integer results; a finishing kernel rebuilds every pair's full table
+ * and folds it into the statistic.  Replaces _batch_mi_cpu / calculate_mi_matrices
+ * (mutual_information.py:49-63, :158-196 -- the reference computes the redundancy matrix on the
+ * CPU even with backend="gpu", :191-193) and _precompute_correlations_cpu / the one-thread-per-
+ * feature GPU kernel of CFS (CFS.py:81-104, :219-243).
+ *
+ * Every column in feat_idx (NULL = all p) must have been marked discrete in
+ * fs_dataset_set_features and hold at most FS_DISTINCT_CAP distinct values (FS_ERR_INVALID
+ * otherwise); a class vector takes part as one more column of X.  Sample order and y_enc of the
+ * data set are irrelevant here.
+ *
+ * fs_joint_matrix: out[a * n_kept + b] = statistic(feat_idx[a], feat_idx[b]) for the pairs with
+ *   pos_begin <= min(a, b) < pos_end (both triangles are written; everything else, and the
+ *   diagonal, is 0, as in mutual_information.py:53 / CFS.py:95), float64.  Ranks of a multi-GPU
+ *   job take disjoint position ranges and sum their matrices.
+ *   kind FS_JOINT_MI: sum p_xy ln(p_xy / (p_x p_y + 1e-12)) / log_base  (mutual_information.py:35-46)
+ *   kind FS_JOINT_SU: 2 I(x; y) / (H(x) + H(y)) in bits                  (CFS.py:26-77; the reference
+ *        keeps float32 intermediates there, this is the float64 value: |difference| < 1e-6)
+ *   out_on_device != 0: out is a device pointer on the data set's device.
+ * fs_joint_tables: the contingency tables themselves for m pairs of positions (pairs[2 * q],
+ *   pairs[2 * q + 1]), exact integers: tables_out[q * 256 + va * 16 + vb] = #samples with the va-th
+ *   smallest value of the first column and the vb-th smallest value of the second (host pointer).
+ */
+typedef enum { FS_JOINT_MI = 0, FS_JOINT_SU = 1 } fs_joint_kind;
+FS_API int fs_joint_matrix(fs_dataset *ds, int kind, double log_base, const int64_t *feat_idx, int64_t n_kept,
+                    int64_t pos_begin, int64_t pos_end, double *out, int out_on_device, fs_stats *stats);
+FS_API int fs_joint_tables(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, const int64_t *pairs, int64_t m,
+                    int64_t *tables_out);
 
 /* Internal order: perm_out[r] = original index of internal row r ([n]). */
 FS_API int fs_dataset_row_order(const fs_dataset *ds, int64_t *perm_out);
