@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- MultiSURF fit throughput (sample-pair*features/s) on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c2|c4]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c2|c4|c5|j1]
 
 A "step" is one pass of the scoring hot path (encode of the active columns, n x n
 distances, neighbour selection, weight accumulation, reduction) over one synthetic data
@@ -574,6 +574,194 @@ def turf_arm(args):
     if world > 1:
         dist.destroy_process_group()
 
+# --------------------------------------------------------------------------- #
+# joint-count path: --workload j1
+# --------------------------------------------------------------------------- #
+J_METRIC = "mi_matrices_sample_feature_pairs_per_s"
+J_UNIT = "samples*feature-pairs/s"
+
+
+def make_j1(n, p):
+    """J1: the matrices mRMR needs (relevance + p x p redundancy, mutual_information.py:158-196) on 0/1/2
+    genotypes with a binary class; unit of work = one sample of one unordered column pair of [X | y]."""
+    rs = np.random.RandomState(45)
+    x = rs.randint(0, 3, (n, p)).astype(np.uint8)
+    y = ((x[:, 25 % p] == 1) & (x[:, 75 % p] == 1)).astype(np.uint8) ^ (rs.random_sample(n) < 0.1).astype(np.uint8)
+    return {"n": n, "p": p, "x": x, "y": y,
+            "desc": f"J1: mutual-information matrices (mRMR) of {n} x {p} synthetic 0/1/2 genotypes + binary class"}
+
+
+def joint_cpu(x, y, threads):
+    """One timed pass of the oracle's MI matrices (the C restatement of _batch_mi_cpu, OpenMP over
+    features like the reference's prange) on [x | y]."""
+    from oracle import ref_oracle as R
+
+    R.set_threads(threads)
+    xi = np.ascontiguousarray(x, np.int32)
+    yi = np.ascontiguousarray(y, np.int32)
+    t0 = time.perf_counter()
+    R.mi_matrices(xi, yi)
+    return time.perf_counter() - t0
+
+
+def joint_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_oracle as R
+
+    R.build()
+    threads = os.cpu_count() or 1
+    n, p = args.n or 10_000, args.p or 10_000
+    n_s, p_s = min(n, 4000), min(p, 2000)
+    w = make_j1(n_s, p_s)
+    for _ in range(args.warmup):
+        joint_cpu(w["x"][:200, :100], w["y"][:200], threads)
+    t = sum(joint_cpu(w["x"], w["y"], threads) for _ in range(args.steps))
+    units = float(n_s) * (p_s + 1) * p_s / 2
+    value = args.steps * units / t
+    line = {"impl": "reference", "metric": J_METRIC, "value": value, "unit": J_UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 (CPU)",
+            "data": "synthetic", "config": {"workload": make_j1(4, 4)["desc"].replace("4 x 4", f"{n} x {p}"), "n": n, "p": p},
+            "cpu_baseline": {"value": value, "unit": J_UNIT, "cores": R.max_threads(), "kind": "port",
+                             "sample": f"{n_s} samples x {p_s} features per step"},
+            "e2e": {"value": value, "unit": J_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def joint_arm(args):
+    """--workload j1: one step = fs_joint_matrix over the resident data set (encode of every column,
+    marginals, the At * At^T GEMM bands, the finishing kernel; result left on the device);
+    e2e = mutual_information.calculate_mi_matrices from host buffers (upload, column scan, the step,
+    the p x p result copied back)."""
+    import torch
+    import torch.distributed as dist
+
+    import fastselect_b200 as fsb
+    from fastselect_b200 import _mi, _native
+    from fastselect_b200._shard import shard_triangle
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    _native.load()
+    if _native.device_count() < 1:
+        raise SystemExit("bench.py: no usable sm_100 GPU (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    os.environ["FASTSELECT_B200_DEVICE"] = str(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w = make_j1(args.n or 10_000, args.p or 10_000)
+    n, p = w["n"], w["p"]
+    q = p + 1
+    units = float(n) * q * (q - 1) / 2
+    xa = torch.from_numpy(_mi._stack_for_upload(w["x"], w["y"])).pin_memory().numpy()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    ds = _native.Dataset(xa, np.zeros(n, np.int32), 1)
+    ones8, ones32 = np.ones(q, np.uint8), np.ones(q, np.float32)
+    lo, hi = shard_triangle(q, world, rank)
+    buf = torch.empty((q, q), dtype=torch.float64, device="cuda")
+    agg = {}
+
+    def step():
+        ds.set_features(ones8, ones32, _native.FS_ARITH_F32)       # invalidates the working set: every step re-encodes
+        _, st = ds.joint_matrix(_native.FS_JOINT_MI, np.log(2.0), pos_begin=lo, pos_end=hi,
+                                out_device_ptr=buf.data_ptr(), want_stats=True)
+        if world > 1:
+            dist.all_reduce(buf)
+        for k_, v in st.items():
+            agg[k_] = agg.get(k_, 0) + v
+
+    for _ in range(args.warmup):
+        step()
+    agg.clear()
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    sampler.stop_flag.set()
+    tt = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    check = buf[p, :p].cpu().numpy()
+    ds.close()
+
+    # ---- end to end through the public API, from host buffers
+    x_in, y_in = w["x"], w["y"]
+    fsb.mutual_information.calculate_mi_matrices(x_in[:, :256], y_in, backend="gpu")
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rel, red = fsb.mutual_information.calculate_mi_matrices(x_in, y_in, backend="gpu")
+    barrier()
+    de = (time.perf_counter() - t0) / args.steps
+    tt = torch.tensor([de], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    de = float(tt.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    steps = args.steps
+    phases = {k_: agg.get(k_, 0.0) / steps for k_ in ("ms_gather", "ms_dist_tensor", "ms_reduce", "ms_total")}
+    ms_step = 1e3 * dt / steps
+    burst = ms_step < 100.0
+    bf16 = peaks.get("bf16_tflops" if burst else "bf16_tflops_sustained", 1590.0 if burst else 1400.0)
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    gemm = agg.get("ops_dist_tensor", 0.0) / steps / max(phases["ms_dist_tensor"], 1e-9) / 1e9     # TOP/s
+    # finishing kernel: reads the 4 reduced counts of every genotype pair once, writes both triangles
+    my_pairs = sum(q - 1 - c for c in range(lo, hi))
+    fin_bytes = my_pairs * (4.0 * 4 + 16.0)
+    fin = fin_bytes / max(phases["ms_reduce"], 1e-9) / 1e6                                          # GB/s
+    kernels = {
+        "ms_dist_tensor": {"bound": "tensor", "achieved": gemm, "peak": 4.0 * bf16, "unit": "TOP/s fp4 (e2m1, exact integers)",
+                           "frac": gemm / (4.0 * bf16), "traffic": None},
+        "ms_reduce": {"bound": "hbm", "achieved": fin, "peak": hbm, "unit": "GB/s", "frac": fin / hbm, "traffic": None,
+                      "note": "finishing kernel: 32 algorithmic bytes per column pair; also carries 9 float64 logarithms per pair"},
+    }
+    top = max(kernels, key=lambda k_: phases[k_])
+    line = {"metric": J_METRIC, "value": units * steps / dt, "unit": J_UNIT, "n_gpus": world, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "e2m1 (FP4) one-hot / exact FP32 counts / f64 statistic", "data": "synthetic",
+            "config": {"workload": w["desc"], "n": n, "p": p, "sharding": f"row bands of the pair matrix x{world}, one allreduce",
+                       "l2": "inputs and the count slab are larger than L2 (no flush needed)",
+                       "timing": "CUDA events on the launching stream around the K steps, max over ranks"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": units / de, "unit": J_UNIT, "h2d_bytes_per_step": int(xa.nbytes),
+                    "d2h_bytes_per_step": int(8 * q * q), "seconds_per_call": de,
+                    "matches_resident_run": bool(np.array_equal(rel, check))},
+            "gpu_launches": int(agg.get("launches", 0)), "roofline": dict(kernels[top], kernel=top),
+            "kernels": kernels, "phases_ms": phases, "bands": int(agg.get("n_chunks", 0) / steps),
+            "cpu_baseline": None}
+    n_s, p_s = min(n, 4000), min(p, 1500)
+    tc = joint_cpu(w["x"][:n_s, :p_s], w["y"][:n_s], os.cpu_count() or 1)
+    from oracle import ref_oracle as R
+    line["cpu_baseline"] = {"value": float(n_s) * (p_s + 1) * p_s / 2 / tc, "unit": J_UNIT, "cores": R.max_threads(),
+                            "kind": "port", "sample": f"first {n_s} samples x {p_s} features, one pass, {tc:.2f} s"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -581,12 +769,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5", "j1"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--n", type=int, default=None)
     ap.add_argument("--p", type=int, default=None)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl == "reference" and args.workload == "j1":
+        joint_reference_arm(args)
+    elif args.workload == "j1":
+        joint_arm(args)
+    elif args.impl == "reference":
         reference_arm(args)
     elif args.workload == "c5":
         turf_arm(args)
