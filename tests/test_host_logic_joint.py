@@ -185,3 +185,89 @@ def test_two_rank_gloo_band_sum_is_the_full_matrix(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
     assert "rank 0 ok" in outs[0] and "rank 1 ok" in outs[1]
+
+
+@pytest.fixture
+def oracle_backend(monkeypatch):
+    """The estimators' host glue without a GPU: the C-ABI call is replaced by the oracle (test only)."""
+    from oracle import ref_oracle as R
+
+    def fake_joint_matrix(codes, kind, log_base=1.0, stats_out=None):
+        codes = np.asarray(codes)
+        xc = np.stack([np.unique(codes[:, f], return_inverse=True)[1] for f in range(codes.shape[1])], axis=1)
+        q = xc.shape[1]
+        if kind == _native.FS_JOINT_MI:
+            vec, mat = R.mi_matrices(xc[:, :-1], xc[:, -1], unit="nat")
+            vec, mat = vec / log_base, mat / log_base
+        else:
+            vec, mat = R.su_matrices(xc[:, :-1], xc[:, -1])
+        full = np.zeros((q, q))
+        full[:q - 1, :q - 1] = mat
+        full[q - 1, :q - 1] = vec
+        full[:q - 1, q - 1] = vec
+        return full
+
+    monkeypatch.setattr(_mi, "joint_matrix", fake_joint_matrix)
+    monkeypatch.setattr(_native, "device_count", lambda: 1)
+
+
+@pytest.mark.parametrize("method", ["MID", "MIQ"])
+def test_mrmr_fit_glue_reproduces_the_reference(g, oracle_backend, method):
+    """tests/test_mrmr.py:53-101, :164-186 through fit / transform with the oracle as the backend."""
+    for data in ("mrmr_fixture", "mrmr_dup", "geno", "states"):
+        x, y = g[f"X_{data}"], g[f"y_{data}"]
+        ref = g[f"mrmr_top_{method}_{data}"]
+        est = fsb.mRMR(n_features_to_select=len(ref), method=method, backend="gpu").fit(x, y)
+        assert np.array_equal(est.top_features_, ref), (data, method)
+        np.testing.assert_allclose(est.relevance_scores_, g[f"mi_rel_bit_{data}"], rtol=1e-9, atol=1e-14)
+        np.testing.assert_allclose(est.redundancy_matrix_, g[f"mi_red_bit_{data}"], rtol=1e-9, atol=1e-14)
+        assert est.feature_importances_ is est.relevance_scores_ and est.n_features_in_ == x.shape[1]
+        assert np.array_equal(est.transform(x), x[:, ref])
+        assert np.array_equal(est.unique_vals_, np.unique(np.concatenate([np.unique(x), np.unique(y)])))
+    with pytest.raises(ValueError, match="n_features_to_select must be a positive integer"):
+        fsb.mRMR(n_features_to_select=x.shape[1] + 1, backend="gpu").fit(x, y)
+    with pytest.raises(ValueError, match=f"X has {x.shape[1] - 1} features, but mRMR is expecting {x.shape[1]} features"):
+        est.transform(x[:, 1:])
+    with pytest.raises(ValueError, match="integer-coded"):
+        fsb.mRMR(n_features_to_select=2, backend="gpu").fit(x.astype(float), y)
+
+
+def test_cfs_fit_glue_reproduces_the_reference(g, oracle_backend):
+    """tests/test_cfs.py:77-105, :126-175 through fit / transform with the oracle as the backend."""
+    import pandas as pd
+
+    for data in ("cfs_fixture", "geno", "states", "mrmr_fixture"):
+        x, y = g[f"X_{data}"], g[f"y_{data}"]
+        est = fsb.CFS(backend="gpu").fit(x, y)
+        assert np.array_equal(est.selected_indices_, g[f"cfs_sel_{data}"]), data
+        assert est.merit_ == pytest.approx(float(g[f"cfs_merit_{data}"][0]), rel=1e-5, abs=1e-6)
+        assert est.r_cf_.dtype == np.float32 and est.r_ff_.dtype == np.float32
+        np.testing.assert_allclose(est.r_cf_, g[f"cfs_rcf_{data}"], rtol=0, atol=1e-6)
+        assert np.array_equal(est.transform(x), x[:, g[f"cfs_sel_{data}"]])
+        assert np.array_equal(est.get_support(indices=True), g[f"cfs_sel_{data}"])
+    x, y = g["X_cfs_fixture"], g["y_cfs_fixture"]
+    df = pd.DataFrame(x, columns=[f"feature_{i}" for i in range(x.shape[1])])
+    est = fsb.CFS(backend="auto").fit(df, y)
+    assert list(est.feature_names_in_) == list(df.columns)
+    out = est.transform(df)
+    assert isinstance(out, pd.DataFrame) and list(out.columns) == ["feature_0", "feature_2"]
+    noise = fsb.CFS(backend="gpu").fit(x[:, 3:5], y)
+    assert len(noise.selected_indices_) == 0 and noise.merit_ == 0.0 and noise.transform(x[:, 3:5]).shape[1] == 0
+    single = fsb.CFS(backend="gpu").fit(x[:, [0]], y)
+    assert single.selected_indices_.tolist() == [0] and single.merit_ > 0
+    with pytest.raises(ValueError, match="up to 16 unique states/bins"):
+        fsb.CFS(backend="gpu", n_bins=20).fit(x, y)
+    with pytest.raises(ValueError, match="backend must be one of"):
+        fsb.CFS(backend="tpu").fit(x, y)
+
+
+def test_mi_function_glue(g, oracle_backend):
+    x, y = g["X_states"], g["y_states"]
+    mi = fsb.mutual_information
+    for unit in ("bit", "nat"):
+        rel, red = mi.calculate_mi_matrices(x, y, backend="auto", unit=unit)
+        np.testing.assert_allclose(rel, g[f"mi_rel_{unit}_states"], rtol=1e-9, atol=1e-14)
+        np.testing.assert_allclose(red, g[f"mi_red_{unit}_states"], rtol=1e-9, atol=1e-14)
+        assert red.flags["C_CONTIGUOUS"] and rel.shape == (x.shape[1],)
+    v = mi.calculate_mi_single_pair(x[:, 0], x[:, 1], backend="gpu", unit="bit")
+    assert v == pytest.approx(g["mi_red_bit_states"][0, 1], rel=1e-9, abs=1e-14)
