@@ -271,3 +271,33 @@ def test_mi_function_glue(g, oracle_backend):
         assert red.flags["C_CONTIGUOUS"] and rel.shape == (x.shape[1],)
     v = mi.calculate_mi_single_pair(x[:, 0], x[:, 1], backend="gpu", unit="bit")
     assert v == pytest.approx(g["mi_red_bit_states"][0, 1], rel=1e-9, abs=1e-14)
+
+
+def test_integration_stubs_bind_the_built_library(tmp_path):
+    """The reference-side ctypes stubs printed in INTEGRATION.md are real code: they load the built
+    library and call it with the documented argument lists.  Without a GPU every compute entry point
+    must come back with the library's 'no usable GPU' error (no crash, no fallback); with one, the stub
+    of the joint-count path reproduces the oracle."""
+    import re
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = [b for b in re.findall(r"```python\n(.*?)```", text, flags=re.S) if "_b200.py" in b.splitlines()[0]]
+    assert len(blocks) == 2
+    src = "\n".join(blocks).replace('C.CDLL("libfastselect_b200.so")', f"C.CDLL({_native.LIB_PATH!r})")
+    ns = {}
+    exec(compile(src, "INTEGRATION.md", "exec"), ns)
+    rs = np.random.RandomState(0)
+    x = rs.randint(0, 3, (40, 6)).astype(np.uint8)
+    y = rs.randint(0, 2, 40)
+    if not ns["available"]():
+        with pytest.raises(RuntimeError, match="no usable NVIDIA sm_100"):
+            ns["score"](x, y, 2, np.ones(6, bool), np.ones(6, np.float32), algo=2)
+        with pytest.raises(RuntimeError, match="no usable NVIDIA sm_100"):
+            ns["joint_matrix"](np.column_stack([x, y]), 0, np.log(2.0))
+        return
+    from oracle import ref_oracle as R
+
+    m = ns["joint_matrix"](np.column_stack([x, y]), 0, np.log(2.0))
+    rel, red = R.mi_matrices(x, y)
+    np.testing.assert_allclose(m[-1, :-1], rel, rtol=1e-11, atol=1e-15)
+    np.testing.assert_allclose(m[:-1, :-1], red, rtol=1e-11, atol=1e-15)
