@@ -613,7 +613,7 @@ def joint_reference_arm(args):
     R.build()
     threads = os.cpu_count() or 1
     n, p = args.n or 10_000, args.p or 10_000
-    n_s, p_s = min(n, 4000), min(p, 2000)
+    n_s, p_s = min(n, 10_000), min(p, 4000)       # ~4 s of CPU work per step on 16 threads
     w = make_j1(n_s, p_s)
     for _ in range(args.warmup):
         joint_cpu(w["x"][:200, :100], w["y"][:200], threads)
@@ -753,7 +753,7 @@ def joint_arm(args):
             "gpu_launches": int(agg.get("launches", 0)), "roofline": dict(kernels[top], kernel=top),
             "kernels": kernels, "phases_ms": phases, "bands": int(agg.get("n_chunks", 0) / steps),
             "cpu_baseline": None}
-    n_s, p_s = min(n, 4000), min(p, 1500)
+    n_s, p_s = min(n, 10_000), min(p, 6000)       # ~10 s of CPU work on 16 threads
     tc = joint_cpu(w["x"][:n_s, :p_s], w["y"][:n_s], os.cpu_count() or 1)
     from oracle import ref_oracle as R
     line["cpu_baseline"] = {"value": float(n_s) * (p_s + 1) * p_s / 2 / tc, "unit": J_UNIT, "cores": R.max_threads(),
