@@ -74,7 +74,7 @@ class _FakeNative:
 
 
 def test_full_size_test_bodies_run_clean_on_the_oracle():
-    import test_gpu_fullsize as T
+    import test_gpu_shapes_full as T
 
     T.run_c3(_FakeNative, 320, 500, 64, check_signal=False)
     T.run_c2(_FakeNative, 300, 400, 32)
