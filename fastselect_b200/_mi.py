@@ -266,12 +266,16 @@ def _best_first_search(r_cf, r_ff, min_r_cf=0.1):
 
 
 def _prune_redundant(selected, r_cf, r_ff):
-    """CFS.py:106-112: in descending r_cf order, drop a feature that is at least as correlated with
-    a kept feature as with the class."""
+    """Redundancy filter of CFS.py:106-112: visit the chosen features from the most to the least
+    class-correlated (stable, so equal correlations keep their index order) and keep one only if no
+    feature kept so far is at least as correlated with it as the class is."""
+    selected = np.asarray(selected, dtype=int)
+    order = selected[np.argsort(-r_cf[selected], kind="stable")]
     kept = []
-    for idx in sorted(selected, key=lambda i: -r_cf[i]):
-        if not any(r_ff[idx, j] >= r_cf[idx] for j in kept):
-            kept.append(idx)
+    for f in order.tolist():
+        if kept and bool((r_ff[f, kept] >= r_cf[f]).any()):
+            continue
+        kept.append(f)
     return kept
 
 
