@@ -174,6 +174,7 @@ struct WorkSet {
     int64_t K = 0;                  // K_used padded to 128
     int64_t K_used = 0;             // sum of (V_f - 1): reduced one-hot rows in use
     bool all_ident = false;         // every tensor column's value is its own code (one-byte input, values 0..V-1)
+    bool all_v3 = false;            // every tensor column has exactly 3 values (2 reduced rows): with all_ident, 0/1/2 genotypes
     DevBuf<int64_t> tcol, tout;     // [pt]
     DevBuf<int32_t> toff;           // [pt+1] first reduced one-hot row of each column
     PinnedBuf<int64_t> p_tcol, p_tout;   // host copies of tcol / tout / toff (pinned staging)

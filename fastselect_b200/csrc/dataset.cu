@@ -432,6 +432,7 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
     const uint8_t *info = ds->col_info.data();
     int64_t pt = 0, K = 0, first_const = -1, first_const_out = -1;
     unsigned ident = kColIdent;
+    bool v3 = true;
     for (int64_t c = 0; c < n_kept; ++c) {
         const int64_t f = all ? c : feat_idx[c];
         FS_REQUIRE(f >= 0 && f < ds->p, FS_ERR_INVALID, "feat_idx[%lld]=%lld outside [0,%lld)", (long long)c,
@@ -445,6 +446,7 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
                     toff[pt] = (int32_t)K;
                     K += ci >> 4;                  // V - 1 reduced one-hot rows
                     ident &= ci;
+                    v3 = v3 && (ci >> 4) == 2;
                     ++pt;
                 } else {
                     cmp_col.push_back(f);
@@ -480,6 +482,7 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
     ws.pt = pt;
     ws.K_used = K;
     ws.all_ident = (ident & kColIdent) != 0;
+    ws.all_v3 = v3 && pt > 0;
     ws.n_cont = (int64_t)cont_col.size();
     ws.n_cmp = (int64_t)cmp_col.size();
 

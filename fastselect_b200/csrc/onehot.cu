@@ -557,8 +557,10 @@ static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
     ws.p_roff.reserve(pr + 1);
     int64_t K = 0;
     unsigned ident = kColIdent;
+    bool v3 = true;
     for (int64_t c = 0; c < pr; ++c) {
         const unsigned ci = ds->col_info[ws.removed[c]];
+        v3 = v3 && (ci >> 4) == 2;
         ws.p_rcol.ptr[c] = ws.removed[c];
         ws.p_roff.ptr[c] = (int32_t)K;
         K += ci >> 4;
@@ -578,7 +580,9 @@ static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
     FS_CUDA(cudaMemcpyAsync(ws.roff.ptr, ws.p_roff.ptr, (pr + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     FS_CUDA(cudaMemsetAsync(ws.srow_r.ptr, 0, ws.ldt * sizeof(int32_t), st));
     const int all_ident = (ident & kColIdent) ? 1 : 0;
-    const bool lean = all_ident && ws.Kr_used == 2 * pr;
+    // the lean kernel hard-codes 0/1/2: EVERY column must have exactly three values (a mix of 2- and
+    // 4-valued columns can also add up to two reduced rows per column on average)
+    const bool lean = all_ident && v3 && pr > 0;
     if (!lean) {
         // general encoder ORs partial words in: clear everything
         FS_CUDA(cudaMemsetAsync(ws.Ur.ptr, 0, (size_t)n * Kb, st));
@@ -657,7 +661,9 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     // rows (columns n..ldt) is never read (the TMA maps are n bytes wide).
     if (ops) FS_CUDA(cudaMemsetAsync(ws.srow.ptr, 0, ws.ldt * sizeof(int32_t), st));
     const size_t Kb = (size_t)ws.K / 2;
-    const bool lean = ws.all_ident && ws.K_used == 2 * pt;
+    // the lean kernel hard-codes 0/1/2 genotypes: identity codes AND exactly three values in EVERY column
+    // (K_used == 2 * pt alone also holds for, say, one 2-valued plus one 4-valued column)
+    const bool lean = ws.all_ident && ws.all_v3;
     if (ops && !lean) {
         // the general encoder ORs the words at unaligned tile edges in: clear the operands first
         FS_CUDA(cudaMemsetAsync(ws.U.ptr, 0, (size_t)(ws.u_hi - ws.u_lo) * Kb, st));

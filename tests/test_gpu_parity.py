@@ -290,13 +290,26 @@ def test_symmetric_distances_across_emulated_ranks(native, starts):
             ds.close()
 
 
-def test_general_encode_path_matches_oracle(native):
+def _balanced_2_and_4_valued(seed, n, p):
+    """As many 2-valued as 4-valued byte columns and nothing else: two reduced one-hot rows per column ON
+    AVERAGE with identity value codes, which is not the 0/1/2 case the lean encoder hard-codes."""
+    rs = np.random.RandomState(seed)
+    x = np.empty((n, p), np.int8)
+    x[:, 0::2] = rs.randint(0, 2, x[:, 0::2].shape)
+    x[:, 1::2] = rs.randint(0, 4, x[:, 1::2].shape)
+    y = ((x[:, 1] >= 2) ^ (rs.random_sample(n) < 0.2)).astype(np.int64)
+    return x, y
+
+
+@pytest.mark.parametrize("make", [lambda: _mixed_cardinality_genotypes(38, 400, 333), lambda: _balanced_2_and_4_valued(39, 300, 128)],
+                         ids=["mixed", "balanced_2_4"])
+def test_general_encode_path_matches_oracle(native, make):
     """Columns with 2, 3 and 4 values and constants on the one-hot path (reduced planes of unequal
     width): distances, masks and weights against the oracle."""
-    x, y = _mixed_cardinality_genotypes(38, 400, 333)
+    x, y = make()
     xf = x.astype(np.float32)
     x32, recip, isd = R.multisurf_prep(xf, 10)
-    tg = np.arange(0, 400, 3)
+    tg = np.arange(0, x.shape[0], 3)
     with native.Dataset(x, y.astype(np.int32), 2) as ds:
         ds.set_features(isd, recip, native.FS_ARITH_F32)
         got = ds.debug_rows(native.FS_MULTISURF, tg, use_star=True)
