@@ -13,7 +13,7 @@ import numpy as np
 from sklearn.base import BaseEstimator, TransformerMixin, clone
 from sklearn.utils.validation import check_is_fitted, validate_data
 
-from ._relief import _ReliefBase
+from ._relief import _ReliefBase, _validate_n_select
 
 
 class TuRF(TransformerMixin, BaseEstimator):
@@ -95,7 +95,18 @@ class TuRF(TransformerMixin, BaseEstimator):
             return self._prune(base_estimator.feature_importances_,
                                lambda active: np.zeros(len(active), dtype=np.float32))
         with session:
-            return self._prune(session.score(), session.score)
+            return self._prune(session.score(), self._checked_scorer(session, base_estimator))
+
+    @staticmethod
+    def _checked_scorer(session, base_estimator):
+        """Scores a column subset of the resident data set after the check the reference's per-iteration
+        ``base_estimator.fit(X[:, active], y)`` (TuRF.py:110-111) would have made: an integer
+        ``n_features_to_select`` of the base estimator larger than the remaining columns is an error."""
+        def score_active(active):
+            _validate_n_select(base_estimator.n_features_to_select, len(active))
+            return session.score(active)
+
+        return score_active
 
     def transform(self, X):
         check_is_fitted(self)

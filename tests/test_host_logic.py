@@ -267,3 +267,20 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0 and line["vs_baseline"] is None
+
+
+def test_turf_resident_scoring_keeps_the_base_estimators_validation():
+    """The reference re-fits the base estimator on X[:, active] every iteration (TuRF.py:110-111), so an
+    integer n_features_to_select of the BASE estimator above the remaining column count raises there;
+    the resident path makes the same check before scoring a subset."""
+    from fastselect_b200._turf import TuRF
+
+    class FakeSession:
+        def score(self, active=None):
+            return np.zeros(5 if active is None else len(active), np.float32)
+
+    scorer = TuRF._checked_scorer(FakeSession(), fsb.MultiSURF(n_features_to_select=4))
+    assert scorer(np.arange(4)).shape == (4,)
+    with pytest.raises(ValueError, match="must be > 0 and <= n_features"):
+        scorer(np.arange(3))
+    assert TuRF._checked_scorer(FakeSession(), fsb.MultiSURF(n_features_to_select=0.2))(np.arange(2)).shape == (2,)
