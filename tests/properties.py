@@ -22,14 +22,16 @@ def check_distance_rows(out, targets, p, integer):
         np.testing.assert_allclose(sub, sub.T, rtol=1e-12, atol=1e-12)
 
 
-def check_multisurf_rows(out, y, targets, use_star):
+def check_multisurf_rows(out, y, targets, use_star, tol=1e-12):
     """MultiSURF.py:175-251: T_i = mean - std / 2 over j != i; near = d < T_i (strict); far misses only
     with use_star; sum_f W_i[f] = (sum_near_miss d - [star] sum_far_miss d) / nM - sum_near_hit d / nH
-    (a division is skipped when its count is 0) -- the accumulation checked against the distances."""
+    (a division is skipped when its count is 0) -- the accumulation checked against the distances.
+    ``tol`` is relative to the size of the two terms being subtracted (they nearly cancel): 1e-12 where
+    every step is exact or float64, ~5e-6 where weights are accumulated from float32 partial sums."""
     d, thresh, mask = out["dist"], out["thresh"], out["mask"]
     n = d.shape[1]
     y = np.asarray(y)
-    checksum = 0.0
+    checksum = scale = 0.0
     for r, i in enumerate(targets):
         others = np.arange(n) != i
         row = d[r]
@@ -46,8 +48,11 @@ def check_multisurf_rows(out, y, targets, use_star):
         assert np.array_equal(mask[r], want), int(i)
         n_h, n_m = int((want == 1).sum()), int((want == 2).sum())
         miss = row[want == 2].sum() - row[want == 3].sum()
-        checksum += (miss / n_m if n_m else miss) - (row[want == 1].sum() / n_h if n_h else 0.0)
-    np.testing.assert_allclose(out["wsum"].sum(), checksum, rtol=1e-9, atol=1e-9)
+        m_term = miss / n_m if n_m else miss
+        h_term = row[want == 1].sum() / n_h if n_h else 0.0
+        checksum += m_term - h_term
+        scale += (row[want == 2].sum() + row[want == 3].sum()) / max(n_m, 1) + abs(h_term)
+    assert abs(out["wsum"].sum() - checksum) <= tol * max(scale, 1.0), (out["wsum"].sum(), checksum, scale)
 
 
 def check_relieff_rows(out, y_enc, class_probs, targets, k):

@@ -53,6 +53,53 @@ def test_c3_full_shape_multisurf_genotypes(native):
     run_c3(native, 4000, 100_000, 256)
 
 
+def make_c4(n, p):
+    """half 0/1/2 genotype columns, half float32 Gaussians, the epistatic label of C3
+    plus a shifted continuous column -- generated in column blocks to keep the temporaries small."""
+    rs = np.random.RandomState(43)
+    h = p // 2
+    x = np.empty((n, p), np.float32)
+    x[:, :h] = rs.randint(0, 3, (n, h), dtype=np.int8)
+    for c0 in range(h, p, 2500):
+        c1 = min(p, c0 + 2500)
+        x[:, c0:c1] = rs.standard_normal((n, c1 - c0))
+    y = np.zeros(n, np.int64)
+    y[(x[:, 25 % h] == 1) & (x[:, 75 % h] == 1)] = 1
+    need = n // 2 - int(y.sum())
+    if need > 0:
+        y[rs.choice(np.flatnonzero(y == 0), need, replace=False)] = 1
+    x[:, h] += 1.0 * y
+    return x, y
+
+
+def run_c4(native, n, p, n_targets, check_signal=True):
+    x, y = make_c4(n, p)
+    h = p // 2
+    # MultiSURF.fit's preprocessing (MultiSURF.py:409-420) without the per-column sort: ranges from the
+    # float32 matrix, zero -> 1; the genotype half is discrete (3 values), the Gaussian half is not
+    ranges = (x.max(axis=0) - x.min(axis=0)).astype(np.float32)
+    ranges[ranges == 0] = 1
+    recip = (1.0 / ranges).astype(np.float32)
+    isd = np.arange(p) < h
+    rs = np.random.RandomState(1)
+    tg = np.sort(rs.choice(n, n_targets, replace=False))
+    sub = tg[::8]
+    with native.Dataset(x, y.astype(np.int32), 2) as ds:
+        ds.set_features(isd, recip, native.FS_ARITH_F32)
+        full = ds.score(native.FS_MULTISURF, use_star=True)
+        got = ds.debug_rows(native.FS_MULTISURF, tg, use_star=True)
+        got8 = ds.debug_rows(native.FS_MULTISURF, sub, use_star=True)
+    if check_signal:
+        assert int(np.argmax(full)) == h                      # the shifted continuous column
+    check_distance_rows(got, tg, p, integer=False)
+    check_multisurf_rows(got, y, tg, use_star=True, tol=5e-6)
+    want = R.multisurf_targets(x, y, recip, isd, True, sub)
+    np.testing.assert_allclose(got8["dist"], want["dist"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(got8["thresh"], want["thresh"], rtol=1e-13)
+    assert np.array_equal(got8["mask"], want["mask"])
+    np.testing.assert_allclose(got8["wsum"], want["wsum"], rtol=RTOL, atol=atol_for(want["wsum"]) * len(sub))
+
+
 def run_c2(native, n, p, n_targets, k=10):
     rs = np.random.RandomState(7)
     y = rs.randint(0, 2, n)
@@ -86,3 +133,8 @@ def test_c2_full_shape_relieff_continuous(native):
     """C2's shape: ReliefF (k = 10) on 10 000 x 10 000 continuous columns (seeded Gaussians with two
     shifted columns instead of make_classification: the property is shape-, not data-specific)."""
     run_c2(native, 10_000, 10_000, 64)
+
+
+def test_c4_full_shape_multisurf_star_mixed(native):
+    """C4: MultiSURF* on 20 000 x 50 000 mixed columns (25 000 genotype + 25 000 float32 Gaussian)."""
+    run_c4(native, 20_000, 50_000, 64)
