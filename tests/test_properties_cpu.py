@@ -78,4 +78,4 @@ def test_full_size_test_bodies_run_clean_on_the_oracle():
 
     T.run_c3(_FakeNative, 320, 500, 64, check_signal=False)
     T.run_c2(_FakeNative, 300, 400, 32)
-    T.run_c4(_FakeNative, 240, 300, 32, check_signal=False)
+    T.run_c4(_FakeNative, 240, 300, 32)
