@@ -93,8 +93,10 @@ def run_c4(native, n, p, n_targets):
     check_distance_rows(got, tg, p, integer=False)
     check_multisurf_rows(got, y, tg, use_star=True, tol=5e-6)
     want = R.multisurf_targets(x, y, recip, isd, True, sub)
-    np.testing.assert_allclose(got8["dist"], want["dist"], rtol=1e-13, atol=1e-13)
-    np.testing.assert_allclose(got8["thresh"], want["thresh"], rtol=1e-13)
+    # float64 sums of 50 000 terms in two different orders; the threshold amplifies the difference by
+    # mean^2 / variance (~1e5 at this width) through the cancellation in sum d^2 / (n - 1) - mean^2
+    np.testing.assert_allclose(got8["dist"], want["dist"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(got8["thresh"], want["thresh"], rtol=1e-9)
     assert np.array_equal(got8["mask"], want["mask"])
     np.testing.assert_allclose(got8["wsum"], want["wsum"], rtol=RTOL, atol=atol_for(want["wsum"]) * len(sub))
 
