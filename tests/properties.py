@@ -19,7 +19,7 @@ def check_distance_rows(out, targets, p, integer):
     if integer:
         assert np.array_equal(sub, sub.T)
     else:
-        np.testing.assert_allclose(sub, sub.T, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(sub, sub.T, rtol=2e-7, atol=1e-12)     # ReliefF / SURF rows are float32-rounded sums
 
 
 def check_multisurf_rows(out, y, targets, use_star, tol=1e-12):
