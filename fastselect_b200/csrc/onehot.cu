@@ -25,7 +25,7 @@ void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_
                     const DistPeers &peers, cudaStream_t st, int *launches, double *ops);
 int tc_accum_tile_desc_ints();
 int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
-                    int64_t R, const int64_t *d_ids, bool contiguous, const RowInfo *rinfo, const uint8_t *codesT,
+                    int64_t R, const int64_t *d_ids, bool contiguous, bool paired, const RowInfo *rinfo, const uint8_t *codesT,
                     int64_t ldt, const uint32_t *krow, int64_t K_rows, DevBuf<double> &tpartial, int32_t *d_tiles,
                     DevBuf<int32_t> &consts, cudaStream_t st, int *launches, const int64_t *h_ids, const int32_t *h_y,
                     const int64_t *h_cls_start, double *ops);
@@ -858,7 +858,8 @@ void launch_accum_tensor(fs_dataset *ds, const WorkSet &ws, int algo, const int6
     const CUtensorMap tat = make_tmap_u8_sw128(ws.At.ptr, row_bytes, (uint64_t)ws.K, (uint64_t)(ws.ldt / 2), 128);
     const CUtensorMap tmh = make_tmap_u8_sw128(ds->maskH.ptr, row_bytes, (uint64_t)R, (uint64_t)(ldn / 2), 240);
     const CUtensorMap tmm = make_tmap_u8_sw128(ds->maskM.ptr, row_bytes, (uint64_t)R, (uint64_t)(ldn / 2), 240);
-    const int parts = launch_tc_accum(tat, tmh, tmm, n, R, d_row_ids, contiguous, rinfo, ws.codesT.ptr, ws.ldt,
+    // every column with exactly three values: one-hot rows 2c, 2c + 1 are column c's two planes (paired epilogue)
+    const int parts = launch_tc_accum(tat, tmh, tmm, n, R, d_row_ids, contiguous, ws.all_v3, rinfo, ws.codesT.ptr, ws.ldt,
                                       ws.krow.ptr, ws.K_used, ds->tpartial, ds->tile_desc.ptr, ds->tile_consts, st, launches,
                                       h_row_ids, ds->y_sorted.data(), ds->cls_start.data(), ops);
     reduce_tensor_partials_kernel<<<(unsigned)ceil_div(ws.pt, 256), 256, 0, st>>>(ds->tpartial.ptr, parts, ws.K_used,

@@ -101,7 +101,7 @@ __device__ __forceinline__ int2 coef_limbs(double c) {
 // (broadcast) loads instead of staging them through shared memory behind a barrier per item.
 __global__ void __launch_bounds__(256) accum_consts_kernel(const TileDesc *__restrict__ tiles, int num_tiles,
                                                            const RowInfo *__restrict__ rinfo, int2 *__restrict__ limbs,
-                                                           int32_t *__restrict__ rsum) {
+                                                           int32_t *__restrict__ rsum, int rsum_as_float) {
     const int t = blockIdx.x >> 1, phase = blockIdx.x & 1, e = threadIdx.x;
     if (t >= num_tiles) return;
     const TileDesc d = tiles[t];
@@ -113,9 +113,16 @@ __global__ void __launch_bounds__(256) accum_consts_kernel(const TileDesc *__res
         rs = phase == 0 ? ri.n_hit - ri.n_far_hit : ri.n_miss - ri.n_far_miss;
     }
     limbs[(size_t)blockIdx.x * 256 + e] = coef_limbs(c);
-    rsum[(size_t)blockIdx.x * 256 + e] = rs;
+    // the paired epilogue works on the FP32 accumulators directly: |rs| <= n < 2^22 is exact in float
+    rsum[(size_t)blockIdx.x * 256 + e] = rsum_as_float ? __float_as_int((float)rs) : rs;
 }
 
+// kPair: every active column has exactly three values, so one-hot rows 2c and 2c + 1 (two adjacent
+// TMEM lanes = two adjacent threads of an epilogue warp) are the two reduced planes of column c.  Per
+// (column, target) only ONE of rs - G0, rs - G1, G0 + G1 is needed, times the coefficient once: the two
+// threads swap accumulators with one shuffle and each finishes half of the targets, instead of each
+// paying the whole select / convert / scale sequence for every target of its own plane.
+template <bool kPair>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_constant__ CUtensorMap tmap_mh,
                 const __grid_constant__ CUtensorMap tmap_mm, int num_k_blocks, int64_t R,
@@ -247,7 +254,7 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         const int et = q * 32 + lane;                         // 0..127: TMEM lane / local one-hot row
-        const int ethread = (warp - 2) * 32 + lane;           // 0..EPI_THREADS-1
+        const uint32_t parity = (uint32_t)lane & 1u;          // kPair: plane of this one-hot row (row 2c + parity)
         const int64_t ids0 = contiguous ? ids[0] : 0;
         int item = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -260,14 +267,51 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
             const uint8_t *at_row = codesT + (int64_t)(meta & 0xffffffu) * ldt;
             const uint32_t own4 = ((meta >> 24) & 0xfu) * 0x01010101u;
             const uint32_t last4 = (meta >> 28) * 0x01010101u;
+            const uint32_t oth4 = own4 ^ 0x01010101u;            // kPair: the partner lane's plane (codes 0 <-> 1)
             long long ah0 = 0, ah1 = 0, al0 = 0, al1 = 0;     // exact fixed-point sums (two chains)
             for (int t = g * group_tiles; t < tile_end; ++t) {
                 const TileDesc d = s_tiles[t];
                 // value codes of this thread's 128 targets in its column (issued before the
                 // accumulator wait so the loads overlap the MMAs); shared by both phases.
                 // Targets beyond the tile's rows get whatever follows: their coefficient is 0.
-                uint32_t oh[HALF / 4];
-                {
+                // kPair: only the targets this thread finishes -- of every 16-target chunk the even lane
+                // takes targets 0..7, the odd lane 8..15 -- i.e. two words per chunk.
+                uint32_t oh[kPair ? HALF / 8 : HALF / 4];
+                if constexpr (kPair) {
+                    const int64_t rbase = (int64_t)d.row0 + half * HALF + 8 * (int)parity;
+                    if (contiguous) {
+                        const int64_t id0 = ids0 + rbase;
+                        if ((id0 & 7) == 0) {
+#pragma unroll
+                            for (int j = 0; j < HALF / 16; ++j) {
+                                const uint2 a = *reinterpret_cast<const uint2 *>(at_row + id0 + 16 * j);
+                                oh[2 * j] = a.x; oh[2 * j + 1] = a.y;
+                            }
+                        } else {
+                            // unaligned start (class-aligned tiles): aligned words + funnel shift
+                            const uint32_t *src = reinterpret_cast<const uint32_t *>(at_row + (id0 & ~(int64_t)3));
+                            const uint32_t sh = (uint32_t)(id0 & 3) * 8u;
+#pragma unroll
+                            for (int j = 0; j < HALF / 16; ++j) {
+                                const uint32_t w0 = src[4 * j], w1 = src[4 * j + 1], w2 = src[4 * j + 2];
+                                oh[2 * j] = __funnelshift_r(w0, w1, sh);
+                                oh[2 * j + 1] = __funnelshift_r(w1, w2, sh);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < HALF / 8; ++w) {
+                            uint32_t x = 0;
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                const int64_t r = rbase + (w >> 1) * 16 + (w & 1) * 4 + b;
+                                const uint32_t byte = r < R ? (uint32_t)at_row[ids[r]] : 0xffu;
+                                x |= byte << (8 * b);
+                            }
+                            oh[w] = x;
+                        }
+                    }
+                } else {
                     const int64_t rbase = (int64_t)d.row0 + half * HALF;
                     if (contiguous) {
                         const int64_t id0 = ids0 + rbase;
@@ -321,6 +365,44 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                         uint32_t v[16];                    // FP32 accumulators holding exact integers
                         tc::tmem_ld_32x16(tacc + c0, v);
                         tc::tmem_ld_wait();
+                        if constexpr (kPair) {
+                            // even lane (plane 0) finishes targets c0 .. c0+7, odd lane (plane 1) c0+8 .. c0+15:
+                            // each sends the partner the accumulators of the partner's targets
+                            uint32_t mine[8], oth[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const uint32_t snd = parity ? v[e] : v[8 + e];
+                                mine[e] = parity ? v[8 + e] : v[e];
+                                oth[e] = __shfl_xor_sync(0xffffffffu, snd, 1);
+                            }
+                            const int4 *cc = reinterpret_cast<const int4 *>(s_c + half * HALF + c0 + 8 * (int)parity);
+                            const float4 *rr = reinterpret_cast<const float4 *>(s_rs + half * HALF + c0 + 8 * (int)parity);
+#pragma unroll
+                            for (int e = 0; e < 8; e += 4) {
+                                const uint32_t w = oh[(c0 >> 3) + (e >> 2)];
+                                // own: the target carries this lane's plane; otr: the partner's plane; else the last value
+                                const uint32_t own = __vcmpeq4(w, own4), otr = __vcmpeq4(w, oth4);
+                                const float4 rs4 = __ldg(rr + (e >> 2));
+                                const int4 ca = __ldg(cc + (e >> 1)), cb = __ldg(cc + (e >> 1) + 1);
+                                const float rsv[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
+                                int tt[4];
+#pragma unroll
+                                for (int b = 0; b < 4; ++b) {
+                                    const float gm = __uint_as_float(mine[e + b]), go = __uint_as_float(oth[e + b]);
+                                    // t = rs - G_code for codes 0 / 1, G_0 + G_1 (= rs - G_last) for the last code: exact in
+                                    // FP32; branch-free select through the 0x00 / 0xff compare bytes widened to word masks
+                                    const uint32_t mo = tc::byte_mask(own, b), mt = tc::byte_mask(otr, b);
+                                    const uint32_t ta = __float_as_uint(rsv[b] - gm), tb = __float_as_uint(rsv[b] - go);
+                                    const uint32_t tl = __float_as_uint(gm + go);
+                                    const uint32_t t1 = (ta & mo) | (tl & ~mo);
+                                    tt[b] = tc::f32_to_int_exact((tb & mt) | (t1 & ~mt));
+                                }
+                                ah0 += (long long)tt[0] * ca.x; al0 += (long long)tt[0] * ca.y;
+                                ah1 += (long long)tt[1] * ca.z; al1 += (long long)tt[1] * ca.w;
+                                ah0 += (long long)tt[2] * cb.x; al0 += (long long)tt[2] * cb.y;
+                                ah1 += (long long)tt[3] * cb.z; al1 += (long long)tt[3] * cb.w;
+                            }
+                        } else {
                         const int4 *cc = reinterpret_cast<const int4 *>(s_c + half * HALF + c0);
                         const int4 *rr = reinterpret_cast<const int4 *>(s_rs + half * HALF + c0);
 #pragma unroll
@@ -340,6 +422,7 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                             ah1 += (long long)t1 * ca.z; al1 += (long long)t1 * ca.w;
                             ah0 += (long long)t2 * cb.x; al0 += (long long)t2 * cb.y;
                             ah1 += (long long)t3 * cb.z; al1 += (long long)t3 * cb.w;
+                        }
                         }
                     }
                     tc::tc_fence_before();
@@ -405,11 +488,15 @@ static AccumPlan make_plan(int64_t n, int64_t R, bool contiguous, const int64_t 
 
 // Returns the number of partial vectors written ([groups x PARTS][K_rows] doubles).
 int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
-                    int64_t R, const int64_t *d_ids, bool contiguous, const RowInfo *rinfo, const uint8_t *codesT,
+                    int64_t R, const int64_t *d_ids, bool contiguous, bool paired, const RowInfo *rinfo, const uint8_t *codesT,
                     int64_t ldt, const uint32_t *krow, int64_t K_rows, DevBuf<double> &tpartial, int32_t *d_tiles,
                     DevBuf<int32_t> &consts, cudaStream_t st, int *launches, const int64_t *h_ids, const int32_t *h_y,
                     const int64_t *h_cls_start, double *ops) {
-    FS_CUDA(cudaFuncSetAttribute(tc_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    // paired epilogue: every column owns exactly two one-hot rows (2c, 2c + 1), see the kernel
+    const char *env_pair = getenv("FS_B200_ACCUM_PAIR");
+    if (env_pair && env_pair[0] == '0') paired = false;
+    auto kernel = paired ? tc_accum_kernel<true> : tc_accum_kernel<false>;
+    FS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int dev = 0, sms = 0;
     FS_CUDA(cudaGetDevice(&dev));
     FS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -443,11 +530,11 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
         consts.reserve((size_t)nt * 2 * 256 * 3);
         int2 *limbs = reinterpret_cast<int2 *>(consts.ptr);
         int32_t *rsum = consts.ptr + (size_t)nt * 2 * 256 * 2;
-        accum_consts_kernel<<<2 * nt, 256, 0, st>>>(reinterpret_cast<const TileDesc *>(d_tiles), nt, rinfo, limbs, rsum);
+        accum_consts_kernel<<<2 * nt, 256, 0, st>>>(reinterpret_cast<const TileDesc *>(d_tiles), nt, rinfo, limbs, rsum, paired ? 1 : 0);
         ++*launches;
         const int units = m_blocks * groups;
         const int grid = units < sms ? units : sms;
-        tc_accum_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(
+        kernel<<<grid, THREADS, SMEM_BYTES, st>>>(
             tmap_at, tmap_mh, tmap_mm, (int)ceil_div(n, KS), R, reinterpret_cast<const TileDesc *>(d_tiles), nt,
             groups, group_tiles, m_blocks, d_ids, contiguous ? 1 : 0, limbs, rsum, codesT, ldt, krow, K_rows,
             tpartial.ptr + (size_t)groups_done * PARTS * K_rows);

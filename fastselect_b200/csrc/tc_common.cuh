@@ -136,6 +136,13 @@ __device__ __forceinline__ int f32_to_int_exact(uint32_t bits) {
     return __float_as_int(__uint_as_float(bits) + 12582912.0f) - 0x4B400000;
 }
 
+// 0xffffffff when byte b of x has its top bit set, else 0 (prmt sign-replicate mode; b is a constant)
+__device__ __forceinline__ uint32_t byte_mask(uint32_t x, int b) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, %2;" : "=r"(r) : "r"(x), "r"(0x8888u + 0x1111u * (uint32_t)b));
+    return r;
+}
+
 // ------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of
 // exactly 128 bytes (one swizzle atom wide): 8-row groups are 1024 B apart (SBO);

@@ -232,6 +232,98 @@ FSO_API int fso_multisurf_targets(const float *x, int64_t n, int64_t p, const in
     return 0;
 }
 
+/*
+ * The same per-target computation for a matrix of one-byte genotype codes in which
+ * EVERY column is discrete (MultiSURF.py:184-185: diff = [a != b]) -- the form the
+ * reference's float32 kernel takes on such data, restated on the bytes so that the
+ * full-width benchmark shapes (20 000 x 500 000 int8 = 10 GB; 40 GB as float32)
+ * fit in host memory.  cols (nullable) restricts the computation to a column
+ * subset, as TuRF's X[:, active] does (TuRF.py:110).  Distances and neighbour
+ * counts are exact integers; the per-feature sums are integer counts divided once
+ * (float64), i.e. the out64 arithmetic of multisurf_target.  Pinned against
+ * multisurf_target on the genotype fixtures by tests/test_oracle_golden.py.
+ */
+static void multisurf_target_u8(const uint8_t *x, int64_t n, int64_t ld, const int64_t *cols, int64_t p,
+                                const int64_t *y, int use_star, int64_t i, double *out64,
+                                double *thresh_out, int8_t *mask_row, double *dist_row) {
+    const uint8_t *xi = x + i * ld;
+    uint8_t *ti = NULL;          /* target row restricted to cols */
+    if (cols) {
+        ti = malloc((size_t)p);
+        for (int64_t f = 0; f < p; ++f) ti[f] = xi[cols[f]];
+    }
+    int32_t *drow = malloc((size_t)n * sizeof(int32_t));
+    /* pass 1: MultiSURF.py:175-196 */
+    double sum_d = 0.0, sum_d2 = 0.0;
+    for (int64_t j = 0; j < n; ++j) {
+        const uint8_t *xj = x + j * ld;
+        int32_t d = 0;
+        if (cols) for (int64_t f = 0; f < p; ++f) d += ti[f] != xj[cols[f]];
+        else for (int64_t f = 0; f < p; ++f) d += xi[f] != xj[f];
+        drow[j] = d;
+        if (j == i) continue;
+        sum_d += (double)d;
+        sum_d2 += (double)d * (double)d;
+    }
+    double inv = 1.0 / (double)(n - 1);
+    double mu = sum_d * inv;
+    double var = fma(sum_d2, inv, -(mu * mu));
+    if (!(var > 0.0)) var = 0.0;
+    double thresh = mu - 0.5 * sqrt(var);
+    if (thresh_out) *thresh_out = thresh;
+    int32_t *h = calloc((size_t)p, sizeof(int32_t)), *m = calloc((size_t)p, sizeof(int32_t));
+    int64_t n_hits = 0, n_miss = 0;
+    /* pass 2: MultiSURF.py:203-243 */
+    for (int64_t j = 0; j < n; ++j) {
+        if (mask_row) mask_row[j] = FSO_NONE;
+        if (dist_row) dist_row[j] = 0.0;
+        if (j == i) continue;
+        const uint8_t *xj = x + j * ld;
+        double d = (double)drow[j];
+        if (dist_row) dist_row[j] = d;
+        int is_hit = (y[i] == y[j]);
+        int code = FSO_NONE;
+        if (d < thresh) code = is_hit ? FSO_NEAR_HIT : FSO_NEAR_MISS;
+        else if (use_star && !is_hit) code = FSO_FAR_MISS;
+        if (mask_row) mask_row[j] = (int8_t)code;
+        if (code == FSO_NONE) continue;
+        if (code == FSO_NEAR_HIT) n_hits++;
+        else if (code == FSO_NEAR_MISS) n_miss++;
+        int32_t *acc = code == FSO_NEAR_HIT ? h : m;
+        const int32_t sgn = code == FSO_FAR_MISS ? -1 : 1;
+        if (cols) for (int64_t f = 0; f < p; ++f) acc[f] += sgn * (int32_t)(ti[f] != xj[cols[f]]);
+        else for (int64_t f = 0; f < p; ++f) acc[f] += sgn * (int32_t)(xi[f] != xj[f]);
+    }
+    for (int64_t f = 0; f < p; ++f) {      /* MultiSURF.py:245-251 */
+        double hh = (double)h[f], mm = (double)m[f];
+        if (n_hits > 0) hh /= (double)n_hits;
+        if (n_miss > 0) mm /= (double)n_miss;
+        out64[f] = mm - hh;
+    }
+    free(h); free(m); free(drow); free(ti);
+}
+
+/* x: n rows of ld bytes (uint8 or int8 codes: only equality is used). */
+FSO_API int fso_multisurf_targets_u8(const uint8_t *x, int64_t n, int64_t ld, const int64_t *cols, int64_t p,
+                                     const int64_t *y, int use_star, const int64_t *targets, int64_t nt,
+                                     double *wsum_out, double *thresh_out, int8_t *mask_out, double *dist_out) {
+    if (n < 2 || p < 1) return -1;
+    double *rows = malloc((size_t)nt * p * sizeof(double));
+    if (!rows) return -2;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t t = 0; t < nt; ++t)
+        multisurf_target_u8(x, n, ld, cols, p, y, use_star, targets[t], rows + t * p,
+                            thresh_out ? thresh_out + t : NULL, mask_out ? mask_out + t * n : NULL,
+                            dist_out ? dist_out + t * n : NULL);
+    for (int64_t f = 0; f < p; ++f) {
+        double s = 0.0;
+        for (int64_t t = 0; t < nt; ++t) s += rows[t * p + f];
+        wsum_out[f] = s;
+    }
+    free(rows);
+    return 0;
+}
+
 /* ------------------------------------------------------------------------ */
 /* SURF / SURF*  (SURF.py:131-218)                                          */
 /*

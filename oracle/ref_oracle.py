@@ -141,6 +141,29 @@ def multisurf_targets(x32, y, recip, isd, use_star, targets, want_mask=True, wan
     return dict(wsum=wsum, thresh=thresh, mask=mask, dist=dist, counts=counts)
 
 
+def multisurf_targets_bytes(x8, y, use_star, targets, cols=None, want_mask=True, want_dist=True):
+    """multisurf_targets for a one-byte genotype matrix whose columns are all discrete, optionally
+    restricted to the column subset ``cols`` (no float32 copy of the matrix is made)."""
+    assert x8.dtype in (np.int8, np.uint8) and x8.ndim == 2 and x8.strides[1] == 1
+    n, p_all = x8.shape
+    ld = x8.strides[0]
+    y = np.ascontiguousarray(y, np.int64)
+    targets = np.ascontiguousarray(targets, np.int64)
+    cols = None if cols is None else np.ascontiguousarray(cols, np.int64)
+    p = p_all if cols is None else cols.size
+    nt = targets.size
+    wsum = np.empty(p, np.float64)
+    thresh = np.empty(nt, np.float64)
+    mask = np.empty((nt, n), np.int8) if want_mask else None
+    dist = np.empty((nt, n), np.float64) if want_dist else None
+    _check(lib().fso_multisurf_targets_u8(C.c_void_p(x8.ctypes.data), C.c_int64(n), C.c_int64(ld), _p(cols, C.c_int64),
+                                          C.c_int64(p), _p(y, C.c_int64), C.c_int(int(use_star)),
+                                          _p(targets, C.c_int64), C.c_int64(nt), _p(wsum, C.c_double),
+                                          _p(thresh, C.c_double), _p(mask, C.c_int8), _p(dist, C.c_double)),
+           "fso_multisurf_targets_u8")
+    return dict(wsum=wsum, thresh=thresh, mask=mask, dist=dist)
+
+
 def surf_scores(x64, y, recip, isd, use_star=False, sum_mode=0):
     x64 = np.ascontiguousarray(x64, np.float64)
     n, p = x64.shape

@@ -132,3 +132,28 @@ def test_per_target_view_sums_to_the_full_fit():
     full = R.relieff_scores(x32, y_enc, recip, isd, 5, cp, 0)
     part = R.relieff_targets(x32, y_enc, recip, isd, 5, cp, np.arange(90), tie_mode=0)["wsum"] / 90
     np.testing.assert_allclose(part, full, rtol=1e-5, atol=2e-6 * np.abs(full).max())
+
+
+@pytest.mark.parametrize("use_star", [False, True])
+def test_byte_genotype_restatement_equals_the_float32_one(use_star):
+    """fso_multisurf_targets_u8 (used at the full 20 000 x 500 000 int8 shape, where a float32 copy of the
+    matrix does not fit) is the same computation as the pinned float32 restatement on all-discrete
+    genotype data: identical distances, thresholds and neighbour codes, weights to float64 rounding;
+    also on a column subset (TuRF's X[:, active])."""
+    from datasets import epistatic_genotypes
+
+    x, y = epistatic_genotypes(11, 300, 157)
+    x[:, 5] = 1                                   # a constant column: every term 0
+    tg = np.arange(0, 300, 7)
+    isd = np.ones(157, bool)
+    recip = np.ones(157, np.float32)
+    a = R.multisurf_targets(x.astype(np.float32), y, recip, isd, use_star, tg)
+    b = R.multisurf_targets_bytes(x, y, use_star, tg)
+    assert np.array_equal(a["dist"], b["dist"]) and np.array_equal(a["thresh"], b["thresh"])
+    assert np.array_equal(a["mask"], b["mask"])
+    np.testing.assert_allclose(b["wsum"], a["wsum"], rtol=1e-13, atol=1e-13)
+    cols = np.sort(np.random.RandomState(3).choice(157, 90, replace=False))
+    a = R.multisurf_targets(np.ascontiguousarray(x[:, cols], np.float32), y, recip[:90], isd[:90], use_star, tg)
+    b = R.multisurf_targets_bytes(x, y, use_star, tg, cols=cols)
+    assert np.array_equal(a["dist"], b["dist"]) and np.array_equal(a["mask"], b["mask"])
+    np.testing.assert_allclose(b["wsum"], a["wsum"], rtol=1e-13, atol=1e-13)
