@@ -9,7 +9,8 @@ falls back to a CPU.
 from . import _mi as mutual_information
 from ._mi import CFS, mRMR
 from ._relief import MultiSURF, ReliefF, SURF
+from ._shard import enable_distributed, set_gpus
 from ._turf import TuRF
 
-__all__ = ["ReliefF", "SURF", "MultiSURF", "TuRF", "mRMR", "CFS", "mutual_information"]
+__all__ = ["ReliefF", "SURF", "MultiSURF", "TuRF", "mRMR", "CFS", "mutual_information", "enable_distributed", "set_gpus"]
 __version__ = "0.1.0"

@@ -16,7 +16,7 @@ from sklearn.base import BaseEstimator, TransformerMixin
 from sklearn.utils.validation import check_is_fitted, validate_data
 
 from . import _native
-from ._shard import score_sharded, setup_peers
+from ._shard import open_dataset, score_sharded
 
 _NO_GPU_MULTISURF = ("backend='gpu' was selected, but no compatible "
                      "NVIDIA GPU was found or CUDA toolkit is not installed.")       # MultiSURF.py:399-403
@@ -38,6 +38,20 @@ def _validate_n_select(n_features_to_select, n_features):
                 f"it must be > 0 and <= n_features ({n_features}).")
         return n_features_to_select
     raise TypeError("n_features_to_select must be an int or a float.")
+
+
+def _narrow_integers(x):
+    """Wide integer matrices whose values fit one byte (``np.random.randint`` returns int64) are narrowed
+    to int8 / uint8 BEFORE validation: sklearn would otherwise convert them to float32 on the host -- four
+    times the bytes to convert and to upload -- and one-byte matrices are what the genotype path is built
+    for.  Values are unchanged, so every result is."""
+    if isinstance(x, np.ndarray) and x.ndim == 2 and x.dtype.kind in "iu" and x.dtype.itemsize > 1 and x.size:
+        lo, hi = int(x.min()), int(x.max())
+        if -128 <= lo and hi <= 127:
+            return x.astype(np.int8)
+        if 0 <= lo and hi <= 255:
+            return x.astype(np.uint8)
+    return x
 
 
 def _count_distinct_host(x, cols):
@@ -66,15 +80,15 @@ class _Session:
     def __init__(self, algo, x, y_enc, n_classes, is_discrete, recip, arith, use_star=False, k=0,
                  class_probs=None, dataset=None):
         self.algo, self.use_star, self.k, self.class_probs = algo, use_star, k, class_probs
-        self.ds = dataset if dataset is not None else _native.Dataset(x, y_enc, n_classes)
+        self.ds = dataset if dataset is not None else open_dataset(x, y_enc, n_classes)
         self.n, self.p = self.ds.n, self.ds.p
         self.is_discrete, self.recip, self.arith = is_discrete, recip, arith
         self.ds.set_features(is_discrete, recip, arith)
         self.last_stats = None
-        # one process per GPU: shard starts are multiples of 4 and, where the GPUs can map each
-        # other's memory, distances are computed symmetrically across ranks (_shard.setup_peers)
+        # one process per GPU without a multi-GPU group (no peer access / gloo): shard starts are multiples of 4
         self.row_align = 4
-        self.peers = setup_peers(self.ds, self.n, self.row_align)
+        # inside a multi-GPU group (or on a MultiDataset) one score call returns the complete sums
+        self.collective = isinstance(self.ds, _native.MultiDataset) or self.ds.comm is not None
 
     def score(self, feat_idx=None, want_stats=False):
         n_kept = self.p if feat_idx is None else len(feat_idx)
@@ -86,7 +100,13 @@ class _Session:
                 res, self.last_stats = res
             return res
 
-        wsum = score_sharded(self.n, n_kept, score_rows, device_buffers=True, align=self.row_align)
+        if isinstance(self.ds, _native.MultiDataset):
+            wsum = score_rows(0, self.n, None)
+        elif self.collective:
+            wsum = score_rows(self.ds.shard[0], self.ds.shard[1], None)      # COLLECTIVE: every rank, own shard
+        else:
+            wsum = score_sharded(self.n, n_kept, score_rows, device_buffers=True, align=self.row_align,
+                                 device=getattr(self.ds, "device", None))
         # "/ n_samples" of the reference host callers (MultiSURF.py:162, SURF.py:128, ReliefF.py:134)
         return (wsum / self.n).astype(np.float32)
 
@@ -175,12 +195,13 @@ class MultiSURF(_ReliefBase):
     def _open_session(self, x, y):
         """Validation and per-column preprocessing of ``fit`` (MultiSURF.py:384-420);
         int8/uint8 genotype matrices are kept as they are (their float32 images are exact)."""
-        x, y = validate_data(self, x, y, y_numeric=True, dtype=[np.float32, np.int8, np.uint8], ensure_2d=True)
+        x, y = validate_data(self, _narrow_integers(x), y, y_numeric=True, dtype=[np.float32, np.int8, np.uint8],
+                             ensure_2d=True)
         self.n_features_in_ = x.shape[1]
         n_select = self._validate_parameters(x.shape[0], self.n_features_in_)
         self.effective_backend_ = self._resolve_backend(_NO_GPU_MULTISURF)
         y_enc = np.unique(y, return_inverse=True)[1].astype(np.int32)    # labels are only compared (:216)
-        ds = _native.Dataset(x, y_enc, int(y_enc.max()) + 1)
+        ds = open_dataset(x, y_enc, int(y_enc.max()) + 1)
         try:
             cmin, cmax, cnt = ds.column_stats()
             # ranges from the float32 matrix, zero -> 1, reciprocal in float32 (:409-412)
@@ -223,14 +244,14 @@ class SURF(_ReliefBase):
     def _open_session(self, X, y):
         # SURF.py:330-332 validates to float64; float32/int8/uint8 inputs are uploaded as
         # they are and widened on the device (their float64 images are exact)
-        X, y = validate_data(self, X, y, y_numeric=True,
+        X, y = validate_data(self, _narrow_integers(X), y, y_numeric=True,
                              dtype=[np.float64, np.float32, np.int8, np.uint8], ensure_2d=True)
         self.n_features_in_ = X.shape[1]
         n_select = self._validate_parameters(X.shape[0], self.n_features_in_)
         self.effective_backend_ = self._resolve_backend(_NO_GPU_SURF)
         # SURF.py:363,371: y.astype(np.int32) truncates before the equality test
         y_enc = np.unique(np.asarray(y).astype(np.int32), return_inverse=True)[1].astype(np.int32)
-        ds = _native.Dataset(X, y_enc, int(y_enc.max()) + 1)
+        ds = open_dataset(X, y_enc, int(y_enc.max()) + 1)
         try:
             cmin, cmax, cnt = ds.column_stats()
             self.is_discrete_ = _is_discrete(X, cnt, self.discrete_limit)
@@ -284,8 +305,8 @@ class ReliefF(_ReliefBase):
                 f"between 1 and n_samples - 1 ({n_samples - 1}).")
 
     def _open_session(self, x, y):
-        x, y = validate_data(self, x, y, dtype=[np.float64, np.float32, np.int8, np.uint8], ensure_2d=True,
-                             y_numeric=True)
+        x, y = validate_data(self, _narrow_integers(x), y, dtype=[np.float64, np.float32, np.int8, np.uint8],
+                             ensure_2d=True, y_numeric=True)
         self.n_features_in_ = x.shape[1]
         n_select = self._validate_parameters(x.shape[0], self.n_features_in_)
         self.classes_, y_encoded = np.unique(y, return_inverse=True)
@@ -302,7 +323,7 @@ class ReliefF(_ReliefBase):
         self.effective_backend_ = self._resolve_backend(_NO_GPU_MULTISURF)
         class_counts = np.bincount(y_encoded)
         class_probs = (class_counts / len(y)).astype(np.float32)    # :371-373, cast at :401
-        ds = _native.Dataset(x, y_encoded.astype(np.int32), len(self.classes_))
+        ds = open_dataset(x, y_encoded.astype(np.int32), len(self.classes_))
         try:
             cmin, cmax, cnt = ds.column_stats()
             self.is_discrete_ = _is_discrete(x, cnt, self.discrete_limit)

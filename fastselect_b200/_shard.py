@@ -1,13 +1,27 @@
-"""Target-row sharding across GPUs (one process per GPU, torch.distributed plumbing).
+"""Multi-GPU plumbing of the estimators.
 
 The reference has no multi-GPU path; its unit of parallelism is the target instance
 (``prange``/one CUDA block per instance: MultiSURF.py:174, SURF.py:139, ReliefF.py:143).
-Here the target rows of the distance matrix are split into ``world_size`` contiguous
-ranges, every rank scores its own range against all samples, and the partial
-per-feature weight sums are combined by ONE allreduce (NCCL over NVLink on GPUs,
-gloo in the CPU tests).  There is no other exchange on the data path.
+Here the target rows of the distance matrix are split into ``world`` contiguous ranges.
+
+Three ways to use more than one GPU, all OPT-IN (a plain ``fit`` uses one GPU and never
+communicates):
+
+* ``FASTSELECT_B200_GPUS=8`` (or ``set_gpus``): one process, the library drives one host
+  thread per GPU (``_native.MultiDataset`` / ``fs_multi_*``); no torch involved.
+* ``enable_distributed()`` (or ``FASTSELECT_B200_DISTRIBUTED=1``) inside a ``torchrun`` job
+  with an initialised NCCL process group: one process per GPU, every rank calls ``fit`` with
+  the SAME ``X, y``.  torch.distributed is used only to exchange the 64-byte CUDA IPC handles
+  of the ranks' exchange arenas (once per arena size); the data path is the library's own:
+  1 / world of X uploaded per rank and replicated over NVLink, symmetric distance tiles,
+  neighbour masks and weight slices stored straight into the peers' arenas, device-side
+  barriers (``include/fastselect_b200.h``, "Multi-GPU group").
+* if the ranks cannot map each other's memory (no peer access) or the backend is gloo (CPU
+  tests): plain row sharding, every rank uploads X, ONE allreduce of the partial weight sums.
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 
@@ -50,8 +64,47 @@ def shard_triangle(q: int, world_size: int, rank: int) -> tuple[int, int]:
     return cuts[rank], cuts[rank + 1]
 
 
+_DISTRIBUTED = None        # None: follow the environment variable
+
+
+def enable_distributed(flag: bool = True) -> None:
+    """Opt in to (or out of) sharding ``fit`` across the ranks of the initialised torch.distributed
+    process group.  Every rank must then call ``fit`` with the same ``X, y``.  Without the opt-in a
+    ``fit`` inside a torchrun job stays local to its process (per-rank data sets, CV folds ...)."""
+    global _DISTRIBUTED
+    _DISTRIBUTED = bool(flag)
+
+
+def distributed_enabled() -> bool:
+    if _DISTRIBUTED is not None:
+        return _DISTRIBUTED
+    return os.environ.get("FASTSELECT_B200_DISTRIBUTED", "").strip() not in ("", "0")
+
+
+def set_gpus(devices) -> None:
+    """Use several GPUs of this process: a count (devices 0..k-1), a list of CUDA ordinals, or None / 1
+    for one GPU.  Same as the environment variable ``FASTSELECT_B200_GPUS``."""
+    if devices is None:
+        os.environ.pop("FASTSELECT_B200_GPUS", None)
+    elif isinstance(devices, int):
+        os.environ["FASTSELECT_B200_GPUS"] = str(devices)
+    else:
+        os.environ["FASTSELECT_B200_GPUS"] = ",".join(str(int(d)) for d in devices)
+
+
+def local_devices() -> list[int]:
+    """CUDA ordinals of FASTSELECT_B200_GPUS ("4" -> [0, 1, 2, 3]; "0,2,5" -> [0, 2, 5]); [] = one GPU."""
+    v = os.environ.get("FASTSELECT_B200_GPUS", "").strip()
+    if v == "":
+        return []
+    devs = [int(t) for t in v.split(",")] if "," in v else list(range(int(v)))
+    return devs if len(devs) > 1 else []
+
+
 def dist_info() -> tuple[int, int]:
-    """(rank, world_size) of the initialised torch.distributed group, else (0, 1)."""
+    """(rank, world_size) of the initialised torch.distributed group when sharding is opted in, else (0, 1)."""
+    if not distributed_enabled():
+        return 0, 1
     try:
         import torch.distributed as dist
     except Exception:  # torch absent: single process
@@ -73,56 +126,99 @@ def allreduce_sum_numpy(partial: np.ndarray) -> np.ndarray:
     return t.cpu().numpy()
 
 
-def setup_peers(ds, n: int, align: int = 4) -> bool:
-    """Multi-GPU symmetric distances for one open data set: exchange the ranks' slab handles
-    (one all_gather) and hand the library a cross-rank barrier.  Returns False (and leaves the
-    plain row-sharded path in place) when there is a single rank, no NCCL, or no peer access."""
+# --------------------------------------------------------------------------- #
+# one process per GPU: the group's communicator (cached for the life of the process)
+# --------------------------------------------------------------------------- #
+_COMM = None            # _native.Comm of this process
+_COMM_BROKEN = False    # the ranks cannot map each other: stay on the allreduce path
+
+
+def _input_digest(n, p, y_enc):
+    """A cheap fingerprint of the call's inputs; ranks that were handed different data must not be
+    summed together."""
+    y = np.ascontiguousarray(y_enc, np.int64)
+    return [int(n), int(p), int(y.sum()), int((y * (np.arange(y.size, dtype=np.int64) % 1009 + 1)).sum())]
+
+
+def group_comm(n, p, dtype, y_enc):
+    """The connected communicator of this rank, with an arena large enough for an n x p data set of
+    ``dtype`` (COLLECTIVE: one all_gather; re-allocation and re-connection happen on all ranks or none).
+    Returns None when there is a single rank, the backend is not NCCL, or the ranks cannot map each
+    other's memory (the caller then shards rows and allreduces)."""
+    global _COMM, _COMM_BROKEN
     rank, world = dist_info()
-    if world == 1:
-        return False
+    if world == 1 or _COMM_BROKEN:
+        return None
     import torch
     import torch.distributed as dist
 
-    if dist.get_backend() != "nccl" or world > 16:
-        return False
-    starts = shard_starts(n, world, align)
-    if any(a == b for a, b in zip(starts, starts[1:])):
-        return False        # a rank without rows would skip the barrier inside fs_score
-    ok = torch.ones(1, dtype=torch.int32, device="cuda")
-    handles = torch.zeros(world * 64, dtype=torch.uint8, device="cuda")
-    try:
-        handle, _ = ds.peer_slab(starts[rank + 1] - starts[rank])
-        mine = torch.from_numpy(handle).cuda()
-    except Exception:
-        ok.zero_()
-        mine = torch.zeros(64, dtype=torch.uint8, device="cuda")
-    dist.all_gather_into_tensor(handles, mine)
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    if int(ok.item()) == 0:
-        return False
+    from . import _native
 
-    def barrier():
-        dist.barrier()
-        torch.cuda.synchronize()
-
+    if dist.get_backend() != "nccl" or world > 16 or n < 8 * world:
+        return None
+    device = _native.default_device()
+    if _COMM is None or _COMM.world != world or _COMM.rank != rank or _COMM.device != device:
+        _COMM = _native.Comm(rank, world, device)
+    need = _native.Comm.required_bytes(n, p, dtype, world, with_x=True)
+    ok = 1
+    handle = np.zeros(64, np.uint8)
+    changed = False
     try:
-        ds.set_peers(rank, world, starts, handles=handles.cpu().numpy(), barrier=barrier)
+        handle, changed = _COMM.reserve(need)
     except Exception:
-        ok.zero_()
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN)      # all ranks or none: the barrier inside fs_score must match
-    if int(ok.item()) == 0:
-        # some rank could not map its peers: every rank falls back to the unsymmetric path
+        ok = 0
+    # one exchange: IPC handle, "my arena moved", "still fine", and the input fingerprint
+    mine = np.zeros(64 + 8 * 6, np.uint8)
+    mine[:64] = handle
+    mine[64:].view(np.int64)[:] = [int(changed or not _COMM.connected), ok] + _input_digest(n, p, y_enc)
+    dev = torch.device("cuda", device)
+    got = torch.empty(world * mine.size, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(got, torch.from_numpy(mine).to(dev))
+    got = got.cpu().numpy().reshape(world, mine.size)
+    meta = got[:, 64:].copy().view(np.int64).reshape(world, 6)
+    if not (meta[:, 2:] == meta[0, 2:]).all():
+        raise ValueError("fastselect_b200: the ranks of the process group were given different X / y; "
+                         "distributed fitting (enable_distributed) needs the same data on every rank")
+    if not meta[:, 1].all():
+        _COMM_BROKEN = True
+        return None
+    if meta[:, 0].any():
         try:
-            ds.set_peers(rank, 1, [0, n], raw_ptrs=[0], barrier=lambda: None)
+            _COMM.connect(handles=np.ascontiguousarray(got[:, :64]).reshape(-1))
         except Exception:
-            pass
-        return False
-    return True
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # also the host-level barrier fs_comm_connect asks for
+        if int(flag.item()) == 0:
+            _COMM_BROKEN = True                          # all ranks or none: the collectives inside fs_score must match
+            return None
+    return _COMM
 
 
-def score_sharded(n: int, n_kept: int, score_rows, device_buffers: bool, align: int = 1):
-    """Run ``score_rows(lo, hi, out_device_ptr)`` on this rank's target rows and return
-    the allreduced float64 weight sums.
+def open_dataset(x, y_enc, n_classes):
+    """The device-resident data set of a ``fit``: several GPUs of this process (FASTSELECT_B200_GPUS),
+    this rank's member of a multi-GPU group (enable_distributed + NCCL), or one plain GPU data set."""
+    from . import _native
+
+    devs = local_devices()
+    rank, world = dist_info()
+    if devs and world == 1:
+        return _native.MultiDataset(x, y_enc, n_classes, devs)
+    comm = group_comm(x.shape[0], x.shape[1], x.dtype, y_enc) if world > 1 else None
+    if comm is None:
+        return _native.Dataset(x, y_enc, n_classes)
+    ds = _native.Dataset(x, y_enc, n_classes, comm=comm)
+    try:
+        ds.attach_comm(comm, shard_starts(ds.n, world, 4))
+    except BaseException:
+        ds.close()
+        raise
+    return ds
+
+
+def score_sharded(n: int, n_kept: int, score_rows, device_buffers: bool, align: int = 1, device: int | None = None):
+    """Fallback without a multi-GPU group: run ``score_rows(lo, hi, out_device_ptr)`` on this rank's
+    target rows and return the allreduced float64 weight sums.
 
     ``score_rows`` returns a float64 numpy vector when ``out_device_ptr`` is None and
     writes the device buffer otherwise (fastselect_b200._native.Dataset.score)."""
@@ -134,7 +230,8 @@ def score_sharded(n: int, n_kept: int, score_rows, device_buffers: bool, align: 
         import torch
         import torch.distributed as dist
 
-        buf = torch.empty(n_kept, dtype=torch.float64, device="cuda")
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        buf = torch.empty(n_kept, dtype=torch.float64, device=dev)
         score_rows(lo, hi, buf.data_ptr())
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)   # one NCCL allreduce over NVLink per fit
         return buf.cpu().numpy()
@@ -156,7 +253,9 @@ def joint_sharded(q: int, compute_band, device_buffers: bool):
 
     lo, hi = shard_triangle(q, world, rank)
     if device_buffers:
-        buf = torch.empty((q, q), dtype=torch.float64, device="cuda")
+        from . import _native
+
+        buf = torch.empty((q, q), dtype=torch.float64, device=torch.device("cuda", _native.default_device()))
         compute_band(lo, hi, buf.data_ptr())
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)       # one NCCL allreduce over NVLink per matrix
         return buf.cpu().numpy()

@@ -13,7 +13,7 @@ import numpy as np
 from sklearn.base import BaseEstimator, TransformerMixin, clone
 from sklearn.utils.validation import check_is_fitted, validate_data
 
-from ._relief import _ReliefBase, _validate_n_select
+from ._relief import _narrow_integers, _ReliefBase, _validate_n_select
 
 
 class TuRF(TransformerMixin, BaseEstimator):
@@ -73,7 +73,7 @@ class TuRF(TransformerMixin, BaseEstimator):
         if resident:
             # keep int8/uint8/float32 matrices as they are: the base estimator's own
             # validation decides the arithmetic, exactly as a direct fit would
-            Xv, y = validate_data(self, X, y, y_numeric=True,
+            Xv, y = validate_data(self, _narrow_integers(X), y, y_numeric=True,
                                   dtype=[np.float64, np.float32, np.int8, np.uint8], ensure_2d=True)
         else:
             Xv, y = validate_data(self, X, y, y_numeric=True, dtype=np.float64, ensure_2d=True)   # TuRF.py:77-79

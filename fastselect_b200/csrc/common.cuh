@@ -155,6 +155,30 @@ struct DistPeers {
     int32_t coarse_shift;           // symmetric mode: log2 of the super-block group size (see tc_dist.cu)
 };
 
+// ---------------------------------------------------------------------------
+// multi-GPU group (comm.cu): every rank owns one exchange arena with the same layout
+// ---------------------------------------------------------------------------
+struct CommHeader {
+    uint32_t flags[kMaxRanks];   // flags[q]: last barrier epoch rank q published here
+    uint32_t error;              // != 0: a barrier gave up (1 + the rank that never arrived)
+    uint32_t pad[15];
+};
+struct CommPeers {
+    CommHeader *hdr[kMaxRanks];  // base of every rank's arena (own: local; others: peer / IPC mappings)
+    int32_t world, rank;
+};
+// Byte offsets inside an arena (identical on every rank: computed from n, p and the world size only)
+struct GroupLayout {
+    size_t off_slab;      // int32 [max shard rows (padded to 128), ldn]  symmetric distance slab of the rank's target rows
+    size_t off_mask_h;    // FP4 nibbles [ldn, ldn / 2]  signed hit masks of ALL target rows (every rank fills its rows everywhere)
+    size_t off_mask_m;    //   "   miss masks
+    size_t off_rinfo;     // RowInfo [ldn]
+    size_t off_w;         // double [world, p]  per-rank contribution to the weight sums
+    size_t off_x;         // raw X (optional; sharded upload)
+    size_t total;
+};
+GroupLayout group_layout(int64_t n, int64_t p, int64_t max_shard_rows, int world, size_t x_bytes);
+
 // Working set of one fs_score call: the active columns split by path.
 struct WorkSet {
     // general (CUDA-core) path
@@ -205,9 +229,27 @@ struct WorkSet {
     // cache key
     std::vector<int64_t> key;
     bool valid = false;
+    // feature-sharded accumulation (multi-GPU group): At / codesT / krow hold only the tensor columns
+    // [a0, a1) of the active list -- this rank's share -- with one-hot rows numbered from 0
+    int64_t a0 = 0, a1 = 0;        // == [0, pt) on one GPU
+    int64_t Ka = 0, Ka_used = 0;   // one-hot rows of the slice (padded / in use)
+    DevBuf<int32_t> atoff;         // [a1 - a0 + 1] first reduced row of each slice column, from 0
+    PinnedBuf<int32_t> p_atoff;
+    bool acc_split = false;
 };
 
 }  // namespace fs
+
+struct fs_comm {
+    int rank = 0, world = 1, device = 0;
+    void *arena = nullptr;
+    size_t arena_bytes = 0;
+    void *opened[fs::kMaxRanks] = {};     // IPC mappings this communicator opened
+    fs::CommPeers peers{};
+    uint32_t epoch = 0;
+    unsigned long long timeout_ns = 0;
+    bool connected = false;
+};
 
 struct fs_dataset {
     int device = 0;
@@ -256,8 +298,6 @@ struct fs_dataset {
     bool peers_on = false;
     int32_t *peer_slab = nullptr;
     size_t peer_slab_count = 0;
-    void (*barrier_fn)(void *) = nullptr;
-    void *barrier_ctx = nullptr;
     bool last_dist_exchanged = false;        // the last distance launch stored into peer slabs
     fs::DevBuf<int8_t> sel;       // [R, ldn] neighbour codes
     fs::DevBuf<fs::RowInfo> rinfo;
@@ -273,6 +313,14 @@ struct fs_dataset {
     fs::DevBuf<int32_t> tile_desc; // target-tile descriptors of the accumulation kernel
     fs::DevBuf<int32_t> tile_consts; // per-(tile, phase, target) coefficient limbs and mask row sums
     fs::DevBuf<int8_t> maskH, maskM;
+    // multi-GPU group (fs_dataset_attach_comm): arena layout of this data set, this rank's target rows
+    fs_comm *comm = nullptr;
+    bool x_in_arena = false;                 // fs_dataset_create_group: the raw matrix lives in the arena
+    fs::GroupLayout glayout{};
+    fs::DevBuf<int64_t> all_ids;             // 0 .. n-1 (the sharded accumulation runs over all target rows)
+    std::vector<int64_t> all_ids_h;
+    std::vector<int64_t> tcol_all_sorted;    // tensor-path columns of the whole data set (ascending): static ownership
+    std::vector<int64_t> owner_bound;        // [world + 1] original-column boundaries of the ranks' accumulation shares
     fs::DevBuf<int8_t> a_gather;  // gathered one-hot target rows (fs_debug_rows)
     fs::DevBuf<int32_t> tie_flag, tie_order, tie_list;   // ReliefF reference tie order (select.cu)
     fs::DevBuf<float> tie_keys;
@@ -293,8 +341,14 @@ namespace fs {
 // dataset.cu
 // r0 / R / slab_cacheable: the (contiguous) target rows of this call and whether their distance
 // slab fits one chunk -- decides between a full, an incremental and no distance computation
+// want_split: a multi-GPU group call that may shard the accumulation by one-hot columns (WorkSet::acc_split)
 void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool allow_tensor, bool need_codes,
-                   int64_t r0, int64_t R, bool contiguous, bool slab_cacheable, int *launches);
+                   int64_t r0, int64_t R, bool contiguous, bool slab_cacheable, bool want_split, int *launches);
+
+// comm.cu
+void comm_barrier(fs_comm *c, cudaStream_t st, int *launches);
+void comm_check(fs_comm *c);
+void comm_push(fs_comm *c, size_t off, size_t bytes, cudaStream_t st, int *launches);
 
 // dist_general.cu: D[r, j] = sum over general columns of the per-feature term
 // between target row r (rows of xa) and sample j (rows of xb).

@@ -73,61 +73,6 @@ void pinned_give(void *ptr, size_t bytes) {
     g_pinned_free.push_back(PinnedBlock{ptr, bytes});
 }
 
-// Process-wide caches of the multi-GPU distance slabs: allocating an IPC-exportable slab and
-// opening the peers' handles cost milliseconds, and every fit opens a new data set.  A slab
-// returns to the free list when its data set is destroyed (it keeps its IPC handle, so the peers'
-// mappings stay valid for the next fit); opened peer mappings are kept until the process exits.
-namespace {
-struct SlabEntry {
-    int device;
-    int32_t *ptr;
-    size_t count;
-    bool in_use;
-};
-std::mutex g_slab_mu;
-std::vector<SlabEntry> g_slabs;
-std::vector<std::pair<std::array<char, 64>, void *>> g_ipc_open;
-}  // namespace
-
-static int32_t *slab_take(int device, size_t count, size_t *got) {
-    std::lock_guard<std::mutex> lk(g_slab_mu);
-    int best = -1;
-    for (int i = 0; i < (int)g_slabs.size(); ++i)
-        if (!g_slabs[i].in_use && g_slabs[i].device == device && g_slabs[i].count >= count &&
-            (best < 0 || g_slabs[i].count < g_slabs[best].count))
-            best = i;
-    if (best < 0) {
-        int32_t *p = nullptr;
-        // plain cudaMalloc: stream-ordered pool memory cannot be exported through CUDA IPC
-        FS_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(int32_t)));
-        g_slabs.push_back(SlabEntry{device, p, count, false});
-        best = (int)g_slabs.size() - 1;
-    }
-    g_slabs[best].in_use = true;
-    *got = g_slabs[best].count;
-    return g_slabs[best].ptr;
-}
-
-static void slab_give(int32_t *ptr) {
-    std::lock_guard<std::mutex> lk(g_slab_mu);
-    for (auto &e : g_slabs)
-        if (e.ptr == ptr) e.in_use = false;
-}
-
-static void *ipc_open_cached(const char *handle_bytes) {
-    std::lock_guard<std::mutex> lk(g_slab_mu);
-    std::array<char, 64> key;
-    memcpy(key.data(), handle_bytes, 64);
-    for (auto &kv : g_ipc_open)
-        if (kv.first == key) return kv.second;
-    cudaIpcMemHandle_t h;
-    memcpy(&h, handle_bytes, sizeof(h));
-    void *p = nullptr;
-    FS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-    g_ipc_open.emplace_back(key, p);
-    return p;
-}
-
 // keep freed blocks in the device's default memory pool (no trimming at synchronisation)
 void configure_pool(int device) {
     static bool done[64] = {false};
@@ -283,6 +228,28 @@ static void finish_create(fs_dataset *ds) {
     FS_CUDA(cudaStreamSynchronize(ds->stream));
 }
 
+// Static ownership of the one-hot columns inside a multi-GPU group: rank r accumulates the tensor-path
+// columns whose original index lies in [owner_bound[r], owner_bound[r + 1]) -- equal shares of the data
+// set's tensor-path columns.  Fixed for the life of the typing, so that TuRF iterations keep finding
+// their columns' value codes in the rank's resident codesT.
+static void compute_owner_bounds(fs_dataset *ds) {
+    ds->owner_bound.clear();
+    if (!ds->comm || !ds->have_features) return;
+    std::vector<int64_t> tc;
+    for (int64_t f = 0; f < ds->p; ++f)
+        if ((ds->col_info[f] & kColPathMask) == kColTensor) tc.push_back(f);
+    const int world = ds->comm->world;
+    const int64_t T = (int64_t)tc.size();
+    ds->owner_bound.assign(world + 1, ds->p);
+    ds->owner_bound[0] = 0;
+    // shares of whole 64-column tiles of the encoder where the list is long enough
+    for (int r = 1; r < world; ++r) {
+        int64_t pos = T * r / world;
+        if (T >= 64LL * 4 * world) pos = pos / 64 * 64;
+        ds->owner_bound[r] = pos < T ? tc[pos] : ds->p;
+    }
+}
+
 static int usable_devices() {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess) {
@@ -393,7 +360,7 @@ static int plan_dist(fs_dataset *ds, const int64_t *tcol, int64_t pt, int64_t r0
 }
 
 void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool allow_tensor, bool need_codes,
-                   int64_t r0, int64_t R, bool contiguous, bool slab_cacheable, int *launches) {
+                   int64_t r0, int64_t R, bool contiguous, bool slab_cacheable, bool want_split, int *launches) {
     WorkSet &ws = ds->ws;
     // sample rows the target-side distance operand U has to hold
     const int64_t want_lo = contiguous ? r0 : 0, want_hi = contiguous ? r0 + R : ds->n;
@@ -401,7 +368,7 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
     // cache key: flags + the explicit column list (none when every column is active)
     const bool all = feat_idx == nullptr;
     std::vector<int64_t> key(3 + (all ? 0 : n_kept));
-    key[0] = allow_tensor ? 1 : 0;
+    key[0] = (allow_tensor ? 1 : 0) | (want_split ? 2 : 0);
     key[1] = ds->arith;
     key[2] = all ? -1 : n_kept;
     if (!all) memcpy(key.data() + 3, feat_idx, n_kept * sizeof(int64_t));
@@ -481,6 +448,21 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
     }
     ws.pt = pt;
     ws.K_used = K;
+    // feature-sharded accumulation: this rank's share of the active one-hot columns is the run of the
+    // (ascending) list that falls inside its static range of original columns (owner_bound)
+    ws.a0 = 0;
+    ws.a1 = pt;
+    ws.acc_split = false;
+    if (want_split && pt > 0 && ds->comm && (int)ds->owner_bound.size() == ds->comm->world + 1) {
+        bool ascending = true;
+        for (int64_t c = 1; c < pt && ascending; ++c) ascending = tcol[c] > tcol[c - 1];
+        if (ascending) {
+            const int rk = ds->comm->rank;
+            ws.a0 = std::lower_bound(tcol, tcol + pt, ds->owner_bound[rk]) - tcol;
+            ws.a1 = std::lower_bound(tcol, tcol + pt, ds->owner_bound[rk + 1]) - tcol;
+            ws.acc_split = true;
+        }
+    }
     ws.all_ident = (ident & kColIdent) != 0;
     ws.all_v3 = v3 && pt > 0;
     ws.n_cont = (int64_t)cont_col.size();
@@ -687,6 +669,7 @@ int fs_dataset_set_features(fs_dataset *ds, const uint8_t *is_discrete, const fl
     ds->ws.valid = false;
     ds->dd_valid = false;
     ds->ct_valid = false;
+    compute_owner_bounds(ds);
     return FS_OK;
 }
 
@@ -699,74 +682,110 @@ int fs_dataset_row_order(const fs_dataset *ds, int64_t *perm_out) {
     return FS_OK;
 }
 
-int fs_dataset_peer_slab(fs_dataset *ds, int64_t rows, void *ipc_handle_out, void **dev_ptr_out) {
+int fs_dataset_attach_comm(fs_dataset *ds, fs_comm *comm, const int64_t *row_starts) {
     try {
-        FS_REQUIRE(ds && rows >= 0, FS_ERR_INVALID, "fs_dataset_peer_slab: invalid argument");
-        FS_CUDA(cudaSetDevice(ds->device));
-        const size_t count = (size_t)round_up(std::max<int64_t>(rows, 1), 128) * (size_t)round_up(ds->n, 128);
-        if (ds->peer_slab == nullptr || ds->peer_slab_count < count) {
-            FS_REQUIRE(!ds->peers_on, FS_ERR_STATE, "fs_dataset_peer_slab: peers already configured");
-            if (ds->peer_slab) slab_give(ds->peer_slab);
+        FS_REQUIRE(ds, FS_ERR_INVALID, "fs_dataset_attach_comm: null data set");
+        if (comm == nullptr || comm->world <= 1) {         // detach: plain single-rank behaviour
+            ds->comm = nullptr;
+            ds->peers_on = false;
             ds->peer_slab = nullptr;
-            ds->peer_slab = slab_take(ds->device, count, &ds->peer_slab_count);
+            ds->dd_valid = false;
+            ds->ws.valid = false;
+            ds->owner_bound.clear();
+            return FS_OK;
         }
-        if (ipc_handle_out) {
-            cudaIpcMemHandle_t h;
-            FS_CUDA(cudaIpcGetMemHandle(&h, ds->peer_slab));
-            static_assert(sizeof(h) == 64, "CUDA IPC handle size");
-            memcpy(ipc_handle_out, &h, sizeof(h));
+        FS_REQUIRE(row_starts, FS_ERR_INVALID, "fs_dataset_attach_comm: row_starts missing");
+        FS_REQUIRE(comm->connected, FS_ERR_STATE, "fs_dataset_attach_comm: the communicator is not connected");
+        FS_REQUIRE(comm->device == ds->device, FS_ERR_INVALID, "fs_dataset_attach_comm: communicator on device %d, data set on %d",
+                   comm->device, ds->device);
+        const int world = comm->world, rank = comm->rank;
+        FS_REQUIRE(row_starts[0] == 0 && row_starts[world] == ds->n, FS_ERR_INVALID,
+                   "fs_dataset_attach_comm: row_starts must run from 0 to n");
+        DistPeers pr{};
+        pr.world = world;
+        pr.rank = rank;
+        int32_t sb = 0;
+        int64_t max_shard = 0;
+        for (int r = 0; r <= world; ++r) {
+            if (r < world) {
+                FS_REQUIRE(row_starts[r] < row_starts[r + 1] && (row_starts[r] & 3) == 0, FS_ERR_INVALID,
+                           "fs_dataset_attach_comm: row_starts must be strictly ascending multiples of 4 (no empty shard)");
+                max_shard = std::max<int64_t>(max_shard, row_starts[r + 1] - row_starts[r]);
+            }
+            pr.starts[r] = row_starts[r];
+            pr.sb_base[r] = sb;
+            if (r < world) sb += (int32_t)ceil_div(row_starts[r + 1] - row_starts[r], 256);
         }
-        if (dev_ptr_out) *dev_ptr_out = ds->peer_slab;
+        // the layout every rank computes from (n, p, world) alone; X lives in the arena only for data
+        // sets created by fs_dataset_create_group (then ds->x already points there)
+        const size_t es = dtype_size(ds->dtype);
+        const bool x_in_arena = ds->x_in_arena;
+        const GroupLayout L = group_layout(ds->n, ds->p, ceil_div(ds->n, world) + 4, world,
+                                           x_in_arena ? (size_t)ds->n * ds->ldx * es : 0);
+        FS_REQUIRE(max_shard <= ceil_div(ds->n, world) + 4, FS_ERR_INVALID,
+                   "fs_dataset_attach_comm: shards must be balanced (largest %lld rows)", (long long)max_shard);
+        FS_REQUIRE(L.total <= comm->arena_bytes, FS_ERR_INVALID,
+                   "fs_dataset_attach_comm: arena of %llu bytes is smaller than the %llu this data set needs",
+                   (unsigned long long)comm->arena_bytes, (unsigned long long)L.total);
+        ds->glayout = L;
+        for (int r = 0; r < world; ++r)
+            pr.slab[r] = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(comm->peers.hdr[r]) + L.off_slab);
+        ds->peers = pr;
+        ds->comm = comm;
+        ds->peer_slab = pr.slab[rank];
+        ds->peer_slab_count = (L.off_mask_h - L.off_slab) / sizeof(int32_t);
+        ds->peers_on = true;
+        ds->dd_valid = false;
+        ds->ws.valid = false;
+        compute_owner_bounds(ds);
         return FS_OK;
     } catch (const Fail &f) {
         return f.code;
     }
 }
 
-int fs_dataset_set_peers(fs_dataset *ds, int32_t rank, int32_t world, const int64_t *row_starts,
-                         const void *ipc_handles, void *const *raw_ptrs, void (*barrier)(void *), void *barrier_ctx) {
+// Sharded upload: this rank copies rows [n * rank / world, n * (rank + 1) / world) of the host matrix into
+// the X region of its arena, stores them into every peer's arena over NVLink, and after a device-side
+// barrier every rank holds all of X having moved 1/world of it over PCIe.
+int fs_dataset_create_group(fs_dataset **out, fs_comm *comm, const void *x, int dtype, int64_t n, int64_t p,
+                            int64_t row_stride_elems, const int32_t *y_enc, int32_t n_classes, void *stream) {
+    fs_dataset *ds = nullptr;
     try {
-        FS_REQUIRE(ds && row_starts && barrier, FS_ERR_INVALID, "fs_dataset_set_peers: null pointer");
-        FS_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, FS_ERR_INVALID,
-                   "fs_dataset_set_peers: bad rank/world %d/%d (at most %d ranks)", rank, world, kMaxRanks);
-        FS_REQUIRE(ipc_handles || raw_ptrs, FS_ERR_INVALID, "fs_dataset_set_peers: no handles");
-        FS_REQUIRE(ds->peer_slab != nullptr, FS_ERR_STATE, "fs_dataset_set_peers: call fs_dataset_peer_slab first");
-        FS_REQUIRE(row_starts[0] == 0 && row_starts[world] == ds->n, FS_ERR_INVALID,
-                   "fs_dataset_set_peers: row_starts must run from 0 to n");
-        FS_CUDA(cudaSetDevice(ds->device));
-        DistPeers pr{};
-        pr.world = world;
-        pr.rank = rank;
-        int32_t sb = 0;
-        for (int r = 0; r <= world; ++r) {
-            if (r < world)
-                FS_REQUIRE(row_starts[r] <= row_starts[r + 1] && (row_starts[r] & 3) == 0, FS_ERR_INVALID,
-                           "fs_dataset_set_peers: row_starts must be ascending multiples of 4");
-            pr.starts[r] = row_starts[r];
-            pr.sb_base[r] = sb;
-            if (r < world) sb += (int32_t)ceil_div(row_starts[r + 1] - row_starts[r], 256);
-        }
-        FS_REQUIRE((size_t)round_up(std::max<int64_t>(pr.starts[rank + 1] - pr.starts[rank], 1), 128) *
-                           (size_t)round_up(ds->n, 128) <= ds->peer_slab_count,
-                   FS_ERR_INVALID, "fs_dataset_set_peers: slab smaller than this rank's shard");
-        ds->peers_on = false;
-        for (int r = 0; r < world; ++r) {
-            if (r == rank) {
-                pr.slab[r] = ds->peer_slab;
-            } else if (raw_ptrs) {
-                pr.slab[r] = static_cast<int32_t *>(raw_ptrs[r]);
-            } else {
-                pr.slab[r] = static_cast<int32_t *>(ipc_open_cached(static_cast<const char *>(ipc_handles) + (size_t)r * 64));
-            }
-        }
-        ds->peers = pr;
-        ds->barrier_fn = barrier;
-        ds->barrier_ctx = barrier_ctx;
-        ds->peers_on = world > 1;
-        ds->dd_valid = false;
+        FS_REQUIRE(out && x && comm, FS_ERR_INVALID, "fs_dataset_create_group: null pointer");
+        FS_REQUIRE(comm->connected, FS_ERR_STATE, "fs_dataset_create_group: the communicator is not connected");
+        ds = create_common(dtype, n, p, row_stride_elems, y_enc, n_classes, comm->device, stream);
+        const size_t es = dtype_size(dtype);
+        ds->ldx = round_up(p, 16 / (int64_t)es > 0 ? 16 / (int64_t)es : 1);
+        const int world = comm->world, rank = comm->rank;
+        const GroupLayout L = group_layout(n, p, ceil_div(n, world) + 4, world, (size_t)n * ds->ldx * es);
+        FS_REQUIRE(L.total <= comm->arena_bytes, FS_ERR_INVALID,
+                   "fs_dataset_create_group: arena of %llu bytes is smaller than the %llu this data set needs",
+                   (unsigned long long)comm->arena_bytes, (unsigned long long)L.total);
+        char *xa = static_cast<char *>(comm->arena) + L.off_x;
+        ds->x = xa;
+        ds->x_in_arena = true;
+        const int64_t lo = n * rank / world, hi = n * (rank + 1) / world;
+        cudaStream_t st = ds->stream;
+        if (hi > lo)
+            FS_CUDA(cudaMemcpy2DAsync(xa + (size_t)lo * ds->ldx * es, ds->ldx * es,
+                                      static_cast<const char *>(x) + (size_t)lo * row_stride_elems * es,
+                                      row_stride_elems * es, p * es, hi - lo, cudaMemcpyHostToDevice, st));
+        prepare_create(ds, y_enc);          // host work (class sort) overlaps the copy
+        int launches = 0;
+        if (hi > lo && world > 1) comm_push(comm, L.off_x + (size_t)lo * ds->ldx * es, (size_t)(hi - lo) * ds->ldx * es, st, &launches);
+        comm_barrier(comm, st, &launches);
+        scan_rows(ds, 0, n, true, true);
+        finish_create(ds);
+        comm_check(comm);
+        *out = ds;
         return FS_OK;
     } catch (const Fail &f) {
+        delete ds;
         return f.code;
+    } catch (const std::exception &e) {
+        set_error("fs_dataset_create_group: %s", e.what());
+        delete ds;
+        return FS_ERR_OOM;
     }
 }
 
@@ -774,7 +793,6 @@ int fs_dataset_destroy(fs_dataset *ds) {
     if (!ds) return FS_OK;
     cudaSetDevice(ds->device);
     cudaStreamSynchronize(ds->stream);
-    if (ds->peer_slab) slab_give(ds->peer_slab);
     alloc_stream() = ds->stream;
     delete ds;
     return FS_OK;

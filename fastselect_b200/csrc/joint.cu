@@ -175,7 +175,7 @@ void run_joint(fs_dataset *ds, int kind, double log_base, const int64_t *feat_id
     tm.begin(PH_ENCODE);
     ds->no_dist_ops = true;
     try {
-        build_workset(ds, feat_idx, n_kept, true, false, 0, n, true, false, &launches);
+        build_workset(ds, feat_idx, n_kept, true, false, 0, n, true, false, false, &launches);
     } catch (...) {
         ds->no_dist_ops = false;
         throw;

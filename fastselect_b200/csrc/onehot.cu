@@ -619,7 +619,7 @@ static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
 
 void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     const int64_t n = ds->n, pt = ws.pt;
-    // tcol / tout / toff, K_used and all_ident were filled by build_workset (pinned staging)
+    // tcol / tout / toff, K_used, all_ident and the accumulation slice [a0, a1) were filled by build_workset
     ws.K = round_up(ws.K_used, 256);          // elements (FP4 nibbles); U / Wd rows are K / 2 bytes
     ws.ldt = round_up(n, 128);
     ws.ldc = round_up(pt, 16);
@@ -628,34 +628,45 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     ws.tout.reserve(pt);
     ws.toff.reserve(pt + 1);
     const bool ops = ws.have_dist_ops;
+    // accumulation operands: the slice [a0, a1) of the active columns (all of them outside a multi-GPU
+    // group), one-hot rows numbered from 0
+    const int64_t a0 = ws.a0, a1 = ws.a1, pa = a1 - a0;
+    const bool split = ws.acc_split;
+    ws.Ka_used = ws.p_toff.ptr[a1] - ws.p_toff.ptr[a0];
+    ws.Ka = round_up(ws.Ka_used, 256);
     if (ops) {
         ws.U.reserve((size_t)(ws.u_hi - ws.u_lo) * (ws.K / 2));   // target rows of this call only
         ws.Wd.reserve((size_t)n * (ws.K / 2));
         ws.srow.reserve(ws.ldt);   // padded: the distance epilogue reads it in 16-byte vectors
     }
-    ws.At.reserve((size_t)ws.K * (ws.ldt / 2));          // FP4 nibbles: two samples per byte
+    ws.At.reserve((size_t)std::max<int64_t>(ws.Ka, 256) * (ws.ldt / 2));          // FP4 nibbles: two samples per byte
     // codesT (value codes, feature-major) depends on a column only, not on which other columns are
-    // active: when every active column already has a row in the resident codesT of an earlier, wider
+    // active: when every column of the slice already has a row in the resident codesT of an earlier, wider
     // encode (TuRF iterations), that table is kept and the one-hot rows point into it (krow)
     bool reuse_ct = ds->ct_valid;
-    for (int64_t c = 0; c < pt && reuse_ct; ++c) reuse_ct = ds->ct_pos[ws.p_tcol.ptr[c]] >= 0;
+    for (int64_t c = a0; c < a1 && reuse_ct; ++c) reuse_ct = ds->ct_pos[ws.p_tcol.ptr[c]] >= 0;
     if (reuse_ct) {
-        ws.p_tpos.reserve(pt);
-        for (int64_t c = 0; c < pt; ++c) ws.p_tpos.ptr[c] = ds->ct_pos[ws.p_tcol.ptr[c]];
-        ws.tpos.reserve(pt);
+        ws.p_tpos.reserve(std::max<int64_t>(pa, 1));
+        for (int64_t c = a0; c < a1; ++c) ws.p_tpos.ptr[c - a0] = ds->ct_pos[ws.p_tcol.ptr[c]];
+        ws.tpos.reserve(std::max<int64_t>(pa, 1));
     } else {
-        ws.codesT.reserve((size_t)pt * ws.ldt + 512);   // slack: the accumulation epilogue reads whole 128-byte runs
+        ws.codesT.reserve((size_t)pa * ws.ldt + 512);   // slack: the accumulation epilogue reads whole 128-byte runs
         ds->ct_pos.assign(ds->p, -1);
-        for (int64_t c = 0; c < pt; ++c) ds->ct_pos[ws.p_tcol.ptr[c]] = (int32_t)c;
+        for (int64_t c = a0; c < a1; ++c) ds->ct_pos[ws.p_tcol.ptr[c]] = (int32_t)(c - a0);
         ds->ct_valid = true;
     }
     if (ws.have_codes) ws.codes.reserve((size_t)n * ws.ldc);
-    ws.krow.reserve(ws.K);
+    ws.krow.reserve(std::max<int64_t>(ws.Ka, 256));
     cudaStream_t st = ds->stream;
     FS_CUDA(cudaMemcpyAsync(ws.tcol.ptr, ws.p_tcol.ptr, pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     FS_CUDA(cudaMemcpyAsync(ws.tout.ptr, ws.p_tout.ptr, pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     FS_CUDA(cudaMemcpyAsync(ws.toff.ptr, ws.p_toff.ptr, (pt + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    if (reuse_ct) FS_CUDA(cudaMemcpyAsync(ws.tpos.ptr, ws.p_tpos.ptr, pt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (reuse_ct && pa > 0) FS_CUDA(cudaMemcpyAsync(ws.tpos.ptr, ws.p_tpos.ptr, pa * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    // slice-local row offsets (the general encoder and the final reduction read them)
+    ws.p_atoff.reserve(pa + 1);
+    for (int64_t c = 0; c <= pa; ++c) ws.p_atoff.ptr[c] = ws.p_toff.ptr[a0 + c] - ws.p_toff.ptr[a0];
+    ws.atoff.reserve(pa + 1);
+    FS_CUDA(cudaMemcpyAsync(ws.atoff.ptr, ws.p_atoff.ptr, (pa + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     // the encode kernel writes every used byte of U, Wd, At and codesT exactly once; only the K
     // padding (reduced rows K_used..K) has to be cleared.  Sample padding of the feature-major
     // rows (columns n..ldt) is never read (the TMA maps are n bytes wide).
@@ -672,42 +683,56 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
         FS_CUDA(cudaMemset2DAsync(ws.U.ptr + ws.K_used / 2, Kb, 0, (size_t)(ws.K - ws.K_used) / 2, (size_t)(ws.u_hi - ws.u_lo), st));
         FS_CUDA(cudaMemset2DAsync(ws.Wd.ptr + ws.K_used / 2, Kb, 0, (size_t)(ws.K - ws.K_used) / 2, (size_t)n, st));
     }
-    if (ws.K > ws.K_used)
-        FS_CUDA(cudaMemsetAsync(ws.At.ptr + (size_t)ws.K_used * (ws.ldt / 2), 0, (size_t)(ws.K - ws.K_used) * (ws.ldt / 2), st));
-    const unsigned grid = (unsigned)(ceil_div(pt, ENC_COLS) * ceil_div(n, ENC_ROWS));
+    if (ws.Ka > ws.Ka_used)
+        FS_CUDA(cudaMemsetAsync(ws.At.ptr + (size_t)ws.Ka_used * (ws.ldt / 2), 0, (size_t)(ws.Ka - ws.Ka_used) * (ws.ldt / 2), st));
     const int as_f32 = (ds->arith == FS_ARITH_F32 && ds->dtype == FS_F64) ? 1 : 0;
     const int all_ident = ws.all_ident ? 1 : 0;
-    if (lean) {
-        // every active column holds exactly the byte values 0/1/2: lean kernel
-        onehot_encode_v3_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(ds->x), ds->ldx, ds->d_perm.ptr,
-                                                      ws.tcol.ptr, n, pt, (int64_t)Kb, ws.ldt, ws.ldc, ops ? ws.U.ptr : nullptr,
-                                                      ops ? ws.Wd.ptr : nullptr, ws.At.ptr, reuse_ct ? nullptr : ws.codesT.ptr,
-                                                      ws.have_codes ? ws.codes.ptr : nullptr,
-                                                      ops ? ws.srow.ptr : nullptr, ws.krow.ptr, ws.u_lo, ws.u_hi,
-                                                      reuse_ct ? ws.tpos.ptr : nullptr);
+    const unsigned row_tiles = (unsigned)ceil_div(n, ENC_ROWS);
+    // One fused launch when the accumulation operands cover the same columns as the distance operands;
+    // in a multi-GPU group two: the distance operands of ALL active columns (every rank needs Wd of all
+    // samples), then the accumulation operands of this rank's slice only.
+    auto launch = [&](int64_t c_lo, int64_t c_hi, bool want_dist, bool want_acc) {
+        const int64_t pc = c_hi - c_lo;
+        if (pc <= 0 || (!want_dist && !want_acc)) return;
+        const unsigned grid = (unsigned)ceil_div(pc, ENC_COLS) * row_tiles;
+        // slice-local offsets: one-hot rows from 0, codesT rows from 0
+        const int32_t *off = want_acc && c_lo == a0 ? ws.atoff.ptr : ws.toff.ptr + c_lo;
+        int8_t *Uo = want_dist ? ws.U.ptr : nullptr, *Wo = want_dist ? ws.Wd.ptr : nullptr;
+        int8_t *Ao = want_acc ? ws.At.ptr : nullptr;
+        uint8_t *Co = want_acc && !reuse_ct ? ws.codesT.ptr : nullptr;
+        uint32_t *Ko = want_acc ? ws.krow.ptr : nullptr;
+        const int32_t *To = want_acc && reuse_ct ? ws.tpos.ptr : nullptr;
+        int32_t *So = want_dist ? ws.srow.ptr : nullptr;
+        uint8_t *codes = ws.have_codes && want_dist ? ws.codes.ptr : nullptr;
+        if (lean) {
+            onehot_encode_v3_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(ds->x), ds->ldx, ds->d_perm.ptr,
+                                                          ws.tcol.ptr + c_lo, n, pc, (int64_t)Kb, ws.ldt, ws.ldc, Uo, Wo, Ao, Co,
+                                                          codes, So, Ko, ws.u_lo, ws.u_hi, To);
+        } else {
+#define FS_ENCODE(T)                                                                                              \
+    onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,        \
+                                                  ws.tcol.ptr + c_lo, off, ds->d_vals.ptr, as_f32, n, pc, (int64_t)Kb, \
+                                                  ws.ldt, ws.ldc, Uo, Wo, Ao, Co, codes, So, Ko, all_ident, ws.u_lo,    \
+                                                  ws.u_hi, To)
+            switch (ds->dtype) {
+                case FS_U8: FS_ENCODE(uint8_t); break;
+                case FS_I8: FS_ENCODE(int8_t); break;
+                case FS_F32: FS_ENCODE(float); break;
+                case FS_F64: FS_ENCODE(double); break;
+            }
+#undef FS_ENCODE
+        }
         FS_CUDA(cudaGetLastError());
         ++*launches;
-        if (ws.dist_mode == kDistIncremental) build_removed(ds, ws, launches);
-        return;
+    };
+    if (!split) {
+        launch(0, pt, ops, true);
+    } else {
+        // (the distance launch addresses U / Wd by the GLOBAL one-hot offsets of toff, the slice launch
+        // addresses At / krow by the slice-local ones)
+        launch(0, pt, ops, false);
+        launch(a0, a1, false, true);
     }
-#define FS_ENCODE(T)                                                                                             \
-    onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,       \
-                                                  ws.tcol.ptr, ws.toff.ptr, ds->d_vals.ptr, as_f32, n, pt, (int64_t)Kb, \
-                                                  ws.ldt, ws.ldc, ops ? ws.U.ptr : nullptr,                      \
-                                                  ops ? ws.Wd.ptr : nullptr, ws.At.ptr,                          \
-                                                  reuse_ct ? nullptr : ws.codesT.ptr,                            \
-                                                  ws.have_codes ? ws.codes.ptr : nullptr,                        \
-                                                  ops ? ws.srow.ptr : nullptr, ws.krow.ptr, all_ident, ws.u_lo, ws.u_hi, \
-                                                  reuse_ct ? ws.tpos.ptr : nullptr)
-    switch (ds->dtype) {
-        case FS_U8: FS_ENCODE(uint8_t); break;
-        case FS_I8: FS_ENCODE(int8_t); break;
-        case FS_F32: FS_ENCODE(float); break;
-        case FS_F64: FS_ENCODE(double); break;
-    }
-#undef FS_ENCODE
-    FS_CUDA(cudaGetLastError());
-    ++*launches;
     // no synchronisation here: the pinned staging buffers live in the working set and are only
     // rewritten by the next build, which starts after fs_score's final stream synchronisation
     if (ws.dist_mode == kDistIncremental) build_removed(ds, ws, launches);
@@ -831,10 +856,10 @@ __global__ void __launch_bounds__(256) reduce_code_partials_kernel(const double 
 }
 
 void launch_accum_tensor(fs_dataset *ds, const WorkSet &ws, int algo, const int64_t *d_row_ids,
-                         const int64_t *h_row_ids, bool contiguous, int64_t R, const int8_t *sel, int64_t ldn,
-                         const RowInfo *rinfo, const int32_t *nbr_idx, const double *nbr_w, const int32_t *nbr_cnt,
-                         int32_t nbr_cap, double *wsum, cudaStream_t st, int *launches, double *ops) {
-    (void)sel;
+                         const int64_t *h_row_ids, bool contiguous, int64_t R, const int8_t *mask_h, const int8_t *mask_m,
+                         int64_t ldn, const RowInfo *rinfo, const int32_t *nbr_idx, const double *nbr_w,
+                         const int32_t *nbr_cnt, int32_t nbr_cap, double *wsum, cudaStream_t st, int *launches,
+                         double *ops) {
     const int64_t n = ds->n;
     if (algo == FS_RELIEFF) {
         const int64_t ctiles = ceil_div(ws.pt, 128);
@@ -852,18 +877,22 @@ void launch_accum_tensor(fs_dataset *ds, const WorkSet &ws, int algo, const int6
         *launches += 2;
         return;
     }
+    // the accumulation operands hold the columns [a0, a1) of the active list (everything outside a
+    // multi-GPU group; this rank's share inside one), one-hot rows numbered from 0
+    const int64_t pa = ws.a1 - ws.a0;
+    if (pa <= 0 || ws.Ka_used <= 0) return;
     ds->tile_desc.reserve(tc_accum_tile_desc_ints());
     // K of this GEMM is the sample index; At and the masks hold FP4 nibbles: rows of (n + 1) / 2 bytes
     const uint64_t row_bytes = (uint64_t)((n + 1) / 2);
-    const CUtensorMap tat = make_tmap_u8_sw128(ws.At.ptr, row_bytes, (uint64_t)ws.K, (uint64_t)(ws.ldt / 2), 128);
-    const CUtensorMap tmh = make_tmap_u8_sw128(ds->maskH.ptr, row_bytes, (uint64_t)R, (uint64_t)(ldn / 2), 240);
-    const CUtensorMap tmm = make_tmap_u8_sw128(ds->maskM.ptr, row_bytes, (uint64_t)R, (uint64_t)(ldn / 2), 240);
+    const CUtensorMap tat = make_tmap_u8_sw128(ws.At.ptr, row_bytes, (uint64_t)ws.Ka, (uint64_t)(ws.ldt / 2), 128);
+    const CUtensorMap tmh = make_tmap_u8_sw128(mask_h, row_bytes, (uint64_t)R, (uint64_t)(ldn / 2), 240);
+    const CUtensorMap tmm = make_tmap_u8_sw128(mask_m, row_bytes, (uint64_t)R, (uint64_t)(ldn / 2), 240);
     // every column with exactly three values: one-hot rows 2c, 2c + 1 are column c's two planes (paired epilogue)
     const int parts = launch_tc_accum(tat, tmh, tmm, n, R, d_row_ids, contiguous, ws.all_v3, rinfo, ws.codesT.ptr, ws.ldt,
-                                      ws.krow.ptr, ws.K_used, ds->tpartial, ds->tile_desc.ptr, ds->tile_consts, st, launches,
+                                      ws.krow.ptr, ws.Ka_used, ds->tpartial, ds->tile_desc.ptr, ds->tile_consts, st, launches,
                                       h_row_ids, ds->y_sorted.data(), ds->cls_start.data(), ops);
-    reduce_tensor_partials_kernel<<<(unsigned)ceil_div(ws.pt, 256), 256, 0, st>>>(ds->tpartial.ptr, parts, ws.K_used,
-                                                                                 ws.toff.ptr, ws.tout.ptr, ws.pt, wsum);
+    reduce_tensor_partials_kernel<<<(unsigned)ceil_div(pa, 256), 256, 0, st>>>(ds->tpartial.ptr, parts, ws.Ka_used,
+                                                                              ws.atoff.ptr, ws.tout.ptr + ws.a0, pa, wsum);
     FS_CUDA(cudaGetLastError());
     ++*launches;
 }

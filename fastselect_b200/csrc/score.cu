@@ -18,8 +18,8 @@ void launch_dist_tensor(fs_dataset *ds, const WorkSet &ws, int64_t r0_internal, 
                         const int64_t *d_row_ids, bool contiguous, int64_t R, int32_t *Dd, int64_t ldn,
                         cudaStream_t st, int *launches, double *ops);
 void launch_accum_tensor(fs_dataset *ds, const WorkSet &ws, int algo, const int64_t *d_row_ids,
-                         const int64_t *h_row_ids, bool contiguous, int64_t R, const int8_t *sel, int64_t ldn,
-                         const RowInfo *rinfo, const int32_t *nbr_idx, const double *nbr_w,
+                         const int64_t *h_row_ids, bool contiguous, int64_t R, const int8_t *mask_h, const int8_t *mask_m,
+                         int64_t ldn, const RowInfo *rinfo, const int32_t *nbr_idx, const double *nbr_w,
                          const int32_t *nbr_cnt, int32_t nbr_cap, double *wsum, cudaStream_t st, int *launches,
                          double *ops);
 
@@ -91,6 +91,16 @@ __global__ void count_selected_kernel(const RowInfo *rinfo, int64_t R, unsigned 
     atomicAdd(out, s);
 }
 
+// wsum[c] = sum over ranks q (in rank order: bitwise identical everywhere) of slots[q * stride + c]
+__global__ void __launch_bounds__(256) sum_rank_slots_kernel(const double *__restrict__ slots, int world, int64_t stride,
+                                                             int64_t n_kept, double *__restrict__ wsum) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_kept) return;
+    double s = 0.0;
+    for (int q = 0; q < world; ++q) s += slots[(int64_t)q * stride + c];
+    wsum[c] = s;
+}
+
 // target rows per chunk of the distance slab; have_general / have_tensor: which slabs exist
 static int64_t chunk_rows(bool have_general, bool have_tensor, int64_t ldn, int algo) {
     int64_t budget_mb = 6144;
@@ -122,39 +132,44 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
     const char *env_t = getenv("FS_B200_TENSOR");
     const bool allow_tensor = tensor_path_available() && !(env_t && env_t[0] == '0');
     const int64_t ldn = round_up(n, 128);
+    // Multi-GPU group call: this rank scores exactly its shard of the target rows, every rank does the
+    // same with the same arguments, and the shard fits one chunk on every rank (the decision must be
+    // identical everywhere: it is taken for the LARGEST shard with the most demanding slab set).  Then
+    // distances are computed symmetrically across ranks, the accumulation may be sharded by one-hot
+    // columns, and wsum_out receives the COMPLETE sums on every rank.
+    fs_comm *comm = ds->comm;
+    int64_t max_shard = 0;
+    for (int q = 0; ds->peers_on && q < ds->peers.world; ++q)
+        max_shard = std::max<int64_t>(max_shard, ds->peers.starts[q + 1] - ds->peers.starts[q]);
+    const bool group_call = ds->peers_on && comm != nullptr && comm->world > 1 && contiguous && dbg == nullptr &&
+                            targets[0] == ds->peers.starts[ds->peers.rank] &&
+                            (int64_t)targets.size() == ds->peers.starts[ds->peers.rank + 1] - ds->peers.starts[ds->peers.rank] &&
+                            round_up(max_shard, 128) <= chunk_rows(true, true, ldn, algo);
+    if (group_call) FS_REQUIRE(comm->connected, FS_ERR_STATE, "fs_score: the multi-GPU group is not connected");
+    const char *env_fs = getenv("FS_B200_FEATURE_SHARD");
+    const bool want_split = group_call && algo != FS_RELIEFF && !(env_fs && env_fs[0] == '0');
     // the one-hot distance slab of a contiguous target range that fits one chunk is kept between
     // calls: TuRF's next iteration subtracts the removed columns instead of recomputing it
     // (with peers configured the decision is taken for the largest shard, so that all ranks agree)
-    int64_t cache_rows = (int64_t)targets.size();
-    for (int q = 0; ds->peers_on && q < ds->peers.world; ++q)
-        cache_rows = std::max<int64_t>(cache_rows, ds->peers.starts[q + 1] - ds->peers.starts[q]);
+    const int64_t cache_rows = std::max<int64_t>((int64_t)targets.size(), max_shard);
     const bool slab_cacheable = contiguous && dbg == nullptr && round_up(cache_rows, 128) <= chunk_rows(true, true, ldn, algo);
     if (!slab_cacheable) ds->dd_valid = false;
     timer.begin(PH_GATHER);
     const auto prep0 = std::chrono::steady_clock::now();
     build_workset(ds, feat_idx, n_kept, allow_tensor, algo == FS_RELIEFF, targets[0], (int64_t)targets.size(),
-                  contiguous, slab_cacheable, &launches);
+                  contiguous, slab_cacheable, want_split, &launches);
     const double ms_prep = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - prep0).count();
     timer.end();
     const WorkSet &ws = ds->ws;
+    const bool fshard = group_call && ws.acc_split && ws.pt > 0;
 
     const int64_t Rmax = std::min<int64_t>(chunk_rows(ws.pg > 0, ws.pt > 0, ldn, algo), round_up((int64_t)targets.size(), 128));
     if (ws.pg > 0) ds->Dc.reserve((size_t)Rmax * ldn);
-    // the one-hot distance slab: this rank's IPC-exported slab when the call scores exactly its
-    // shard (multi-GPU symmetric mode), else the data set's own buffer
+    // the one-hot distance slab: this rank's slab inside its exchange arena for a group call (the
+    // peers store their mirrored tiles into it), else the data set's own buffer
     int32_t *Dd = nullptr;
     if (ws.pt > 0) {
-        // every rank must take the same decision (the barrier inside the pipeline has to match):
-        // the single-chunk condition is evaluated for the LARGEST shard, not for this rank's own
-        int64_t max_shard = 0;
-        for (int q = 0; ds->peers_on && q < ds->peers.world; ++q)
-            max_shard = std::max<int64_t>(max_shard, ds->peers.starts[q + 1] - ds->peers.starts[q]);
-        const bool my_shard = ds->peers_on && contiguous && dbg == nullptr &&
-                              targets[0] == ds->peers.starts[ds->peers.rank] &&
-                              (int64_t)targets.size() == ds->peers.starts[ds->peers.rank + 1] - ds->peers.starts[ds->peers.rank] &&
-                              round_up(max_shard, 128) <= chunk_rows(ws.pg > 0, ws.pt > 0, ldn, algo) &&
-                              (size_t)Rmax * ldn <= ds->peer_slab_count && Rmax >= (int64_t)targets.size();
-        if (my_shard) {
+        if (group_call) {
             Dd = ds->peer_slab;
         } else {
             ds->Dd.reserve((size_t)Rmax * ldn);
@@ -167,18 +182,39 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
                 ds->dd_valid = false;
                 ds->ws.valid = false;
                 build_workset(ds, feat_idx, n_kept, allow_tensor, algo == FS_RELIEFF, targets[0], (int64_t)targets.size(),
-                              contiguous, slab_cacheable, &launches);
+                              contiguous, slab_cacheable, want_split, &launches);
             }
             ds->dd_valid = false;
         }
     }
     ds->sel.reserve((size_t)Rmax * ldn);
     const bool use_masks = ws.pt > 0 && algo != FS_RELIEFF;
-    if (use_masks) {
-        ds->maskH.reserve((size_t)Rmax * ldn);
-        ds->maskM.reserve((size_t)Rmax * ldn);
+    // neighbour masks and row constants: inside a group call they live in the arena at the rows of this
+    // rank's shard (with a sharded accumulation every rank then receives every other rank's rows)
+    int8_t *mask_h = nullptr, *mask_m = nullptr;
+    RowInfo *rinfo_buf = nullptr;
+    char *arena = group_call ? static_cast<char *>(comm->arena) : nullptr;
+    const int64_t shard0 = group_call ? targets[0] : 0;
+    if (group_call) {
+        mask_h = reinterpret_cast<int8_t *>(arena + ds->glayout.off_mask_h) + (size_t)shard0 * (ldn / 2);
+        mask_m = reinterpret_cast<int8_t *>(arena + ds->glayout.off_mask_m) + (size_t)shard0 * (ldn / 2);
+        rinfo_buf = reinterpret_cast<RowInfo *>(arena + ds->glayout.off_rinfo) + shard0;
+    } else {
+        if (use_masks) {
+            ds->maskH.reserve((size_t)Rmax * ldn);
+            ds->maskM.reserve((size_t)Rmax * ldn);
+            mask_h = ds->maskH.ptr;
+            mask_m = ds->maskM.ptr;
+        }
+        ds->rinfo.reserve(Rmax);
+        rinfo_buf = ds->rinfo.ptr;
     }
-    ds->rinfo.reserve(Rmax);
+    // a group call accumulates into this rank's slot of the arena; the slots are summed at the end
+    double *acc_out = d_wsum;
+    if (group_call) {
+        FS_REQUIRE(n_kept <= ds->p, FS_ERR_INVALID, "fs_score: more output columns than the data set has");
+        acc_out = reinterpret_cast<double *>(arena + ds->glayout.off_w) + (size_t)comm->rank * ds->p;
+    }
     ds->row_ids.reserve(Rmax);
     int32_t nbr_cap = 0;
     if (algo == FS_RELIEFF) {
@@ -192,7 +228,7 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
     }
     ds->counters.reserve(1);
     FS_CUDA(cudaMemsetAsync(ds->counters.ptr, 0, sizeof(unsigned long long), st));
-    FS_CUDA(cudaMemsetAsync(d_wsum, 0, n_kept * sizeof(double), st));
+    FS_CUDA(cudaMemsetAsync(acc_out, 0, n_kept * sizeof(double), st));
 
     int n_chunks = 0;
     for (int64_t t0 = 0; t0 < (int64_t)targets.size(); t0 += Rmax) {
@@ -222,11 +258,10 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
             launch_dist_tensor(ds, ws, h_ids[0], h_ids, ds->row_ids.ptr, contiguous, R, Dd, ldn, st, &launches, &ops_dist);
             timer.end();
             if (ds->last_dist_exchanged) {
-                // tiles computed here were also stored into the peers' slabs and theirs into this
-                // one: every rank must have finished its distance kernel before anyone selects
-                FS_CUDA(cudaStreamSynchronize(st));
-                FS_REQUIRE(ds->barrier_fn != nullptr, FS_ERR_STATE, "peer mode without a barrier callback");
-                ds->barrier_fn(ds->barrier_ctx);
+                // tiles computed here were also stored into the peers' slabs and theirs into this one:
+                // every rank must have finished its distance kernel before anyone selects (device-side
+                // barrier over flags in the arenas: no host synchronisation inside the step)
+                comm_barrier(comm, st, &launches);
             }
         }
         if (ws.pt > 0 && slab_cacheable) {
@@ -245,19 +280,41 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
         // ---- neighbour selection
         timer.begin(PH_SELECT);
         launch_select(ds, algo, use_star, k, ds->row_ids.ptr, R, ws.pg > 0 ? ds->Dc.ptr : nullptr,
-                      ws.pt > 0 ? Dd : nullptr, ldn, ds->sel.ptr, use_masks ? ds->maskH.ptr : nullptr,
-                      use_masks ? ds->maskM.ptr : nullptr, ds->rinfo.ptr, ds->nbr_idx.ptr,
+                      ws.pt > 0 ? Dd : nullptr, ldn, ds->sel.ptr, use_masks ? mask_h : nullptr,
+                      use_masks ? mask_m : nullptr, rinfo_buf, ds->nbr_idx.ptr,
                       ds->nbr_w.ptr, ds->nbr_cnt.ptr, nbr_cap, ds->d_class_probs.ptr, st, &launches);
         if (stats) {
-            count_selected_kernel<<<32, 256, 0, st>>>(ds->rinfo.ptr, R, ds->counters.ptr);
+            count_selected_kernel<<<32, 256, 0, st>>>(rinfo_buf, R, ds->counters.ptr);
             ++launches;
         }
         timer.end();
         // ---- accumulation
-        if (ws.pt > 0) {
+        if (ws.pt > 0 && fshard) {
+            // sharded by one-hot columns: every rank sends the masks / constants of its target rows to all
+            // peers, then contracts ITS columns against the masks of ALL n targets (the complete weight of
+            // those columns, with the tiling of a single-GPU pass: bitwise the single-GPU result)
             timer.begin(PH_ACC_T);
-            launch_accum_tensor(ds, ws, algo, ds->row_ids.ptr, h_ids, contiguous, R, ds->sel.ptr, ldn,
-                                ds->rinfo.ptr, ds->nbr_idx.ptr, ds->nbr_w.ptr, ds->nbr_cnt.ptr, nbr_cap, d_wsum,
+            const size_t mrow = (size_t)(ldn / 2);
+            comm_push(comm, ds->glayout.off_mask_h + (size_t)shard0 * mrow, (size_t)R * mrow, st, &launches);
+            comm_push(comm, ds->glayout.off_mask_m + (size_t)shard0 * mrow, (size_t)R * mrow, st, &launches);
+            comm_push(comm, ds->glayout.off_rinfo + (size_t)shard0 * sizeof(RowInfo), (size_t)R * sizeof(RowInfo), st, &launches);
+            comm_barrier(comm, st, &launches);
+            if ((int64_t)ds->all_ids_h.size() != n) {
+                ds->all_ids_h.resize(n);
+                for (int64_t r = 0; r < n; ++r) ds->all_ids_h[r] = r;
+                ds->all_ids.alloc(n);
+                FS_CUDA(cudaMemcpyAsync(ds->all_ids.ptr, ds->all_ids_h.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+            }
+            launch_accum_tensor(ds, ws, algo, ds->all_ids.ptr, ds->all_ids_h.data(), true, n,
+                                reinterpret_cast<const int8_t *>(arena + ds->glayout.off_mask_h),
+                                reinterpret_cast<const int8_t *>(arena + ds->glayout.off_mask_m), ldn,
+                                reinterpret_cast<const RowInfo *>(arena + ds->glayout.off_rinfo), nullptr, nullptr, nullptr, 0,
+                                acc_out, st, &launches, &ops_accum);
+            timer.end();
+        } else if (ws.pt > 0) {
+            timer.begin(PH_ACC_T);
+            launch_accum_tensor(ds, ws, algo, ds->row_ids.ptr, h_ids, contiguous, R, mask_h, mask_m, ldn,
+                                rinfo_buf, ds->nbr_idx.ptr, ds->nbr_w.ptr, ds->nbr_cnt.ptr, nbr_cap, acc_out,
                                 st, &launches, &ops_accum);
             timer.end();
         }
@@ -269,11 +326,11 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
                 launch_relieff_gather(ws, n, xa, ds->nbr_idx.ptr, ds->nbr_w.ptr, ds->nbr_cnt.ptr, nbr_cap, R,
                                       ds->partial.ptr, n_part, st, &launches);
             else
-                launch_accum_general(ws, n, xa, ds->sel.ptr, ldn, ds->rinfo.ptr, R, ds->partial.ptr, n_part, st,
+                launch_accum_general(ws, n, xa, ds->sel.ptr, ldn, rinfo_buf, R, ds->partial.ptr, n_part, st,
                                      &launches);
             timer.end();
             timer.begin(PH_REDUCE);
-            launch_reduce_partials(ws, ds->partial.ptr, n_part, d_wsum, st, &launches);
+            launch_reduce_partials(ws, ds->partial.ptr, n_part, acc_out, st, &launches);
             timer.end();
         }
         // ---- parity/debug view of this chunk
@@ -292,7 +349,7 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
                 FS_CUDA(cudaMemcpy(hdd.data(), Dd, hdd.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
             }
             FS_CUDA(cudaMemcpy(hs.data(), ds->sel.ptr, hs.size(), cudaMemcpyDeviceToHost));
-            FS_CUDA(cudaMemcpy(hr.data(), ds->rinfo.ptr, R * sizeof(RowInfo), cudaMemcpyDeviceToHost));
+            FS_CUDA(cudaMemcpy(hr.data(), rinfo_buf, R * sizeof(RowInfo), cudaMemcpyDeviceToHost));
             for (int64_t r = 0; r < R; ++r) {
                 const int64_t t = t0 + r;
                 if (dbg->thresh) dbg->thresh[t] = hr[r].thresh;
@@ -310,7 +367,23 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
             }
         }
     }
+    if (group_call) {
+        // every rank's contribution (its share of the one-hot columns in full, or partial sums over its
+        // target rows) goes into its slot of every arena; the slots are added in rank order
+        timer.begin(PH_REDUCE);
+        const size_t slot_bytes = (size_t)round_up(n_kept * (int64_t)sizeof(double), 16);
+        comm_push(comm, ds->glayout.off_w + (size_t)comm->rank * ds->p * sizeof(double), slot_bytes, st, &launches);
+        comm_barrier(comm, st, &launches);
+        sum_rank_slots_kernel<<<(unsigned)ceil_div(n_kept, 256), 256, 0, st>>>(
+            reinterpret_cast<const double *>(arena + ds->glayout.off_w), comm->world, ds->p, n_kept, d_wsum);
+        FS_CUDA(cudaGetLastError());
+        ++launches;
+        // nobody may start the next call's memset of its slot before every rank has read all slots
+        comm_barrier(comm, st, &launches);
+        timer.end();
+    }
     FS_CUDA(cudaStreamSynchronize(st));
+    if (group_call) comm_check(comm);
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         timer.finish(stats);
@@ -395,6 +468,29 @@ int fs_debug_rows(fs_dataset *ds, int algo, int use_star, int32_t k, const float
     } catch (const std::exception &e) {
         set_error("fs_debug_rows: %s", e.what());
         return FS_ERR_OOM;
+    }
+}
+
+int fs_debug_slab(fs_dataset *ds, int64_t row_begin, int64_t nrows, int32_t *out, int64_t *info_out) {
+    try {
+        FS_REQUIRE(ds && out && nrows >= 1, FS_ERR_INVALID, "fs_debug_slab: invalid argument");
+        FS_REQUIRE(ds->dd_valid && ds->dd_buf != nullptr, FS_ERR_STATE, "fs_debug_slab: no distance slab is cached");
+        FS_REQUIRE(row_begin >= ds->dd_r0 && row_begin + nrows <= ds->dd_r0 + ds->dd_R, FS_ERR_STATE,
+                   "fs_debug_slab: rows [%lld, %lld) outside the cached range [%lld, %lld)", (long long)row_begin,
+                   (long long)(row_begin + nrows), (long long)ds->dd_r0, (long long)(ds->dd_r0 + ds->dd_R));
+        FS_CUDA(cudaSetDevice(ds->device));
+        FS_CUDA(cudaStreamSynchronize(ds->stream));
+        const int64_t ldn = round_up(ds->n, 128);
+        FS_CUDA(cudaMemcpy2D(out, ds->n * sizeof(int32_t), ds->dd_buf + (size_t)(row_begin - ds->dd_r0) * ldn,
+                             ldn * sizeof(int32_t), ds->n * sizeof(int32_t), nrows, cudaMemcpyDeviceToHost));
+        if (info_out) {
+            info_out[0] = ds->dd_r0;
+            info_out[1] = ds->dd_R;
+            info_out[2] = (int64_t)ds->dd_cols.size();
+        }
+        return FS_OK;
+    } catch (const Fail &f) {
+        return f.code;
     }
 }
 

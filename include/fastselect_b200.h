@@ -32,7 +32,7 @@ extern "C" {
 #define FS_API
 #endif
 
-#define FS_ABI_VERSION 4
+#define FS_ABI_VERSION 6
 /* distinct values tracked per column by fs_dataset_create; a column with more
  * distinct values reports FS_DISTINCT_CAP + 1 */
 #define FS_DISTINCT_CAP 16
@@ -52,7 +52,8 @@ typedef enum {
     FS_ERR_NO_DEVICE = -2,  /* no usable sm_100 GPU / driver */
     FS_ERR_CUDA = -3,       /* CUDA runtime error (message has the detail) */
     FS_ERR_OOM = -4,        /* device or host allocation failed */
-    FS_ERR_STATE = -5       /* call order violated (e.g. score before set_features) */
+    FS_ERR_STATE = -5,      /* call order violated (e.g. score before set_features) */
+    FS_ERR_TIMEOUT = -6     /* a multi-GPU barrier gave up: a rank failed or left the collective call */
 } fs_status;
 
 /* neighbour codes in fs_debug_rows' mask_out (same values as the oracle's) */
@@ -146,24 +147,68 @@ FS_API int fs_debug_rows(fs_dataset *ds, int algo, int use_star, int32_t k, cons
                   double *dist_out, double *thresh_out, int8_t *mask_out, double *wsum_out);
 
 /*
- * Multi-GPU symmetric distances (one process per GPU; optional).  The reference has no
- * multi-GPU path; target rows are sharded across ranks (fs_score's row range).  D is symmetric,
- * so with peers configured each rank computes only half of the off-diagonal blocks of its row
- * shard and stores every computed tile twice -- into its own slab and, transposed, straight into
- * the slab of the rank that owns those rows (peer stores over NVLink from the GEMM epilogue).
+ * Multi-GPU group (the reference has no multi-GPU path; its unit of parallelism is the
+ * target instance, MultiSURF.py:174).  One rank per GPU -- one process per GPU (CUDA IPC) or one host
+ * thread per GPU inside one process (peer access; see fs_multi_* below).  Every rank owns an exchange
+ * ARENA (one cudaMalloc block) that the other ranks map; all exchanges are stores into the peers' arenas
+ * over NVLink followed by a device-side barrier (flags in the arenas; no host synchronisation):
+ *   - target rows are sharded across ranks; D is symmetric, so each rank computes half of the
+ *     off-diagonal blocks of its row shard and stores every tile twice, the transposed copy straight
+ *     into the owner's slab (from the GEMM epilogue);
+ *   - MultiSURF / SURF: every rank sends the neighbour masks of its rows to all ranks and accumulates
+ *     ITS SHARE OF THE ONE-HOT COLUMNS against the masks of all targets (so the one-hot encode of the
+ *     accumulation operand is not replicated); ReliefF and continuous columns accumulate partial sums
+ *     over the rank's rows;
+ *   - the ranks' weight contributions are exchanged and added in rank order: fs_score then returns the
+ *     COMPLETE sums, bitwise identical on every rank.
  *
- * fs_dataset_peer_slab: allocate this rank's distance slab for `rows` target rows and return its
- *   CUDA IPC handle (64 bytes) for the other ranks.
- * fs_dataset_set_peers: row_starts[world + 1] = first internal row of every rank's shard (multiples
- *   of 4; row_starts[world] = n); ipc_handles = world x 64 bytes (this rank's own entry is ignored);
- *   raw_ptrs (nullable) = device pointers to use instead of opening handles (ranks emulated inside
- *   one process, for tests); barrier(ctx) must return only after EVERY rank has called it -- it
- *   is invoked inside fs_score between the distance kernel and the neighbour selection.
- *   Every rank must then call fs_score with exactly its own shard and the same arguments.
+ * fs_comm_create / fs_comm_reserve / fs_comm_connect: create this rank's communicator, make sure its
+ *   arena holds `bytes` (fs_comm_required_bytes; *changed_out = 1 when it was (re)allocated -- then the
+ *   64-byte IPC handle must be exchanged again), and map the peers: ipc_handles = world x 64 bytes, or
+ *   raw_ptrs = the peers' arena pointers (ranks inside one process).  After fs_comm_connect the CALLER
+ *   must run a host-level barrier over all ranks before the first collective call.
+ * fs_dataset_create_group: like fs_dataset_create, but this rank uploads only rows
+ *   [n * rank / world, n * (rank + 1) / world) of the host matrix (every rank passes the same x) and the
+ *   shards are replicated over NVLink.  COLLECTIVE.
+ * fs_dataset_attach_comm: row_starts[world + 1] = first internal row of every rank's shard (ascending
+ *   multiples of 4, row_starts[world] = n, no empty shard, at most ceil(n / world) + 4 rows each).
+ *   Afterwards fs_score(row_begin = row_starts[rank], row_end = row_starts[rank + 1]) is COLLECTIVE:
+ *   every rank must call it with its own shard and otherwise identical arguments, and wsum_out
+ *   receives the complete sums.  Other row ranges and fs_debug_rows stay local.  comm = NULL detaches.
+ *   A barrier that waits longer than FS_B200_BARRIER_TIMEOUT_S (default 20 s) fails the call with
+ *   FS_ERR_TIMEOUT instead of hanging; the group must then be connected again.
  */
-FS_API int fs_dataset_peer_slab(fs_dataset *ds, int64_t rows, void *ipc_handle_out, void **dev_ptr_out);
-FS_API int fs_dataset_set_peers(fs_dataset *ds, int32_t rank, int32_t world, const int64_t *row_starts,
-                         const void *ipc_handles, void *const *raw_ptrs, void (*barrier)(void *), void *barrier_ctx);
+typedef struct fs_comm fs_comm;
+FS_API int fs_comm_create(fs_comm **out, int32_t rank, int32_t world, int32_t device);
+FS_API uint64_t fs_comm_required_bytes(int64_t n, int64_t p, int32_t dtype, int32_t world, int32_t with_x);
+FS_API int fs_comm_reserve(fs_comm *comm, uint64_t bytes, void *ipc_handle_out, int32_t *changed_out);
+FS_API int fs_comm_connect(fs_comm *comm, const void *ipc_handles, void *const *raw_ptrs);
+FS_API void *fs_comm_arena(fs_comm *comm);
+FS_API uint64_t fs_comm_arena_bytes(fs_comm *comm);
+FS_API int fs_comm_connected(fs_comm *comm);
+FS_API int fs_comm_destroy(fs_comm *comm);
+FS_API int fs_dataset_create_group(fs_dataset **out, fs_comm *comm, const void *x, int dtype, int64_t n, int64_t p,
+                            int64_t row_stride_elems, const int32_t *y_enc, int32_t n_classes, void *stream);
+FS_API int fs_dataset_attach_comm(fs_dataset *ds, fs_comm *comm, const int64_t *row_starts);
+
+/*
+ * Several GPUs from ONE process (no torchrun, no torch): one host thread per device drives one rank of a
+ * multi-GPU group whose arenas are mapped through peer access.  Replaces, for a multi-GPU box, the same
+ * host callers as fs_dataset_create + fs_score (MultiSURF.py:147-162, :409-432; SURF.py:117-128;
+ * ReliefF.py:127-134).  devices[n_devices]: CUDA device ordinals (distinct, all sm_100, peer-accessible).
+ * Every device uploads 1 / n_devices of X and the shards are replicated over NVLink; fs_multi_score
+ * returns the complete weight sums (the value a single-GPU fs_score over all rows returns).
+ * Communicators (arenas, peer mappings, streams) are cached per device list for the life of the process.
+ */
+typedef struct fs_multi fs_multi;
+FS_API int fs_multi_create(fs_multi **out, const void *x, int dtype, int64_t n, int64_t p, int64_t row_stride_elems,
+                    const int32_t *y_enc, int32_t n_classes, const int32_t *devices, int32_t n_devices);
+FS_API int fs_multi_world(const fs_multi *m);        /* ranks in use (fewer than n_devices for tiny data sets) */
+FS_API int fs_multi_column_stats(const fs_multi *m, double *col_min, double *col_max, int32_t *n_distinct);
+FS_API int fs_multi_set_features(fs_multi *m, const uint8_t *is_discrete, const float *recip, int arith);
+FS_API int fs_multi_score(fs_multi *m, int algo, int use_star, int32_t k, const float *class_probs,
+                   const int64_t *feat_idx, int64_t n_kept, double *wsum_out, fs_stats *stats);
+FS_API int fs_multi_destroy(fs_multi *m);
 
 /*
  * Joint-count path: pairwise statistics of DISCRETE columns from their
@@ -197,6 +242,16 @@ FS_API int fs_joint_matrix(fs_dataset *ds, int kind, double log_base, const int6
                     int64_t pos_begin, int64_t pos_end, double *out, int out_on_device, fs_stats *stats);
 FS_API int fs_joint_tables(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, const int64_t *pairs, int64_t m,
                     int64_t *tables_out);
+
+/*
+ * Parity/debug view of the RESIDENT one-hot distance slab fs_score keeps between calls for TuRF's
+ * incremental update (d_ij -= sum over removed columns, TuRF.py:99-113): the integer mismatch counts
+ * of internal target rows [row_begin, row_begin + nrows) against all n samples (internal order), as
+ * left by the last fs_score call.  out: host int32 [nrows * n].  FS_ERR_STATE when no slab is cached
+ * or the rows are outside the cached range.  `info_out` (nullable, int64[3]) receives the first cached
+ * row, the number of cached rows and the number of one-hot columns the slab sums over.
+ */
+FS_API int fs_debug_slab(fs_dataset *ds, int64_t row_begin, int64_t nrows, int32_t *out, int64_t *info_out);
 
 /* Internal order: perm_out[r] = original index of internal row r ([n]). */
 FS_API int fs_dataset_row_order(const fs_dataset *ds, int64_t *perm_out);

@@ -247,49 +247,6 @@ def test_incremental_distance_update_equals_full_recompute(native, monkeypatch, 
     assert inc[3][1]["ops_dist_tensor"] == 0 and full[3][1]["ops_dist_tensor"] > 0
 
 
-@pytest.mark.parametrize("starts", [[0, 448, 900], [0, 256, 900], [0, 300, 600, 900]])
-def test_symmetric_distances_across_emulated_ranks(native, starts):
-    """Multi-GPU symmetric distances: every rank computes half of the off-diagonal super-blocks of
-    its row shard and stores each tile also (transposed) into the owner's slab.  Ranks are emulated
-    inside one process on one GPU (raw slab pointers instead of CUDA IPC handles; the barrier of
-    rank r runs rank r + 1): partial weight sums must be bitwise those of the plain row-range path."""
-    n, p = 900, 700
-    x, y = _mixed_cardinality_genotypes(39, n, p)
-    isd = np.ones(p, bool)
-    recip = np.ones(p, np.float32)
-    world = len(starts) - 1
-    sets = []
-    for r in range(world):
-        ds = native.Dataset(x, y.astype(np.int32), 2)
-        ds.set_features(isd, recip, native.FS_ARITH_F32)
-        sets.append(ds)
-    try:
-        ptrs = [sets[r].peer_slab(starts[r + 1] - starts[r])[1] for r in range(world)]
-        got, stats = {}, {}
-
-        def run(r):
-            got[r], stats[r] = sets[r].score(native.FS_MULTISURF, use_star=True, row_begin=starts[r],
-                                             row_end=starts[r + 1], want_stats=True)
-
-        for r in range(world):
-            nxt = (lambda q: (lambda: run(q + 1)))(r) if r + 1 < world else (lambda: None)
-            sets[r].set_peers(r, world, starts, raw_ptrs=ptrs, barrier=nxt)
-        run(0)
-        with native.Dataset(x, y.astype(np.int32), 2) as plain:
-            plain.set_features(isd, recip, native.FS_ARITH_F32)
-            full_ops = 0.0
-            for r in range(world):
-                want, st = plain.score(native.FS_MULTISURF, use_star=True, row_begin=starts[r], row_end=starts[r + 1],
-                                       want_stats=True)
-                assert np.array_equal(got[r], want), r
-                full_ops += st["ops_dist_tensor"]
-        # well under the full distance work (diagonal and ragged super-blocks are computed in full)
-        assert sum(stats[r]["ops_dist_tensor"] for r in range(world)) < 0.9 * full_ops
-    finally:
-        for ds in sets:
-            ds.close()
-
-
 def _balanced_2_and_4_valued(seed, n, p):
     """As many 2-valued as 4-valued byte columns and nothing else: two reduced one-hot rows per column ON
     AVERAGE with identity value codes, which is not the 0/1/2 case the lean encoder hard-codes."""

@@ -175,11 +175,16 @@ import os, sys
 import numpy as np
 import torch.distributed as dist
 sys.path.insert(0, {root!r})
-from fastselect_b200._shard import score_sharded, shard_rows, dist_info
+from fastselect_b200._shard import score_sharded, shard_rows, dist_info, enable_distributed, group_comm
 from oracle import ref_oracle as R
 from datasets import mixed
 
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+# sharding across the process group is OPT-IN: without it a fit inside a torchrun job stays local
+assert dist_info() == (0, 1)
+enable_distributed()
+assert dist_info() == (dist.get_rank(), 2)
+assert group_comm(61, 18, np.float32, np.zeros(61, np.int32)) is None      # gloo: no multi-GPU group, allreduce path
 x, y = mixed(3, 61, 18, 3)
 x32, recip, isd = R.multisurf_prep(x, 10)
 yc = np.unique(y, return_inverse=True)[1].astype(np.int64)

@@ -147,6 +147,8 @@ from fastselect_b200._shard import joint_sharded, shard_triangle
 from oracle import ref_oracle as R
 
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+from fastselect_b200._shard import enable_distributed
+enable_distributed()          # sharding across the process group is opt-in
 rs = np.random.RandomState(5)
 x = rs.randint(0, 4, (90, 23)); y = rs.randint(0, 3, 90)
 xa = np.concatenate([x, y[:, None]], axis=1)
