@@ -35,6 +35,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "multisurf_fit_pair_features_per_s"
 UNIT = "sample-pair*features/s"
+WORKLOAD_SHAPES = {"c3": (4000, 100_000), "c2": (10_000, 10_000), "c4": (20_000, 50_000), "c4surf": (20_000, 50_000),
+                   "c5": (20_000, 500_000)}
 
 
 # --------------------------------------------------------------------------- #
@@ -54,6 +56,9 @@ def make_workload(name, n_gpus, scaling, n_override=None, p_override=None, rows=
     elif name == "c4":
         n, p = 20_000, 50_000
         algo, star = "MultiSURF", True
+    elif name == "c4surf":
+        n, p = 20_000, 50_000
+        algo, star = "SURF", True
     else:
         raise SystemExit(f"unknown workload {name}")
     if n_override:
@@ -77,11 +82,15 @@ def make_workload(name, n_gpus, scaling, n_override=None, p_override=None, rows=
         x[:, :h] = rs.randint(0, 3, (n, h))
         x[:, h:] = rs.standard_normal((n, p - h)).astype(np.float32)
         y = np.zeros(n, np.int64)
-        y[(x[:, 25] == 1) & (x[:, 75] == 1)] = 1
+        y[(x[:, 25 % h] == 1) & (x[:, 75 % h] == 1)] = 1
         need = n // 2 - int(y.sum())
         y[rs.choice(np.flatnonzero(y == 0), need, replace=False)] = 1
         x[:, h] += 1.0 * y
-        desc = f"C4: MultiSURF* on mixed {n} x {p} (half genotype, half gaussian)"
+        if name == "c4surf":
+            x = x.astype(np.float64)           # SURF validates X to float64 (SURF.py:330-332)
+            desc = f"C4: SURF* on mixed float64 {n} x {p} (half genotype, half gaussian)"
+        else:
+            desc = f"C4: MultiSURF* on mixed {n} x {p} (half genotype, half gaussian)"
     return dict(name=name, x=x, y=y, n=n, p=p, algo=algo, star=star, desc=desc)
 
 
@@ -96,7 +105,7 @@ def make_c5(n, p, rows=None):
         x[b0:b1] = np.random.default_rng([44, b0 // 1000]).integers(0, 3, size=(b1 - b0, p), dtype=np.int8)
     rs = np.random.RandomState(44)
     y = np.zeros(m, np.int64)
-    y[(x[:, 25] == 1) & (x[:, 75] == 1)] = 1
+    y[(x[:, 25 % p] == 1) & (x[:, 75 % p] == 1)] = 1
     need = m // 2 - int(y.sum())
     if need > 0:
         y[rs.choice(np.flatnonzero(y == 0), need, replace=False)] = 1
@@ -121,6 +130,8 @@ def make_estimator(w):
 
     if w["algo"] == "ReliefF":
         return fsb.ReliefF(n_features_to_select=10, n_neighbors=10, backend="gpu")
+    if w["algo"] == "SURF":
+        return fsb.SURF(n_features_to_select=10, backend="gpu", use_star=w["star"])
     return fsb.MultiSURF(n_features_to_select=10, backend="gpu", use_star=w["star"])
 
 
@@ -190,8 +201,11 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------- #
 # CPU baseline (oracle port on a bounded sample)
 # --------------------------------------------------------------------------- #
-def cpu_sample(w, n_s=2000, p_s=5000):
-    n_s, p_s = min(n_s, w["n"], w["x"].shape[0]), min(p_s, w["p"])
+def cpu_sample(w, units=2.0e10):
+    """Bounded CPU sample of the workload: ALL n samples (the neighbour statistics depend on n) and the
+    first p_s columns, p_s sized for about `units` sample-pair*features (~10 s on 16 host threads)."""
+    n_s = min(w["n"], w["x"].shape[0])
+    p_s = int(max(32, min(w["p"], units / (float(n_s) * n_s))))
     return w["x"][:n_s, :p_s], w["y"][:n_s], n_s, p_s
 
 
@@ -204,6 +218,11 @@ def run_cpu_port(w, xs, ys):
         x32, y_enc, cp, recip, isd = R.relieff_prep(xs, ys, 10)
         t0 = time.perf_counter()
         R.relieff_scores(x32, y_enc, recip, isd, 10, cp, 0)
+    elif w["algo"] == "SURF":
+        x64, recip, isd = R.surf_prep(xs, 10)
+        y32 = np.asarray(ys).astype(np.int32)
+        t0 = time.perf_counter()
+        R.surf_scores(x64, y32, recip, isd, w["star"], sum_mode=2)
     else:
         x32, recip, isd = R.multisurf_prep(xs, 10)
         yc = np.unique(ys, return_inverse=True)[1].astype(np.int64)
@@ -219,7 +238,7 @@ def cpu_baseline(w):
     xs, ys, n_s, p_s = cpu_sample(w)
     dt = run_cpu_port(w, xs, ys)
     return {"value": n_s * n_s * p_s / dt, "unit": UNIT, "cores": R.max_threads(), "kind": "port",
-            "sample": f"first {n_s} samples x {p_s} features of the workload, one fit, {dt:.2f} s"}
+            "sample": f"all {n_s} samples x first {p_s} features of the workload, one fit, {dt:.2f} s"}
 
 
 def reference_arm(args):
@@ -232,18 +251,26 @@ def reference_arm(args):
 
     R.build()
     R.set_threads(os.cpu_count() or 1)
-    w = make_workload(args.workload, 1, "weak", args.n, args.p, rows=2000)
+    # the same n as the own arm's single-GPU workload; only as many columns as a bounded CPU step needs
+    n_full, p_full = WORKLOAD_SHAPES[args.workload]
+    n_full, p_full = args.n or n_full, args.p or p_full
+    p_gen = int(max(32, min(p_full, 2.0e10 / (float(n_full) * n_full))))
+    w = make_workload(args.workload, 1, "weak", n_full, p_gen)
     xs, ys, n_s, p_s = cpu_sample(w)
     for _ in range(args.warmup):
         run_cpu_port(w, xs[:200], ys[:200])
     t = sum(run_cpu_port(w, xs, ys) for _ in range(args.steps))
     value = args.steps * n_s * n_s * p_s / t
+    desc = w["desc"].replace(f"x {p_gen}", f"x {p_full}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (CPU)",
-            "data": "synthetic", "config": {"workload": w["desc"], "n": w["n"], "p": w["p"]},
+            "data": "synthetic",
+            "config": {"workload": desc + f" -- CPU sample per step: all {n_s} samples x first {p_s} features "
+                                          "(throughput in the same unit; the full width would take hours)",
+                       "n": n_full, "p": p_full, "sample_n": n_s, "sample_p": p_s},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": R.max_threads(), "kind": "port",
-                             "sample": f"first {n_s} samples x {p_s} features per step"},
+                             "sample": f"all {n_s} samples x first {p_s} features per step"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -263,17 +290,18 @@ def load_traffic(workload):
 # --------------------------------------------------------------------------- #
 # own arm
 # --------------------------------------------------------------------------- #
-def own_arm(args):
+def init_ranks():
+    """One process per GPU under torchrun (NCCL only carries the 64-byte arena handles); returns
+    (rank, local_rank, world, barrier)."""
     import torch
     import torch.distributed as dist
 
+    import fastselect_b200 as fsb
     from fastselect_b200 import _native
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.gpus != world and world == 1 and args.gpus > 1:
-        raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
     _native.load()
     if _native.device_count() < 1:
         raise SystemExit("bench.py: no usable sm_100 GPU (there is no CPU fallback)")
@@ -282,31 +310,118 @@ def own_arm(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        fsb.enable_distributed()          # every rank fits the SAME X, y: shard the fit across the group
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    w = make_workload(args.workload, world, args.scaling, args.n, args.p)
-    n, p = w["n"], w["p"]
-    est = make_estimator(w)
-    peaks = {}
+    return rank, local_rank, world, barrier
+
+
+def load_peaks():
+    """Roofline denominators: MEASURED_PEAKS.json (driver-written: HBM copy, cuBLAS bf16) and the FP4
+    tensor peak measured with tools/fp4_peak.cu on this pool's B200 (profiles/r02_fp4_peak.json)."""
+    peaks, fp4 = {}, {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    try:
+        for sh in json.load(open(os.path.join(ROOT, "profiles", "r02_fp4_peak.json")))["shapes"]:
+            if sh["cta_group"] == 1 and sh["n"] == 256:
+                fp4 = {"burst": 1e3 * sh["burst_pops"], "sustained": 1e3 * sh["sustained_pops"]}
+    except Exception:
+        pass
+    return peaks, fp4
 
-    # ---- resident-data timing: the estimator's own session, kept open
+
+def fp4_denominator(peaks, fp4, burst):
+    if fp4:
+        return fp4["burst" if burst else "sustained"], ("measured tcgen05 kind::mxf4 peak, %s (tools/fp4_peak.cu, profiles/r02_fp4_peak.json)"
+                                                        % ("burst" if burst else "sustained 4 s"))
+    bf16 = peaks.get("bf16_tflops" if burst else "bf16_tflops_sustained", 1590.0 if burst else 1400.0)
+    return 4.0 * bf16, "4 x cuBLAS bf16 (no measured FP4 peak file)"
+
+
+def parity_check(w, est_factory, weights, world, rank, barrier, n_targets=16):
+    """The timed run's weights against (a) the other ranks' (must be identical), (b) a plain single-GPU
+    run of the same data on rank 0 (bitwise for one-hot columns), (c) the CPU oracle on `n_targets`
+    targets through fs_debug_rows on rank 0."""
+    import torch
+    import torch.distributed as dist
+
+    import fastselect_b200 as fsb
+    from fastselect_b200 import _native
+    from oracle import ref_oracle as R
+
+    out = {"ranks_identical": True}
+    if world > 1:
+        t = torch.from_numpy(weights.astype(np.float64)).cuda()
+        hi, lo = t.clone(), t.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        out["ranks_identical"] = bool(torch.equal(hi, lo))
+    if rank == 0:
+        fsb.enable_distributed(False)              # a plain one-GPU session on rank 0; the other ranks wait
+        try:
+            R.set_threads(os.cpu_count() or 1)
+            sess, _ = est_factory()._open_session(w["x"], w["y"])
+            with sess:
+                single = sess.score()
+                tg = np.sort(np.random.RandomState(7).choice(w["n"], min(n_targets, w["n"]), replace=False))
+                got = sess.ds.debug_rows(sess.algo, tg, use_star=sess.use_star, k=sess.k, class_probs=sess.class_probs)
+                x_dev_dtype = w["x"]
+            out["equals_single_gpu"] = "bitwise" if np.array_equal(single, weights) else (
+                "allclose(rtol 1e-6)" if np.allclose(single, weights, rtol=1e-6, atol=1e-9) else "MISMATCH")
+            if w["algo"] == "MultiSURF" and x_dev_dtype.dtype in (np.int8, np.uint8):
+                want = R.multisurf_targets_bytes(w["x"], w["y"], w["star"], tg)
+            elif w["algo"] == "MultiSURF":
+                x32, recip, isd = R.multisurf_prep(w["x"], 10)
+                want = R.multisurf_targets(x32, np.unique(w["y"], return_inverse=True)[1], recip, isd, w["star"], tg)
+            elif w["algo"] == "SURF":
+                x64, recip, isd = R.surf_prep(w["x"], 10)
+                want = R.surf_targets(x64, np.asarray(w["y"]).astype(np.int32), recip, isd, w["star"], tg, sum_mode=2)
+            else:
+                x32, y_enc, cp, recip, isd = R.relieff_prep(w["x"], w["y"], 10)
+                want = R.relieff_targets(x32, y_enc, recip, isd, 10, cp, tg, tie_mode=0)
+            ok = bool(np.array_equal(got["mask"], want["mask"])) and bool(
+                np.allclose(got["wsum"], want["wsum"], rtol=1e-5, atol=1e-7 * len(tg) * max(1.0, float(np.abs(want["wsum"]).max()))))
+            exact = bool(np.array_equal(got["dist"], want["dist"]))
+            out.update(oracle_targets=int(len(tg)), oracle_neighbour_sets_and_weights="ok" if ok else "MISMATCH",
+                       oracle_distances="bit-exact" if exact else
+                       ("allclose(rtol 2e-7)" if np.allclose(got["dist"], want["dist"], rtol=2e-7, atol=1e-12) else "MISMATCH"))
+        finally:
+            fsb.enable_distributed(world > 1)
+    barrier()
+    out["ok"] = bool(out["ranks_identical"]) and "MISMATCH" not in json.dumps(out)
+    return out
+
+
+def own_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from fastselect_b200 import _native
     from fastselect_b200._shard import shard_rows
 
+    rank, local_rank, world, barrier = init_ranks()
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    w = make_workload(args.workload, world, args.scaling, args.n, args.p)
+    n, p = w["n"], w["p"]
+    est = make_estimator(w)
+    peaks, fp4 = load_peaks()
+
+    # ---- resident-data timing: the estimator's own session, kept open
     # host inputs live in pinned memory, so the e2e leg's upload runs at PCIe speed
     x_pinned = torch.from_numpy(w["x"]).pin_memory()
     x_in = x_pinned.numpy()
-    sess, _ = est._open_session(x_in, w["y"])
-    lo, hi = shard_rows(n, world, rank, sess.row_align)
-    sess_peers = bool(sess.peers)
-    buf = torch.empty(p, dtype=torch.float64, device="cuda")
+    sess, _ = est._open_session(x_in, w["y"])         # N > 1: collective (1 / N of X uploaded per rank, NVLink replication)
+    collective = bool(sess.collective)
+    lo, hi = sess.ds.shard if collective else shard_rows(n, world, rank, sess.row_align)
+    buf = torch.empty(p, dtype=torch.float64, device=torch.device("cuda", local_rank))
     last_stats = {}
 
     def step():
@@ -315,8 +430,8 @@ def own_arm(args):
         nonlocal last_stats
         _, last_stats = sess.ds.score(sess.algo, sess.use_star, sess.k, sess.class_probs, None, lo, hi,
                                       out_device_ptr=buf.data_ptr(), want_stats=True)
-        if world > 1:
-            dist.all_reduce(buf)
+        if world > 1 and not collective:
+            dist.all_reduce(buf)          # fallback without peer access: partial sums over the rank's rows
 
     for _ in range(args.warmup):
         step()
@@ -345,97 +460,128 @@ def own_arm(args):
 
     # ---- end to end through the estimator API from host buffers
     e2e_steps = max(1, min(args.steps, 3))
-    make_estimator(w).fit(x_in[: min(n, 256), : min(p, 512)], w["y"][: min(n, 256)])   # warm the API path
-    for _ in range(2 if n * p <= 2_000_000_000 else 0):
-        make_estimator(w).fit(x_in, w["y"])        # untimed full-size fits: device pool and pinned staging grown
+    for _ in range(2 if n * p <= 2_000_000_000 else 1):
+        make_estimator(w).fit(x_in, w["y"])        # untimed full-size fits: device pool, arenas and pinned staging grown
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         fitted = make_estimator(w).fit(x_in, w["y"])
     barrier()
     dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    # the same from PAGEABLE host memory (what a caller's numpy array usually is)
+    x_page = np.array(x_in)
+    barrier()
+    t0 = time.perf_counter()
+    make_estimator(w).fit(x_page, w["y"])
+    barrier()
+    dt_page = time.perf_counter() - t0
+    del x_page
+    tt = torch.tensor([dt, dt_page], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dt = float(tt.item())
+    dt, dt_page = float(tt[0].item()), float(tt[1].item())
     e2e_value = units * e2e_steps / dt
-    h2d = int(x_in.nbytes + 4 * n + p * 5 + p * 4)
+    rows_up = n // world if collective else n           # rows this rank copies over PCIe
+    h2d = int(rows_up * x_in.shape[1] * x_in.itemsize + 4 * n + p * 5 + p * 4)
     d2h = int(p * (8 + 8 + 4) + p * 8)
-    same = bool(np.allclose(fitted.feature_importances_, weights, rtol=1e-6, atol=1e-9))
+    same = bool(np.array_equal(fitted.feature_importances_, weights))
+
+    # ---- parity of the timed run (every rank takes part in the collectives; rank 0 runs the checks)
+    w_in = dict(w, x=x_in)
+    parity = parity_check(w_in, lambda: make_estimator(w), weights, world, rank, barrier) if not args.no_parity else None
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (per-phase CUDA events from fs_stats)
+    # ---- rooflines (per-phase CUDA events from fs_stats, on the stream the kernels run on)
     steps = args.steps
     phases = {k_: agg.get(k_, 0.0) / steps for k_ in ("ms_gather", "ms_dist_tensor", "ms_dist_general", "ms_select",
                                                       "ms_accum_tensor", "ms_accum_general", "ms_reduce", "ms_total",
                                                       "ms_host_prep")}
     rows = hi - lo
-    u_rank = float(rows) * n * p
-    top = max(("ms_dist_tensor", "ms_dist_general", "ms_accum_tensor", "ms_accum_general"), key=lambda q: phases[q])
-    # tensor peak: MEASURED_PEAKS.json has the cuBLAS bf16 figure as a burst (kernel timed alone, SM
-    # clocks at max) and sustained under the power cap; int8 dense is nominally 2 x bf16 on B200.
-    # Use the burst figure when the kernels run for milliseconds (steps under 100 ms), the
-    # sustained one for second-scale steps; the clocks sampled during the timed region are in `clocks`.
     clk = sampler.summary()
-    at_max = (ms / steps) < 100.0          # millisecond-scale kernels: burst; second-scale steps: sustained
-    bf16 = peaks.get("bf16_tflops" if at_max else "bf16_tflops_sustained", 1590.0 if at_max else 1400.0)
-    peak_src = ("2 x measured %s bf16 (MEASURED_PEAKS.json)" % ("burst" if at_max else "sustained")) if peaks \
-        else "2 x fallback bf16 (%s)" % ("1.59 PF burst" if at_max else "1.4 PF sustained")
+    burst = (ms / steps) < 100.0          # millisecond-scale kernels: burst peak; second-scale steps: sustained
+    fp4_peak, peak_src = fp4_denominator(peaks, fp4, burst)
     hbm = peaks.get("hbm_gbs", 6650.0)
-    # both one-hot GEMMs run on tcgen05 kind::mxf4 (e2m1 operands, FP32 accumulation): dense FP4 is
-    # nominally 4 x bf16 on B200; MEASURED_PEAKS.json has no FP4 entry, so the denominator is
-    # 4 x the measured cuBLAS bf16 figure
-    fp4_peak = 4.0 * bf16
-    peak_src = peak_src.replace("2 x", "4 x")
     traffic = load_traffic(args.workload if world == 1 else None)
+    st_avg = {k_: agg.get(k_, 0) / steps for k_ in ("n_tensor_cols", "n_general_cols", "onehot_k", "pairs_selected")}
+    pt, pg, kk = st_avg["n_tensor_cols"], st_avg["n_general_cols"], st_avg["onehot_k"]
     kernels = {}
+    # tensor kernels.  USEFUL operations = the contraction the algebra needs (2 per MAC): distances
+    # rows x n x K over the reduced one-hot rows, halved when the symmetric half is skipped; accumulation
+    # this rank's one-hot rows x all their (target, sample) pairs once.  ISSUED = what went to the tensor
+    # pipe (tile padding included; fs_stats).  SURVEY 8(d)'s symmetric-free 3-plane figure (6 ops/u) beside.
+    k_acc = kk / world if collective and w["algo"] != "ReliefF" else kk
+    r_acc = n if collective and w["algo"] != "ReliefF" else rows
+    useful = {"ms_dist_tensor": 2.0 * rows * n * kk * (0.5 if (world == 1 or collective) else 1.0),
+              "ms_accum_tensor": 2.0 * k_acc * r_acc * n}
     for ph, key in (("ms_dist_tensor", "ops_dist_tensor"), ("ms_accum_tensor", "ops_accum_tensor")):
-        if phases[ph] > 0:
-            # operations actually issued to the tensor pipe (fs_stats), not the 6/u of SURVEY 8d:
-            # the reduced one-hot operands need 2 MAC per (pair, 3-valued feature) and symmetric tiles half of that
-            ex = agg.get(key, 0.0) / steps / (phases[ph] / 1e3) / 1e12
-            kernels[ph] = {"bound": "tensor", "achieved": ex, "peak": fp4_peak, "unit": "TOP/s fp4 (e2m1, exact integers)",
-                           "frac": ex / fp4_peak, "survey_algorithmic_rate": 6.0 * u_rank / (phases[ph] / 1e3) / 1e12,
-                           "traffic": traffic.get(ph)}
-    if phases["ms_gather"] > 0 and agg.get("onehot_k", 0) > 0:
-        kk = agg["onehot_k"] / steps
-        pt = agg["n_tensor_cols"] / steps
-        # encode: raw columns read once; U (this rank's rows), Wd, At as FP4 nibbles (K / 2 bytes per
-        # sample each) and codesT (n x pt) written once
-        byts = n * pt * w["x"].itemsize + (rows + 2.0 * n) * kk / 2.0 + n * pt
+        if phases[ph] > 0 and agg.get(key, 0) > 0:
+            sec = phases[ph] / 1e3
+            ach = useful[ph] / sec / 1e12
+            kernels[ph] = {"bound": "tensor", "achieved": ach, "peak": fp4_peak, "unit": "TOP/s fp4 (e2m1, exact integers)",
+                           "frac": ach / fp4_peak, "issued_rate": agg[key] / steps / sec / 1e12,
+                           "survey_algorithmic_rate": 6.0 * rows * n * pt / sec / 1e12, "traffic": traffic.get(ph)}
+    if phases["ms_gather"] > 0 and kk > 0:
+        # encode: raw columns read once; U (this rank's rows), Wd (all rows) and this rank's share of At as FP4
+        # nibbles (K / 2 bytes per sample) and of codesT written once
+        share = 1.0 / world if collective and w["algo"] != "ReliefF" else 1.0
+        byts = n * pt * w["x"].itemsize * (1.0 + (share if share < 1 else 0.0)) + (rows + n) * kk / 2.0 + share * (n * kk / 2.0 + n * pt)
         gbs = byts / (phases["ms_gather"] / 1e3) / 1e9
         kernels["ms_gather"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                                 "traffic": traffic.get("ms_gather"), "note": "time includes the host-side working-set preparation (ms_host_prep)"}
-    if top.endswith("tensor"):
-        roof = dict(kernels[top], kernel=top, peak_source=peak_src)
-    else:
-        # CUDA-core kernels re-use every loaded element >= 64 times: algorithmic bytes are one
-        # read of both operand slabs plus the D slab write
-        byts = (rows + n) * p * 4.0 + rows * n * 8.0
-        achieved = byts / (phases[top] / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                "frac": achieved / hbm, "traffic": traffic.get(top),
-                "peak_source": "measured copy (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
-                "note": "issue-bound CUDA-core kernel; HBM fraction is low by construction"}
+    # CUDA-core kernels: FP32-lane issue rate: 2 lane-instructions per (pair, continuous feature)
+    # for distances, 2 per SELECTED pair and feature for the accumulation, against SMs x 128 lanes x clock
+    clock_mhz = clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0
+    issue_peak = 148 * 128 * clock_mhz * 1e6 / 1e12                       # T lane-instr/s at the clock sampled under load
+    if phases["ms_dist_general"] > 0 and pg > 0:
+        ach = 2.0 * rows * n * pg / (phases["ms_dist_general"] / 1e3) / 1e12
+        kernels["ms_dist_general"] = {"bound": "fp32-issue", "achieved": ach, "peak": issue_peak, "unit": "T lane-instr/s",
+                                      "frac": ach / issue_peak, "traffic": traffic.get("ms_dist_general"),
+                                      "note": "2 algorithmic lane-instructions per (ordered pair, continuous feature); symmetric tiles evaluate half of the pairs"}
+    if phases["ms_accum_general"] > 0 and pg > 0:
+        if w["algo"] == "ReliefF":
+            byts = st_avg["pairs_selected"] * pg * 4.0
+            gbs = byts / (phases["ms_accum_general"] / 1e3) / 1e9
+            kernels["ms_accum_general"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                           "traffic": traffic.get("ms_accum_general"),
+                                           "note": "ReliefF sparse gather: bytes of the selected neighbours' rows (n k C p x 4); mostly L2 hits"}
+        else:
+            ach = 2.0 * st_avg["pairs_selected"] * pg / (phases["ms_accum_general"] / 1e3) / 1e12
+            kernels["ms_accum_general"] = {"bound": "fp32-issue", "achieved": ach, "peak": issue_peak, "unit": "T lane-instr/s",
+                                           "frac": ach / issue_peak, "traffic": traffic.get("ms_accum_general"),
+                                           "note": "2 algorithmic lane-instructions per (selected pair, continuous feature)"}
+    top = max((q for q in ("ms_dist_tensor", "ms_dist_general", "ms_accum_tensor", "ms_accum_general") if q in kernels),
+              key=lambda q: phases[q])
+    roof = dict(kernels[top], kernel=top,
+                peak_source=peak_src if kernels[top]["bound"] == "tensor" else
+                ("148 SMs x 128 FP32 lanes x %.0f MHz (SM clock sampled during the timed region)" % clock_mhz
+                 if kernels[top]["bound"] == "fp32-issue" else "measured copy (MEASURED_PEAKS.json)"))
 
     # the CPU baseline is reported at N = 1 only (rank 0)
     cpu = cpu_baseline(w) if world == 1 else None
+    sharding = f"target rows x{world}"
+    if collective:
+        sharding += (", symmetric distance tiles / neighbour masks / weight slices stored into the peers' arenas over NVLink, "
+                     "accumulation sharded by one-hot columns, device-side barriers; 1/N of X uploaded per rank")
+    elif world > 1:
+        sharding += ", one NCCL allreduce"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": "e2m1 (FP4) one-hot / exact FP32 accum (genotype), f32 terms + f64 accum (continuous)",
             "data": "synthetic",
             "config": {"workload": w["desc"], "n": n, "p": p, "algo": w["algo"] + ("*" if w["star"] else ""),
-                       "rows_per_gpu": rows, "sharding": f"target rows x{world}, one NCCL allreduce" + (", symmetric distances via NVLink peer stores" if sess_peers else ""),
+                       "rows_per_gpu": rows, "sharding": sharding,
                        "l2": "inputs larger than L2 (no flush needed)", "step": "encode + distances + select + accumulate"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "seconds_per_fit": dt / e2e_steps, "matches_resident_run": same},
+                    "steps": e2e_steps, "seconds_per_fit": dt / e2e_steps, "matches_resident_run": same,
+                    "pageable_seconds_per_fit": dt_page, "pageable_value": units / dt_page,
+                    "note": "value: X in pinned host memory; pageable_*: the same fit from an ordinary numpy array"},
             "gpu_launches": int(agg.get("launches", 0)),
-            "roofline": roof, "kernels": kernels, "phases_ms": phases, "cpu_baseline": cpu,
+            "roofline": roof, "kernels": kernels, "phases_ms": phases, "cpu_baseline": cpu, "parity": parity,
             "top_features": fitted.top_features_.tolist(),
             "stats": {k_: int(agg[k_] / steps) for k_ in ("n_tensor_cols", "n_general_cols", "onehot_k",
                                                            "pairs_selected", "n_chunks") if k_ in agg}}
@@ -451,24 +597,8 @@ def turf_arm(args):
     import torch.distributed as dist
 
     import fastselect_b200 as fsb
-    from fastselect_b200 import _native
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    _native.load()
-    if _native.device_count() < 1:
-        raise SystemExit("bench.py: no usable sm_100 GPU (there is no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    os.environ["FASTSELECT_B200_DEVICE"] = str(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    rank, local_rank, world, barrier = init_ranks()
 
     t_gen = time.perf_counter()
     w = make_workload("c5", world, "strong", args.n, args.p)
@@ -477,11 +607,7 @@ def turf_arm(args):
     x_pinned = torch.from_numpy(w["x"]).pin_memory()
     x_in = x_pinned.numpy()
     w["x"] = x_in
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks, fp4 = load_peaks()
 
     def new_turf():
         return fsb.TuRF(fsb.MultiSURF(n_features_to_select=10, backend="gpu"), n_features_to_select=10, pct_remove=0.1)
@@ -536,6 +662,17 @@ def turf_arm(args):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     de = float(tt.item())
+    # parity of the run: identical selection on every rank and the two planted SNPs on top
+    parity = {"ranks_identical": True}
+    if world > 1:
+        tf = torch.from_numpy(np.ascontiguousarray(fitted.top_features_, np.int64)).cuda()
+        hi_, lo_ = tf.clone(), tf.clone()
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        parity["ranks_identical"] = bool(torch.equal(hi_, lo_))
+    parity["planted_snps_selected"] = bool({25, 75} <= set(fitted.top_features_.tolist()))
+    parity["note"] = "oracle parity of this shape (16 targets, first and second TuRF pass): tests/test_gpu_shapes_more.py"
+    parity["ok"] = parity["ranks_identical"] and parity["planted_snps_selected"]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -544,22 +681,23 @@ def turf_arm(args):
     steps = args.steps
     phases = {k_: agg.get(k_, 0.0) / steps for k_ in ("ms_gather", "ms_dist_tensor", "ms_select", "ms_accum_tensor",
                                                       "ms_reduce", "ms_total", "ms_host_prep")}
-    at_max = False                       # second-scale steps: sustained peak
-    bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
-    fp4_peak = 4.0 * bf16                # kind::mxf4: nominally 4 x bf16; no measured FP4 figure in MEASURED_PEAKS.json
+    fp4_peak, peak_src = fp4_denominator(peaks, fp4, burst=False)       # second-scale steps: sustained peak
     kernels = {}
-    for ph, key in (("ms_dist_tensor", "ops_dist_tensor"), ("ms_accum_tensor", "ops_accum_tensor")):
-        ex = agg.get(key, 0.0) / steps / (phases[ph] / 1e3) / 1e12
-        kernels[ph] = {"bound": "tensor", "achieved": ex, "peak": fp4_peak, "unit": "TOP/s fp4 (e2m1, exact integers)", "frac": ex / fp4_peak,
-                       "traffic": None}
+    # useful accumulation work of this rank: 2 ops per (one-hot row, target, sample), rows = 2 per active SNP,
+    # sharded by columns across the ranks; the distance kernel's useful work is dominated by the first pass
+    useful_acc = 2.0 * 2.0 * float(sum(sizes)) / world * n * n
+    useful_dist = 2.0 * 2.0 * (sizes[0] * 0.5 + float(sizes[0] - sizes[-1])) * (n / world) * n
+    for ph, key, useful in (("ms_dist_tensor", "ops_dist_tensor", useful_dist), ("ms_accum_tensor", "ops_accum_tensor", useful_acc)):
+        sec = phases[ph] / 1e3
+        kernels[ph] = {"bound": "tensor", "achieved": useful / sec / 1e12, "peak": fp4_peak, "unit": "TOP/s fp4 (e2m1, exact integers)",
+                       "frac": useful / sec / 1e12 / fp4_peak, "issued_rate": agg.get(key, 0.0) / steps / sec / 1e12, "traffic": None}
     top = max(kernels, key=lambda q: phases[q])
-    roof = dict(kernels[top], kernel=top,
-                peak_source="4 x measured sustained bf16 (MEASURED_PEAKS.json)" if peaks else "4 x fallback 1.4 PF")
+    roof = dict(kernels[top], kernel=top, peak_source=peak_src)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "e2m1 (FP4) one-hot / exact FP32 accum (genotype)", "data": "synthetic",
             "config": {"workload": w["desc"], "n": n, "p": p, "algo": "TuRF(MultiSURF)", "scoring_passes": len(sizes),
-                       "sum_p_t": int(sum(sizes)), "sharding": f"target rows x{world}, one NCCL allreduce per pass",
+                       "sum_p_t": int(sum(sizes)), "sharding": f"target rows x{world}" + (", accumulation sharded by one-hot columns, exchanges through the peers' arenas over NVLink, device-side barriers" if world > 1 else ""),
                        "l2": "inputs larger than L2 (no flush needed)",
                        "step": "one whole TuRF run: first fit + every pruning iteration (encode + distances + select + accumulate each)",
                        "timing": "host wall clock around the run (barrier + synchronize both sides), max over ranks",
@@ -568,6 +706,7 @@ def turf_arm(args):
             "e2e": {"value": units / de, "unit": UNIT, "h2d_bytes_per_step": int(x_in.nbytes + 4 * n + 9 * p),
                     "d2h_bytes_per_step": int(20 * p + 8 * sum(sizes)), "steps": 1, "seconds_per_fit": de,
                     "matches_resident_run": bool(np.array_equal(fitted.top_features_, resident.top_features_))},
+            "parity": parity,
             "gpu_launches": int(agg.get("launches", 0)), "roofline": roof, "kernels": kernels, "phases_ms": phases,
             "cpu_baseline": None, "top_features": fitted.top_features_.tolist(), "seconds_per_turf_run": dt / steps}
     print(json.dumps(line))
@@ -643,22 +782,7 @@ def joint_arm(args):
     from fastselect_b200 import _mi, _native
     from fastselect_b200._shard import shard_triangle
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    _native.load()
-    if _native.device_count() < 1:
-        raise SystemExit("bench.py: no usable sm_100 GPU (there is no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    os.environ["FASTSELECT_B200_DEVICE"] = str(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    rank, local_rank, world, barrier = init_ranks()
 
     w = make_j1(args.n or 10_000, args.p or 10_000)
     n, p = w["n"], w["p"]
@@ -769,8 +893,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5", "j1"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c4surf", "c5", "j1"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-parity", dest="no_parity", action="store_true", help="skip the oracle / single-GPU parity checks of the timed run")
     ap.add_argument("--n", type=int, default=None)
     ap.add_argument("--p", type=int, default=None)
     args = ap.parse_args()

@@ -13,16 +13,44 @@
 // an epoch to every peer and spins until every peer's epoch arrived (bounded: FS_B200_BARRIER_TIMEOUT_S,
 // default 20 s, then an error flag is raised instead of hanging the GPUs).
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
+#include <map>
 #include <mutex>
 
 #include "common.cuh"
 
 namespace fs {
 
+struct HostBarrier {
+    std::mutex mu;
+    std::condition_variable cv;
+    int world = 0, waiting = 0;
+    unsigned long long generation = 0;
+};
+
+// false on timeout (a rank never arrived)
+bool host_barrier_wait(HostBarrier *hb, double timeout_s) {
+    std::unique_lock<std::mutex> lk(hb->mu);
+    const unsigned long long gen = hb->generation;
+    if (++hb->waiting == hb->world) {
+        hb->waiting = 0;
+        ++hb->generation;
+        hb->cv.notify_all();
+        return true;
+    }
+    const bool ok = hb->cv.wait_for(lk, std::chrono::duration<double>(timeout_s), [&] { return hb->generation != gen; });
+    if (!ok) --hb->waiting;
+    return ok;
+}
+
 namespace {
 constexpr size_t kAlign = 1024;
 size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+// host barriers of in-process groups, keyed by rank 0's arena
+std::mutex g_hb_mu;
+std::map<void *, std::weak_ptr<HostBarrier>> g_host_barriers;
 
 std::mutex g_ipc_mu;
 struct IpcEntry {
@@ -111,10 +139,20 @@ __global__ void comm_barrier_kernel(CommPeers peers, uint32_t epoch, unsigned lo
 
 void comm_barrier(fs_comm *c, cudaStream_t st, int *launches) {
     if (c->world <= 1) return;
+    if (c->host_barrier && !host_barrier_wait(c->host_barrier.get(), (double)c->timeout_ns * 1e-9)) {
+        c->connected = false;
+        FS_REQUIRE(false, FS_ERR_TIMEOUT, "multi-GPU barrier timed out on the host: a rank of this process never joined the call");
+    }
     ++c->epoch;
     comm_barrier_kernel<<<1, 32, 0, st>>>(c->peers, c->epoch, c->timeout_ns);
     FS_CUDA(cudaGetLastError());
     if (launches) ++*launches;
+    // ... and nobody issues anything further before every rank's barrier kernel is in its queue (a
+    // synchronising call in between would order a late barrier kernel behind an early, spinning one)
+    if (c->host_barrier && !host_barrier_wait(c->host_barrier.get(), (double)c->timeout_ns * 1e-9)) {
+        c->connected = false;
+        FS_REQUIRE(false, FS_ERR_TIMEOUT, "multi-GPU barrier timed out on the host: a rank of this process never joined the call");
+    }
 }
 
 // Raises FS_ERR_TIMEOUT when a barrier of this call gave up (stream must be synchronised).
@@ -241,6 +279,18 @@ int fs_comm_connect(fs_comm *c, const void *ipc_handles, void *const *raw_ptrs) 
             }
             FS_REQUIRE(p != nullptr, FS_ERR_INVALID, "fs_comm_connect: rank %d has no arena", q);
             c->peers.hdr[q] = static_cast<CommHeader *>(p);
+        }
+        // ranks of one process (raw pointers) share a host barrier, found through rank 0's arena
+        c->host_barrier.reset();
+        if (raw_ptrs && c->world > 1) {
+            std::lock_guard<std::mutex> lk(g_hb_mu);
+            std::shared_ptr<HostBarrier> hb = g_host_barriers[raw_ptrs[0]].lock();
+            if (!hb || hb->world != c->world) {
+                hb = std::make_shared<HostBarrier>();
+                hb->world = c->world;
+                g_host_barriers[raw_ptrs[0]] = hb;
+            }
+            c->host_barrier = hb;
         }
         // epochs restart: every rank clears its own header, and the caller runs a host-level barrier
         // (all ranks connected) before the first collective call

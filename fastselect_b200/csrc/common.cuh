@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -240,8 +241,21 @@ struct WorkSet {
 
 }  // namespace fs
 
+namespace fs {
+// Ranks that live in ONE process (host threads; fs_multi_*, emulated ranks in the tests) also meet on the
+// host right before every device-side barrier is launched.  The GPUs are not drained -- their queues
+// keep running -- but once every thread has ISSUED its work up to the barrier, no barrier kernel can
+// spin on a peer whose host thread is still stuck in a CUDA call that implicitly synchronises the
+// process (page-locked or device allocations: CUDA programming guide, "Implicit Synchronization").
+// Ranks in separate processes (CUDA IPC) have no such coupling and never meet on the host.
+struct HostBarrier;
+bool host_barrier_wait(HostBarrier *hb, double timeout_s);
+
+}  // namespace fs
+
 struct fs_comm {
     int rank = 0, world = 1, device = 0;
+    std::shared_ptr<fs::HostBarrier> host_barrier;
     void *arena = nullptr;
     size_t arena_bytes = 0;
     void *opened[fs::kMaxRanks] = {};     // IPC mappings this communicator opened

@@ -691,9 +691,9 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     // One fused launch when the accumulation operands cover the same columns as the distance operands;
     // in a multi-GPU group two: the distance operands of ALL active columns (every rank needs Wd of all
     // samples), then the accumulation operands of this rank's slice only.
-    auto launch = [&](int64_t c_lo, int64_t c_hi, bool want_dist, bool want_acc) {
+    auto launch = [&](int64_t c_lo, int64_t c_hi, bool want_dist, bool want_acc, bool want_codes) {
         const int64_t pc = c_hi - c_lo;
-        if (pc <= 0 || (!want_dist && !want_acc)) return;
+        if (pc <= 0 || (!want_dist && !want_acc && !want_codes)) return;
         const unsigned grid = (unsigned)ceil_div(pc, ENC_COLS) * row_tiles;
         // slice-local offsets: one-hot rows from 0, codesT rows from 0
         const int32_t *off = want_acc && c_lo == a0 ? ws.atoff.ptr : ws.toff.ptr + c_lo;
@@ -703,7 +703,7 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
         uint32_t *Ko = want_acc ? ws.krow.ptr : nullptr;
         const int32_t *To = want_acc && reuse_ct ? ws.tpos.ptr : nullptr;
         int32_t *So = want_dist ? ws.srow.ptr : nullptr;
-        uint8_t *codes = ws.have_codes && want_dist ? ws.codes.ptr : nullptr;
+        uint8_t *codes = want_codes ? ws.codes.ptr : nullptr;       // sample-major value codes (ReliefF)
         if (lean) {
             onehot_encode_v3_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(ds->x), ds->ldx, ds->d_perm.ptr,
                                                           ws.tcol.ptr + c_lo, n, pc, (int64_t)Kb, ws.ldt, ws.ldc, Uo, Wo, Ao, Co,
@@ -726,12 +726,12 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
         ++*launches;
     };
     if (!split) {
-        launch(0, pt, ops, true);
+        launch(0, pt, ops, true, ws.have_codes);
     } else {
         // (the distance launch addresses U / Wd by the GLOBAL one-hot offsets of toff, the slice launch
         // addresses At / krow by the slice-local ones)
-        launch(0, pt, ops, false);
-        launch(a0, a1, false, true);
+        launch(0, pt, ops, false, ws.have_codes);
+        launch(a0, a1, false, true, false);
     }
     // no synchronisation here: the pinned staging buffers live in the working set and are only
     // rewritten by the next build, which starts after fs_score's final stream synchronisation
