@@ -192,6 +192,12 @@ struct WorkSet {
     DevBuf<int64_t> gcol;  // [pg] original column of each general column
     DevBuf<int64_t> gout;  // [pg] position in the caller's feat_idx list
     std::vector<int64_t> h_gcol, h_gout;
+    std::vector<uint8_t> h_ctype;
+    std::vector<float> h_rg;
+    // cache of the column lists of an all-columns call (see build_workset)
+    bool lists_all = false, lists_uploaded = false;
+    uint64_t lists_typing = 0, lists_version = 0;
+    int64_t lists_flags = -1, lists_n = -1;
     int64_t n_cont = 0, n_cmp = 0;
     // one-hot tensor-core path (filled by onehot.cu).  A column with V distinct values owns
     // V - 1 "reduced" one-hot rows (values 0..V-2); the last value is implied (see onehot.cu)
@@ -289,6 +295,8 @@ struct fs_dataset {
     std::vector<int32_t> cnt;
     // typing
     bool have_features = false;
+    uint64_t typing_epoch = 0;               // bumped whenever the typing (or the group's column shares) changes
+    uint64_t ct_version = ~0ull, dd_version = ~0ull;   // WorkSet::lists_version ct_pos / dd_cols were filled for
     int arith = FS_ARITH_F32;
     std::vector<uint8_t> is_discrete;
     std::vector<float> recip;

@@ -385,6 +385,12 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
     const int chunk = kChunkBytes / (ds->arith == FS_ARITH_F64 ? 8 : 4);
     ws.elem = ds->arith == FS_ARITH_F64 ? 8 : 4;
 
+    // The column lists of an all-columns call depend only on the typing (fs_dataset_set_features) and the
+    // call's flags: they are kept (host vectors, pinned staging and their device copies) until one of those
+    // changes, so that re-scoring the same data set does not walk all p columns on the host again.
+    const bool lists_ok = all && ws.lists_all && ws.lists_typing == ds->typing_epoch && ws.lists_flags == key[0] &&
+                          ws.lists_n == n_kept;
+    if (!lists_ok) {
     // split the active columns: one-hot tensor path (discrete, 2 <= V <= FS_DISTINCT_CAP),
     // continuous, and wide discrete ("compare") columns.  The tensor-path lists are written
     // straight into the pinned staging buffers the encode kernel's inputs are copied from;
@@ -471,8 +477,10 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
     // general path layout: [continuous | pad to chunk | compare | pad to chunk]
     ws.h_gcol.clear();
     ws.h_gout.clear();
-    std::vector<uint8_t> ctype;
-    std::vector<float> rg;
+    std::vector<uint8_t> &ctype = ws.h_ctype;
+    std::vector<float> &rg = ws.h_rg;
+    ctype.clear();
+    rg.clear();
     auto append = [&](const std::vector<int64_t> &cols, const std::vector<int64_t> &outs, uint8_t type) {
         if (cols.empty()) return;
         for (size_t q = 0; q < cols.size(); ++q) {
@@ -492,7 +500,7 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
     ws.pg = (int64_t)ws.h_gcol.size();
     ws.ldg = ws.pg;
     if (ws.pg > 0) {
-        ws.xg.reserve((size_t)ds->n * ws.ldg * ws.elem);
+        // (the staging vectors live in the working set: no synchronisation needed before they go out of scope)
         ws.rg.reserve(ws.ldg);
         ws.ctype.reserve(ctype.size());
         ws.gcol.reserve(ws.pg);
@@ -501,14 +509,22 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
         FS_CUDA(cudaMemcpyAsync(ws.ctype.ptr, ctype.data(), ctype.size(), cudaMemcpyHostToDevice, ds->stream));
         FS_CUDA(cudaMemcpyAsync(ws.gcol.ptr, ws.h_gcol.data(), ws.pg * sizeof(int64_t), cudaMemcpyHostToDevice, ds->stream));
         FS_CUDA(cudaMemcpyAsync(ws.gout.ptr, ws.h_gout.data(), ws.pg * sizeof(int64_t), cudaMemcpyHostToDevice, ds->stream));
+    }
+    ws.lists_all = all;
+    ws.lists_typing = ds->typing_epoch;
+    ws.lists_flags = key[0];
+    ws.lists_n = n_kept;
+    ++ws.lists_version;
+    ws.lists_uploaded = false;
+    }   // !lists_ok
+    if (ws.pg > 0) {
+        ws.xg.reserve((size_t)ds->n * ws.ldg * ws.elem);
         switch (ds->dtype) {
             case FS_U8: run_gather<uint8_t>(ds, ws, launches); break;
             case FS_I8: run_gather<int8_t>(ds, ws, launches); break;
             case FS_F32: run_gather<float>(ds, ws, launches); break;
             case FS_F64: run_gather<double>(ds, ws, launches); break;
         }
-        // the staging vectors must outlive the async copies
-        FS_CUDA(cudaStreamSynchronize(ds->stream));
     }
     ws.K = 0;
     ws.have_codes = need_codes;
@@ -643,6 +659,18 @@ int fs_dataset_set_features(fs_dataset *ds, const uint8_t *is_discrete, const fl
         set_error("fs_dataset_set_features: invalid argument");
         return FS_ERR_INVALID;
     }
+    // the same typing again (a second fit-like pass over a resident data set): the per-column decisions,
+    // the ownership bounds and the cached column lists stay; the GPU-side working set is still rebuilt
+    const bool same = ds->have_features && ds->arith == arith && (int64_t)ds->is_discrete.size() == ds->p &&
+                      memcmp(ds->is_discrete.data(), is_discrete, ds->p) == 0 &&
+                      memcmp(ds->recip.data(), recip, ds->p * sizeof(float)) == 0;
+    if (same) {
+        ds->ws.valid = false;
+        ds->dd_valid = false;
+        ds->ct_valid = false;
+        return FS_OK;
+    }
+    ++ds->typing_epoch;
     ds->is_discrete.assign(is_discrete, is_discrete + ds->p);
     ds->recip.assign(recip, recip + ds->p);
     ds->arith = arith;
@@ -691,6 +719,7 @@ int fs_dataset_attach_comm(fs_dataset *ds, fs_comm *comm, const int64_t *row_sta
             ds->peer_slab = nullptr;
             ds->dd_valid = false;
             ds->ws.valid = false;
+            ++ds->typing_epoch;
             ds->owner_bound.clear();
             return FS_OK;
         }
@@ -737,6 +766,7 @@ int fs_dataset_attach_comm(fs_dataset *ds, fs_comm *comm, const int64_t *row_sta
         ds->peers_on = true;
         ds->dd_valid = false;
         ds->ws.valid = false;
+        ++ds->typing_epoch;          // the accumulation shares changed: cached column lists are stale
         compute_owner_bounds(ds);
         return FS_OK;
     } catch (const Fail &f) {

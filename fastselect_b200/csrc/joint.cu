@@ -32,8 +32,8 @@ namespace fs {
 // onehot.cu / tc_dist.cu
 CUtensorMap make_tmap_u8_sw128(const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch_bytes,
                                uint32_t box_rows);
-void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_t K, const int32_t *srow,
-                    const int64_t *d_ids, int64_t R, int64_t n, int64_t ldd, bool symmetric, bool subtract,
+void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, const CUtensorMap *tmap_b_half, int64_t K,
+                    const int32_t *srow, const int64_t *d_ids, int64_t R, int64_t n, int64_t ldd, bool symmetric, bool subtract,
                     const DistPeers &peers, cudaStream_t st, int *launches, double *ops);
 
 namespace {
@@ -234,7 +234,8 @@ void run_joint(fs_dataset *ds, int kind, double log_base, const int64_t *feat_id
             peers.sb_base[0] = 0;
             peers.sb_base[1] = (int32_t)ceil_div(ncols, 256);
             peers.coarse_shift = 3;
-            launch_tc_dist(ta, tb, k_bytes, ds->joint_zero.ptr, ds->joint_ids.ptr, R, ncols, ldd, false, false, peers, st,
+            const CUtensorMap tbh = make_tmap_u8_sw128(base, row_bytes, ncols, pitch, 128);      // CTA pairs
+            launch_tc_dist(ta, tb, &tbh, k_bytes, ds->joint_zero.ptr, ds->joint_ids.ptr, R, ncols, ldd, false, false, peers, st,
                            &launches, &ops);
             tm.end();
         }

@@ -66,11 +66,19 @@ void run_ranks(int world, const std::function<int(int)> &fn) {
             if (rc != FS_OK) errs[r].msg = get_error();
         });
     for (auto &t : th) t.join();
+    // a rank that failed leaves the others waiting at their next barrier until it times out: report the
+    // root cause (the first error that is not a timeout) with every failing rank's message
+    int first = -1;
+    std::string all;
     for (int r = 0; r < world; ++r)
         if (errs[r].code != FS_OK) {
-            set_error("rank %d: %s", r, errs[r].msg.c_str());
-            throw Fail{errs[r].code};
+            if (first < 0 || (errs[first].code == FS_ERR_TIMEOUT && errs[r].code != FS_ERR_TIMEOUT)) first = r;
+            all += (all.empty() ? "" : " | ") + std::string("rank ") + std::to_string(r) + ": " + errs[r].msg;
         }
+    if (first >= 0) {
+        set_error("%s", all.c_str());
+        throw Fail{errs[first].code};
+    }
 }
 
 std::string key_of(const std::vector<int> &devices) {

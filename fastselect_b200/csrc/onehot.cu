@@ -20,8 +20,8 @@
 
 namespace fs {
 
-void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_t K, const int32_t *srow,
-                    const int64_t *d_ids, int64_t R, int64_t n, int64_t ldd, bool symmetric, bool subtract,
+void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, const CUtensorMap *tmap_b_half, int64_t K,
+                    const int32_t *srow, const int64_t *d_ids, int64_t R, int64_t n, int64_t ldd, bool symmetric, bool subtract,
                     const DistPeers &peers, cudaStream_t st, int *launches, double *ops);
 int tc_accum_tile_desc_ints();
 int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
@@ -651,22 +651,29 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
         ws.tpos.reserve(std::max<int64_t>(pa, 1));
     } else {
         ws.codesT.reserve((size_t)pa * ws.ldt + 512);   // slack: the accumulation epilogue reads whole 128-byte runs
-        ds->ct_pos.assign(ds->p, -1);
-        for (int64_t c = a0; c < a1; ++c) ds->ct_pos[ws.p_tcol.ptr[c]] = (int32_t)(c - a0);
+        if (ds->ct_version != ws.lists_version || (int64_t)ds->ct_pos.size() != ds->p) {
+            ds->ct_pos.assign(ds->p, -1);
+            for (int64_t c = a0; c < a1; ++c) ds->ct_pos[ws.p_tcol.ptr[c]] = (int32_t)(c - a0);
+            ds->ct_version = ws.lists_version;
+        }
         ds->ct_valid = true;
     }
     if (ws.have_codes) ws.codes.reserve((size_t)n * ws.ldc);
     ws.krow.reserve(std::max<int64_t>(ws.Ka, 256));
     cudaStream_t st = ds->stream;
-    FS_CUDA(cudaMemcpyAsync(ws.tcol.ptr, ws.p_tcol.ptr, pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    FS_CUDA(cudaMemcpyAsync(ws.tout.ptr, ws.p_tout.ptr, pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    FS_CUDA(cudaMemcpyAsync(ws.toff.ptr, ws.p_toff.ptr, (pt + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if (reuse_ct && pa > 0) FS_CUDA(cudaMemcpyAsync(ws.tpos.ptr, ws.p_tpos.ptr, pa * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    // slice-local row offsets (the general encoder and the final reduction read them)
-    ws.p_atoff.reserve(pa + 1);
-    for (int64_t c = 0; c <= pa; ++c) ws.p_atoff.ptr[c] = ws.p_toff.ptr[a0 + c] - ws.p_toff.ptr[a0];
-    ws.atoff.reserve(pa + 1);
-    FS_CUDA(cudaMemcpyAsync(ws.atoff.ptr, ws.p_atoff.ptr, (pa + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (!ws.lists_uploaded) {
+        // (skipped when the cached lists of an all-columns call are already on the device)
+        FS_CUDA(cudaMemcpyAsync(ws.tcol.ptr, ws.p_tcol.ptr, pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        FS_CUDA(cudaMemcpyAsync(ws.tout.ptr, ws.p_tout.ptr, pt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        FS_CUDA(cudaMemcpyAsync(ws.toff.ptr, ws.p_toff.ptr, (pt + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        // slice-local row offsets (the general encoder and the final reduction read them)
+        ws.p_atoff.reserve(pa + 1);
+        for (int64_t c = 0; c <= pa; ++c) ws.p_atoff.ptr[c] = ws.p_toff.ptr[a0 + c] - ws.p_toff.ptr[a0];
+        ws.atoff.reserve(pa + 1);
+        FS_CUDA(cudaMemcpyAsync(ws.atoff.ptr, ws.p_atoff.ptr, (pa + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        ws.lists_uploaded = true;
+    }
     // the encode kernel writes every used byte of U, Wd, At and codesT exactly once; only the K
     // padding (reduced rows K_used..K) has to be cleared.  Sample padding of the feature-major
     // rows (columns n..ldt) is never read (the TMA maps are n bytes wide).
@@ -789,7 +796,8 @@ void launch_dist_tensor(fs_dataset *ds, const WorkSet &ws, int64_t r0_internal, 
     }
     const CUtensorMap ta = make_tmap_u8_sw128(a_rows, K, R, K, 128);
     const CUtensorMap tb = make_tmap_u8_sw128(Wop, K, ds->n, K, 256);
-    launch_tc_dist(ta, tb, K, sop, d_row_ids, R, ds->n, ldn, symmetric, incr, peers, st, launches, ops);
+    const CUtensorMap tbh = make_tmap_u8_sw128(Wop, K, ds->n, K, 128);      // CTA pairs: each CTA stages half of the sample rows
+    launch_tc_dist(ta, tb, &tbh, K, sop, d_row_ids, R, ds->n, ldn, symmetric, incr, peers, st, launches, ops);
     ds->last_dist_exchanged = symmetric && peers.world > 1;
 }
 

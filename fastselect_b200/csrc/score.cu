@@ -267,7 +267,10 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
         if (ws.pt > 0 && slab_cacheable) {
             ds->dd_buf = Dd;
             // Dd now holds the mismatch counts of exactly these columns for these target rows
-            ds->dd_cols.assign(ws.p_tcol.ptr, ws.p_tcol.ptr + ws.pt);
+            if (ds->dd_version != ws.lists_version || (int64_t)ds->dd_cols.size() != ws.pt) {
+                ds->dd_cols.assign(ws.p_tcol.ptr, ws.p_tcol.ptr + ws.pt);
+                ds->dd_version = ws.lists_version;
+            }
             ds->dd_r0 = targets[0];
             ds->dd_R = (int64_t)targets.size();
             ds->dd_valid = true;

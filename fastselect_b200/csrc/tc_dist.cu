@@ -61,6 +61,73 @@ __host__ __device__ inline bool dist_row_side(int sb_i, int sb_j, int coarse_shi
     return (((sb_i + sb_j) & 1) == 0) == (sb_j > sb_i);
 }
 
+// Epilogue of one 128 x 256 accumulator tile (this warp's 32 TMEM lanes = 32 target rows): distances
+// s_i + s_j - acc, stored (or subtracted, incremental update) into the slab row and, for a mirrored
+// tile, transposed into the slab of the rank that owns the samples as target rows.
+__device__ __forceinline__ void dist_store_tile(uint32_t tmem_base, int q, int64_t row, int32_t s_i, int64_t R, int64_t n0,
+                                                int64_t cend, const int32_t *__restrict__ srow, int64_t ldd, int subtract,
+                                                bool mirror, int32_t *Dd, int32_t *Dm, int64_t owner_start,
+                                                int64_t row_global0) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            const int64_t col = n0 + c0;
+            if (col >= cend) continue;                         // warp-uniform
+            uint32_t v[32];
+            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tc::tmem_ld_wait();
+            // distances of this thread's row to samples col .. col+31 (srow is padded to ldd;
+            // col is a multiple of 4)
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+                const int4 sj = *reinterpret_cast<const int4 *>(srow + col + e);
+                v[e] = (uint32_t)(s_i + sj.x - __float2int_rn(__uint_as_float(v[e])));
+                v[e + 1] = (uint32_t)(s_i + sj.y - __float2int_rn(__uint_as_float(v[e + 1])));
+                v[e + 2] = (uint32_t)(s_i + sj.z - __float2int_rn(__uint_as_float(v[e + 2])));
+                v[e + 3] = (uint32_t)(s_i + sj.w - __float2int_rn(__uint_as_float(v[e + 3])));
+            }
+            // subtract mode (incremental update): the operands are those of removed columns and
+            // their mismatch count is taken off the resident slab.  All loads of a chunk are issued
+            // before the first store (the slab pointers may alias, so the compiler would otherwise
+            // order every load behind the previous store: 32 dependent round trips per chunk).
+            if (row < R) {
+                int32_t *dst = Dd + row * ldd + col;           // ldd multiple of 128, col multiple of 4: 16-byte aligned
+                if (subtract) {
+                    int4 old[8];
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        old[e >> 2] = col + e < cend ? *reinterpret_cast<const int4 *>(dst + e) : make_int4(0, 0, 0, 0);
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        if (col + e < cend)                    // cend is a multiple of 4 or the padded end
+                            *reinterpret_cast<int4 *>(dst + e) =
+                                make_int4(old[e >> 2].x - (int)v[e], old[e >> 2].y - (int)v[e + 1],
+                                          old[e >> 2].z - (int)v[e + 2], old[e >> 2].w - (int)v[e + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 4)
+                        if (col + e < cend)
+                            *reinterpret_cast<int4 *>(dst + e) = make_int4((int)v[e], (int)v[e + 1], (int)v[e + 2], (int)v[e + 3]);
+                }
+            }
+            if (mirror && row < R) {
+                // transposed copy: row (col + e) of the owner's slab, column = this row's sample
+                int32_t *m = Dm + (col - owner_start) * ldd + row_global0 + row;
+                if (subtract) {
+                    int32_t old[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) old[e] = col + e < cend ? m[e * ldd] : 0;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (col + e < cend) m[e * ldd] = old[e] - (int32_t)v[e];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (col + e < cend) m[e * ldd] = (int32_t)v[e];
+                }
+            }
+        }
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                int num_k_blocks, const int32_t *__restrict__ srow, const int64_t *__restrict__ ids, int64_t R,
@@ -167,64 +234,7 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int32_t s_i = row < R ? srow[ids[row]] : 0;      // issued before the accumulator wait
         tc::mbar_wait(accum_bar, 0);
         tc::tc_fence_after();
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            const int64_t col = n0 + c0;
-            if (col >= cend) continue;                         // warp-uniform
-            uint32_t v[32];
-            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            tc::tmem_ld_wait();
-            // distances of this thread's row to samples col .. col+31 (srow is padded to ldd;
-            // col is a multiple of 4)
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-                const int4 sj = *reinterpret_cast<const int4 *>(srow + col + e);
-                v[e] = (uint32_t)(s_i + sj.x - __float2int_rn(__uint_as_float(v[e])));
-                v[e + 1] = (uint32_t)(s_i + sj.y - __float2int_rn(__uint_as_float(v[e + 1])));
-                v[e + 2] = (uint32_t)(s_i + sj.z - __float2int_rn(__uint_as_float(v[e + 2])));
-                v[e + 3] = (uint32_t)(s_i + sj.w - __float2int_rn(__uint_as_float(v[e + 3])));
-            }
-            // subtract mode (incremental update): the operands are those of removed columns and
-            // their mismatch count is taken off the resident slab.  All loads of a chunk are issued
-            // before the first store (the slab pointers may alias, so the compiler would otherwise
-            // order every load behind the previous store: 32 dependent round trips per chunk).
-            if (row < R) {
-                int32_t *dst = Dd + row * ldd + col;           // ldd multiple of 128, col multiple of 4: 16-byte aligned
-                if (subtract) {
-                    int4 old[8];
-#pragma unroll
-                    for (int e = 0; e < 32; e += 4)
-                        old[e >> 2] = col + e < cend ? *reinterpret_cast<const int4 *>(dst + e) : make_int4(0, 0, 0, 0);
-#pragma unroll
-                    for (int e = 0; e < 32; e += 4)
-                        if (col + e < cend)                    // cend is a multiple of 4 or the padded end
-                            *reinterpret_cast<int4 *>(dst + e) =
-                                make_int4(old[e >> 2].x - (int)v[e], old[e >> 2].y - (int)v[e + 1],
-                                          old[e >> 2].z - (int)v[e + 2], old[e >> 2].w - (int)v[e + 3]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; e += 4)
-                        if (col + e < cend)
-                            *reinterpret_cast<int4 *>(dst + e) = make_int4((int)v[e], (int)v[e + 1], (int)v[e + 2], (int)v[e + 3]);
-                }
-            }
-            if (mirror && row < R) {
-                // transposed copy: row (col + e) of the owner's slab, column = this row's sample
-                int32_t *m = Dm + (col - peers.starts[owner]) * ldd + row_global0 + row;
-                if (subtract) {
-                    int32_t old[32];
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) old[e] = col + e < cend ? m[e * ldd] : 0;
-#pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        if (col + e < cend) m[e * ldd] = old[e] - (int32_t)v[e];
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        if (col + e < cend) m[e * ldd] = (int32_t)v[e];
-                }
-            }
-        }
+        dist_store_tile(tmem_base, q, row, s_i, R, n0, cend, srow, ldd, subtract, mirror, Dd, Dm, peers.starts[owner], row_global0);
         tc::tc_fence_before();
     }
     __syncthreads();
@@ -234,23 +244,206 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
 }
 
-void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, int64_t K, const int32_t *srow,
-                    const int64_t *d_ids, int64_t R, int64_t n, int64_t ldd, bool symmetric, bool subtract,
-                    const DistPeers &peers, cudaStream_t st, int *launches, double *ops) {
-    static bool configured = false;
-    if (!configured) {
-        FS_CUDA(cudaFuncSetAttribute(tc_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
+// ---------------------------------------------------------------------------------------------
+// CTA-pair version (tcgen05 cta_group::2): one cluster of two CTAs per 256 x 256 super-block of D.
+// Each CTA stages its own 128 target rows and HALF of the 256 sample rows (32 KB per K slab instead
+// of 48 KB -- the single-CTA kernel is bound by the operand feed from L2, not by the tensor pipe:
+// tools/fp4_peak.cu reaches 128 cycles per M128 N256 K64 MMA from resident operands, the kernel
+// above ~190), six stages deep; the leader CTA issues one M256 N256 MMA for the pair, which reads the
+// B operand from both CTAs' shared memory; commits are multicast to both CTAs' barriers; each CTA
+// drains its own 128 TMEM lanes.  A pair is exactly one super-block of the symmetric scheme.
+// Probed stand-alone first (tools/tc_dist_cg2_probe.cu, profiles/r02_tc_dist_cg2_probe_run1.txt: exact).
+namespace {
+constexpr int P_STAGES = 6;
+constexpr int P_B_BYTES = (BN / 2) * BK;                       // 16 KB: this CTA's half of the sample rows
+constexpr int P_SMEM_BYTES = P_STAGES * (A_BYTES + P_B_BYTES) + 1024 + 256;
+constexpr int P_BAND = BAND / 2;                               // rasterisation band in super-block rows
+constexpr uint32_t kLeaderMask = 0xFEFFFFFFu;                  // shared::cluster address of the same offset in CTA 0
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-D tile load by either CTA of the pair; the bytes are credited to the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            tc::smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(dst_smem)), "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(TMEM_COLS) : "memory");
+}
+// arrives on the mbarrier at this shared-memory offset in BOTH CTAs when the pair's MMAs retire
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     tc::smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_mxf4_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t tmem_sfa, uint32_t tmem_sfb, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+}
+}  // namespace
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+tc_dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    int num_k_blocks, const int32_t *__restrict__ srow, const int64_t *__restrict__ ids, int64_t R,
+                    int64_t n, int64_t ldd, int symmetric, int subtract, int pair_rows, int tiles_x,
+                    const __grid_constant__ DistPeers peers) {
+    const uint32_t crank = cluster_ctarank();
+    // the same L2-friendly raster as above, in super-block rows
+    int pair_y, tile_x;
+    {
+        const int lin = (int)(blockIdx.x >> 1);
+        const int band = lin / (P_BAND * tiles_x);
+        const int band_rows = pair_rows - band * P_BAND < P_BAND ? pair_rows - band * P_BAND : P_BAND;
+        const int in_band = lin - band * P_BAND * tiles_x;
+        pair_y = band * P_BAND + in_band % band_rows;
+        tile_x = in_band / band_rows;
     }
+    int owner = 0;
+    while (owner + 1 < peers.world && tile_x >= peers.sb_base[owner + 1]) ++owner;
+    const int64_t n0 = peers.starts[owner] + (int64_t)(tile_x - peers.sb_base[owner]) * BN;
+    const int64_t cend = n0 + BN < peers.starts[owner + 1] ? n0 + BN : peers.starts[owner + 1];
+    const int sb_i = peers.sb_base[peers.rank] + pair_y, sb_j = tile_x;
+    const bool diagonal = sb_i == sb_j;
+    if (symmetric && !dist_row_side(sb_i, sb_j, peers.coarse_shift)) return;      // both CTAs of the pair take the same exit
+    const bool mirror = symmetric && !diagonal;
+    int32_t *Dd = peers.slab[peers.rank];
+    int32_t *Dm = peers.slab[owner];
+    const int64_t row_global0 = peers.starts[peers.rank];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *smem_a = smem;
+    unsigned char *smem_b = smem + P_STAGES * A_BYTES;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + P_STAGES * (A_BYTES + P_B_BYTES));
+    uint64_t *empty_bar = full_bar + P_STAGES;
+    uint64_t *accum_bar = empty_bar + P_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = pair_y * (2 * BM) + (int)crank * BM;           // this CTA's 128 target rows
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmap_a);
+        tc::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < P_STAGES; ++s) {
+            tc::mbar_init(&full_bar[s], 1);       // the leader's producer arrives with the pair's byte count
+            tc::mbar_init(&empty_bar[s], 1);      // the pair's MMA commit arrives (multicast)
+        }
+        tc::mbar_init(accum_bar, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                           // the peer's barriers exist before anything signals them
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp >= 2) {
+        for (int c = 0; c < 8; ++c) tc::tmem_st_32x1(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + SF_COL + c, 0x7f7f7f7fu);
+        tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                           // both CTAs' scale factors are in place before the leader issues
+    tc::tc_fence_after();
+
+    if (warp == 0) {
+        // ===== TMA producer (one per CTA: own A rows, own half of the B rows) =====
+        if (lane == 0) {
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int s = kb % P_STAGES;
+                const uint32_t ph = (kb / P_STAGES) & 1;
+                tc::mbar_wait(&empty_bar[s], ph ^ 1);
+                if (crank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * (A_BYTES + P_B_BYTES));
+                tma_load_2d_pair(smem_a + s * A_BYTES, &tmap_a, &full_bar[s], kb * BK, m0);
+                tma_load_2d_pair(smem_b + s * P_B_BYTES, &tmap_b, &full_bar[s], kb * BK, (int32_t)(n0 + crank * (BN / 2)));
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA, for the pair =====
+        if (lane == 0 && crank == 0) {
+            constexpr uint32_t idesc = tc::make_idesc_mxf4(2 * BM, BN);
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int s = kb % P_STAGES;
+                const uint32_t ph = (kb / P_STAGES) & 1;
+                tc::mbar_wait(&full_bar[s], ph);
+                tc::tc_fence_after();
+                const uint64_t da = tc::make_smem_desc_sw128(tc::smem_u32(smem_a + s * A_BYTES));
+                const uint64_t db = tc::make_smem_desc_sw128(tc::smem_u32(smem_b + s * P_B_BYTES));
+#pragma unroll
+                for (int k = 0; k < BK / 32; ++k)
+                    mma_mxf4_pair(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, tmem_base + SF_COL,
+                                  tmem_base + SF_COL, (kb | k) != 0);
+                tc_commit_pair(&empty_bar[s]);
+            }
+            tc_commit_pair(accum_bar);
+        }
+    } else {
+        // ===== epilogue: this CTA's 128 TMEM lanes =====
+        const int q = warp & 3;
+        const int64_t row = (int64_t)m0 + q * 32 + lane;
+        const int32_t s_i = row < R ? srow[ids[row]] : 0;
+        tc::mbar_wait(accum_bar, 0);
+        tc::tc_fence_after();
+        dist_store_tile(tmem_base, q, row, s_i, R, n0, cend, srow, ldd, subtract, mirror, Dd, Dm, peers.starts[owner], row_global0);
+        tc::tc_fence_before();
+    }
+    __syncthreads();
+    cluster_sync_all();                           // neither CTA leaves (or frees TMEM) while the pair is in flight
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tmem_dealloc_pair(tmem_base);
+    }
+}
+
+void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, const CUtensorMap *tmap_b_half, int64_t K,
+                    const int32_t *srow, const int64_t *d_ids, int64_t R, int64_t n, int64_t ldd, bool symmetric, bool subtract,
+                    const DistPeers &peers, cudaStream_t st, int *launches, double *ops) {
     const int tiles_x = peers.sb_base[peers.world], tiles_y = (int)ceil_div(R, BM);
-    tc_dist_kernel<<<(unsigned)(tiles_x * tiles_y), THREADS, SMEM_BYTES, st>>>(
-        tmap_a, tmap_b, (int)(K / BK), srow, d_ids, R, n, ldd, symmetric ? 1 : 0, subtract ? 1 : 0, tiles_y, tiles_x,
-        peers);
+    // CTA pairs (cta_group::2) unless switched off: FS_B200_DIST_PAIR=0 keeps the single-CTA kernel
+    const char *env = getenv("FS_B200_DIST_PAIR");
+    const bool pair = tmap_b_half != nullptr && !(env && env[0] == '0');
+    if (pair) {
+        // per launch: the attribute belongs to the CURRENT device (several devices per process: fs_multi_*)
+        FS_CUDA(cudaFuncSetAttribute(tc_dist_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+        const int pair_rows = (int)ceil_div(R, 2 * BM);
+        tc_dist_pair_kernel<<<(unsigned)(2 * tiles_x * pair_rows), THREADS, P_SMEM_BYTES, st>>>(
+            tmap_a, *tmap_b_half, (int)(K / BK), srow, d_ids, R, n, ldd, symmetric ? 1 : 0, subtract ? 1 : 0, pair_rows, tiles_x,
+            peers);
+    } else {
+        FS_CUDA(cudaFuncSetAttribute(tc_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        tc_dist_kernel<<<(unsigned)(tiles_x * tiles_y), THREADS, SMEM_BYTES, st>>>(
+            tmap_a, tmap_b, (int)(K / BK), srow, d_ids, R, n, ldd, symmetric ? 1 : 0, subtract ? 1 : 0, tiles_y, tiles_x,
+            peers);
+    }
     FS_CUDA(cudaGetLastError());
     ++*launches;
     if (ops) {
         int64_t tiles = 0;
-        for (int by = 0; by < tiles_y; ++by)
+        const int rows_y = pair ? 2 * (int)ceil_div(R, 2 * BM) : tiles_y;       // a pair always runs both of its row tiles
+        for (int by = 0; by < rows_y; ++by)
             for (int bx = 0; bx < tiles_x; ++bx) {
                 const int sb_i = peers.sb_base[peers.rank] + (by >> 1);
                 tiles += (!symmetric || dist_row_side(sb_i, bx, peers.coarse_shift)) ? 1 : 0;
