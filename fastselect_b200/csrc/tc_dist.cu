@@ -258,51 +258,6 @@ constexpr int P_STAGES = 6;
 constexpr int P_B_BYTES = (BN / 2) * BK;                       // 16 KB: this CTA's half of the sample rows
 constexpr int P_SMEM_BYTES = P_STAGES * (A_BYTES + P_B_BYTES) + 1024 + 256;
 constexpr int P_BAND = BAND / 2;                               // rasterisation band in super-block rows
-constexpr uint32_t kLeaderMask = 0xFEFFFFFFu;                  // shared::cluster address of the same offset in CTA 0
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// 2-D tile load by either CTA of the pair; the bytes are credited to the LEADER's mbarrier
-__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int32_t c0, int32_t c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            tc::smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(m)), "r"(tc::smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(dst_smem)), "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(TMEM_COLS) : "memory");
-}
-// arrives on the mbarrier at this shared-memory offset in BOTH CTAs when the pair's MMAs retire
-__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                     tc::smem_u32(bar)),
-                 "h"((uint16_t)3)
-                 : "memory");
-}
-__device__ __forceinline__ void mma_mxf4_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                              uint32_t tmem_sfa, uint32_t tmem_sfb, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
-        : "memory");
-}
 }  // namespace
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -310,7 +265,7 @@ tc_dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     int num_k_blocks, const int32_t *__restrict__ srow, const int64_t *__restrict__ ids, int64_t R,
                     int64_t n, int64_t ldd, int symmetric, int subtract, int pair_rows, int tiles_x,
                     const __grid_constant__ DistPeers peers) {
-    const uint32_t crank = cluster_ctarank();
+    const uint32_t crank = tc::cluster_ctarank();
     // the same L2-friendly raster as above, in super-block rows
     int pair_y, tile_x;
     {
@@ -354,10 +309,10 @@ tc_dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tc::mbar_init(accum_bar, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc_pair(tmem_slot);
+    if (warp == 1) tc::tmem_alloc_pair<TMEM_COLS>(tmem_slot);
     tc::tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                           // the peer's barriers exist before anything signals them
+    tc::cluster_sync_all();                           // the peer's barriers exist before anything signals them
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (warp >= 2) {
@@ -366,7 +321,7 @@ tc_dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     tc::tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                           // both CTAs' scale factors are in place before the leader issues
+    tc::cluster_sync_all();                           // both CTAs' scale factors are in place before the leader issues
     tc::tc_fence_after();
 
     if (warp == 0) {
@@ -377,8 +332,8 @@ tc_dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const uint32_t ph = (kb / P_STAGES) & 1;
                 tc::mbar_wait(&empty_bar[s], ph ^ 1);
                 if (crank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * (A_BYTES + P_B_BYTES));
-                tma_load_2d_pair(smem_a + s * A_BYTES, &tmap_a, &full_bar[s], kb * BK, m0);
-                tma_load_2d_pair(smem_b + s * P_B_BYTES, &tmap_b, &full_bar[s], kb * BK, (int32_t)(n0 + crank * (BN / 2)));
+                tc::tma_load_2d_pair(smem_a + s * A_BYTES, &tmap_a, &full_bar[s], kb * BK, m0);
+                tc::tma_load_2d_pair(smem_b + s * P_B_BYTES, &tmap_b, &full_bar[s], kb * BK, (int32_t)(n0 + crank * (BN / 2)));
             }
         }
     } else if (warp == 1) {
@@ -394,11 +349,11 @@ tc_dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const uint64_t db = tc::make_smem_desc_sw128(tc::smem_u32(smem_b + s * P_B_BYTES));
 #pragma unroll
                 for (int k = 0; k < BK / 32; ++k)
-                    mma_mxf4_pair(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, tmem_base + SF_COL,
+                    tc::mma_mxf4_pair(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, tmem_base + SF_COL,
                                   tmem_base + SF_COL, (kb | k) != 0);
-                tc_commit_pair(&empty_bar[s]);
+                tc::tc_commit_pair(&empty_bar[s]);
             }
-            tc_commit_pair(accum_bar);
+            tc::tc_commit_pair(accum_bar);
         }
     } else {
         // ===== epilogue: this CTA's 128 TMEM lanes =====
@@ -411,10 +366,10 @@ tc_dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tc::tc_fence_before();
     }
     __syncthreads();
-    cluster_sync_all();                           // neither CTA leaves (or frees TMEM) while the pair is in flight
+    tc::cluster_sync_all();                           // neither CTA leaves (or frees TMEM) while the pair is in flight
     if (warp == 1) {
         tc::tc_fence_after();
-        tmem_dealloc_pair(tmem_base);
+        tc::tmem_dealloc_pair<TMEM_COLS>(tmem_base);
     }
 }
 
