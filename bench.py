@@ -896,8 +896,9 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c4surf", "c5", "j1"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-parity", dest="no_parity", action="store_true", help="skip the oracle / single-GPU parity checks of the timed run")
-    ap.add_argument("--n", type=int, default=None)
-    ap.add_argument("--p", type=int, default=None)
+    # (--samples / --features: torchrun's own parser treats "--n" as an ambiguous abbreviation of its options)
+    ap.add_argument("--n", "--samples", dest="n", type=int, default=None)
+    ap.add_argument("--p", "--features", dest="p", type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference" and args.workload == "j1":
         joint_reference_arm(args)

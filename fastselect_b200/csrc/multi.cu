@@ -100,6 +100,7 @@ int fs_multi_create(fs_multi **out, const void *x, int dtype, int64_t n, int64_t
     try {
         FS_REQUIRE(out && x && devices, FS_ERR_INVALID, "fs_multi_create: null pointer");
         FS_REQUIRE(n_devices >= 1 && n_devices <= kMaxRanks, FS_ERR_INVALID, "fs_multi_create: 1..%d devices", kMaxRanks);
+        FS_REQUIRE(fs_device_count() > 0, FS_ERR_NO_DEVICE, "no usable NVIDIA sm_100 (B200) GPU: this library has no CPU fallback");
         // no empty shard: fewer ranks for very small data sets
         int world = n_devices;
         while (world > 1 && n / world < 8) --world;

@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
     const int32_t *__restrict__ toff, const double *__restrict__ vals, int as_f32, int64_t n, int64_t pt, int64_t K,
     int64_t ldt, int64_t ldc, int8_t *__restrict__ U, int8_t *__restrict__ Wd, int8_t *__restrict__ At,
     uint8_t *__restrict__ codesT, uint8_t *__restrict__ codes, int32_t *__restrict__ srow,
-    uint32_t *__restrict__ krow, int all_ident, int64_t u_lo, int64_t u_hi, const int32_t *__restrict__ tpos) {
+    uint32_t *__restrict__ krow, int all_ident, int64_t u_lo, int64_t u_hi, const int32_t *__restrict__ tpos, int uk0) {
+    // uk0: one-hot row of U / Wd that this launch's row 0 of `toff` stands for (a launch over a slice of the
+    // columns numbers At / krow rows from 0 but addresses the distance operands globally)
     __shared__ __align__(16) uint8_t code_rc[ENC_ROWS][ENC_COLS];       // [sample][column]
     __shared__ __align__(16) uint8_t code_cr[ENC_COLS][ENC_CR_LD];      // [column][sample]
     __shared__ uint8_t kcol[ENC_KMAX];                                  // reduced row -> column in tile
@@ -238,7 +240,8 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
     // ---- step 2: U[r, k0..k1), Wd[r, k0..k1), s[r]
     // fast path (every column of the tile has 3 values and k0 is 16-byte aligned, i.e. 0/1/2
     // genotypes): 8 codes -> 16 bytes of U and of Wd, built with shifts
-    const bool v3 = __syncthreads_and((tid >= ncols) || clast[tid < ncols ? tid : 0] == 2) && (k0 & 31) == 0 &&
+    const int kg0 = k0 + uk0, kg1 = k1 + uk0;          // the same rows in U / Wd
+    const bool v3 = __syncthreads_and((tid >= ncols) || clast[tid < ncols ? tid : 0] == 2) && (kg0 & 31) == 0 &&
                     (ncols & 15) == 0;
     if (U == nullptr) {
         // distance operands not wanted (the slab is updated incrementally from other columns)
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
                 expand_v3_fp4(cw.y, u.y, w.y, cnt);
                 expand_v3_fp4(cw.z, u.z, w.z, cnt);
                 expand_v3_fp4(cw.w, u.w, w.w, cnt);
-                const int64_t o = (r0 + rr) * K + (k0 >> 1) + 16 * g;      // K = row pitch in bytes
+                const int64_t o = (r0 + rr) * K + (kg0 >> 1) + 16 * g;     // K = row pitch in bytes
                 // U holds only the rows [u_lo, u_hi) (the target rows of this rank)
                 if (r0 + rr >= u_lo && r0 + rr < u_hi) *reinterpret_cast<uint4 *>(U + o - u_lo * K) = u;
                 *reinterpret_cast<uint4 *>(Wd + o) = w;
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
         // general path: nibbles k0..k1 of the row; 32-bit words (8 nibbles) that belong to this tile
         // entirely are stored, the words at the unaligned edges are OR-ed in (the operands were
         // cleared by the host; a neighbouring tile owns the other nibbles of such a word)
-        const int w0 = k0 >> 3, w1 = (k1 + 7) >> 3;               // word range covering [k0, k1)
+        const int w0 = kg0 >> 3, w1 = (kg1 + 7) >> 3;             // word range covering [kg0, kg1)
         for (int rr = tid >> 5; rr < ENC_ROWS; rr += 8) {          // uniform trip count
             int cnt = 0;
             if (rr < nrows) {
@@ -278,10 +281,10 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
 #pragma unroll
                     for (int b = 0; b < 8; ++b) {
                         const int k = 8 * w + b;
-                        if (k >= k0 && k < k1) {
-                            const int col = kcol[k - k0];
+                        if (k >= kg0 && k < kg1) {
+                            const int col = kcol[k - kg0];
                             const uint32_t code = code_rc[rr][col];
-                            const uint32_t on = code == kval[k - k0] ? 1u : 0u;
+                            const uint32_t on = code == kval[k - kg0] ? 1u : 0u;
                             uw |= (on << 1) << (4 * b);                                        // 1.0 = 0x2
                             ww |= ((on + (code != clast[col] ? 1u : 0u)) << 1) << (4 * b);      // 0 / 1.0 / 2.0 = 0x0 / 0x2 / 0x4
                         } else {
@@ -378,7 +381,8 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
     const uint8_t *__restrict__ x, int64_t ldx, const int64_t *__restrict__ perm, const int64_t *__restrict__ tcol,
     int64_t n, int64_t pt, int64_t K, int64_t ldt, int64_t ldc, int8_t *__restrict__ U, int8_t *__restrict__ Wd,
     int8_t *__restrict__ At, uint8_t *__restrict__ codesT, uint8_t *__restrict__ codes, int32_t *__restrict__ srow,
-    uint32_t *__restrict__ krow, int64_t u_lo, int64_t u_hi, const int32_t *__restrict__ tpos) {
+    uint32_t *__restrict__ krow, int64_t u_lo, int64_t u_hi, const int32_t *__restrict__ tpos, int64_t ucol0) {
+    // ucol0: column of U / Wd that this launch's column 0 stands for (see onehot_encode_kernel's uk0)
     __shared__ __align__(16) uint8_t code_rc[ENC_ROWS][ENC_COLS];       // [sample][column]
     __shared__ __align__(16) uint8_t code_cr[ENC_COLS][ENC_CR_LD];      // [column][sample]
     __shared__ int64_t sperm[ENC_ROWS];
@@ -485,7 +489,7 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
                     expand_v3_fp4(cw.y, u.y, w.y, cnt);
                     expand_v3_fp4(cw.z, u.z, w.z, cnt);
                     expand_v3_fp4(cw.w, u.w, w.w, cnt);
-                    const int64_t o = (r0 + rr) * K + c0 + 16 * g;       // K = row pitch in bytes; k0 / 2 = c0
+                    const int64_t o = (r0 + rr) * K + ucol0 + c0 + 16 * g;       // K = row pitch in bytes; one byte per column
                     // U holds only the rows [u_lo, u_hi) (the target rows of this rank)
                     if (r0 + rr >= u_lo && r0 + rr < u_hi) *reinterpret_cast<uint4 *>(U + o - u_lo * K) = u;
                     *reinterpret_cast<uint4 *>(Wd + o) = w;
@@ -501,7 +505,7 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
                 if (rr < nrows)
                     for (int cc = tid & 31; cc < ncols; cc += 32) {
                         const uint32_t code = code_rc[rr][cc];
-                        const int64_t o = (r0 + rr) * K + c0 + cc;
+                        const int64_t o = (r0 + rr) * K + ucol0 + c0 + cc;
                         if (r0 + rr >= u_lo && r0 + rr < u_hi)
                             U[o - u_lo * K] = (int8_t)(code == 0u ? 0x02u : code == 1u ? 0x20u : 0u);
                         Wd[o] = (int8_t)(code == 0u ? 0x24u : code == 1u ? 0x42u : 0u);
@@ -596,7 +600,7 @@ static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
     if (lean) {
         onehot_encode_v3_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(ds->x), ds->ldx, ds->d_perm.ptr,
                                                       ws.rcol.ptr, n, pr, (int64_t)Kb, ws.ldt, 0, ws.Ur.ptr, ws.Wdr.ptr, nullptr,
-                                                      nullptr, nullptr, ws.srow_r.ptr, nullptr, 0, n, nullptr);
+                                                      nullptr, nullptr, ws.srow_r.ptr, nullptr, 0, n, nullptr, 0);
         FS_CUDA(cudaGetLastError());
         ++*launches;
         return;
@@ -605,7 +609,7 @@ static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
     onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,        \
                                                   ws.rcol.ptr, ws.roff.ptr, ds->d_vals.ptr, as_f32, n, pr, (int64_t)Kb, \
                                                   ws.ldt, 0, ws.Ur.ptr, ws.Wdr.ptr, nullptr, nullptr, nullptr,    \
-                                                  ws.srow_r.ptr, nullptr, all_ident, 0, n, nullptr)
+                                                  ws.srow_r.ptr, nullptr, all_ident, 0, n, nullptr, 0)
     switch (ds->dtype) {
         case FS_U8: FS_ENCODE_R(uint8_t); break;
         case FS_I8: FS_ENCODE_R(int8_t); break;
@@ -703,7 +707,9 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
         if (pc <= 0 || (!want_dist && !want_acc && !want_codes)) return;
         const unsigned grid = (unsigned)ceil_div(pc, ENC_COLS) * row_tiles;
         // slice-local offsets: one-hot rows from 0, codesT rows from 0
-        const int32_t *off = want_acc && c_lo == a0 ? ws.atoff.ptr : ws.toff.ptr + c_lo;
+        const bool local_rows = want_acc && c_lo == a0;        // At / krow rows numbered from the slice's first column
+        const int32_t *off = local_rows ? ws.atoff.ptr : ws.toff.ptr + c_lo;
+        const int uk0 = local_rows ? ws.p_toff.ptr[a0] : 0;    // where those rows sit in U / Wd
         int8_t *Uo = want_dist ? ws.U.ptr : nullptr, *Wo = want_dist ? ws.Wd.ptr : nullptr;
         int8_t *Ao = want_acc ? ws.At.ptr : nullptr;
         uint8_t *Co = want_acc && !reuse_ct ? ws.codesT.ptr : nullptr;
@@ -714,13 +720,13 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
         if (lean) {
             onehot_encode_v3_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(ds->x), ds->ldx, ds->d_perm.ptr,
                                                           ws.tcol.ptr + c_lo, n, pc, (int64_t)Kb, ws.ldt, ws.ldc, Uo, Wo, Ao, Co,
-                                                          codes, So, Ko, ws.u_lo, ws.u_hi, To);
+                                                          codes, So, Ko, ws.u_lo, ws.u_hi, To, c_lo);
         } else {
 #define FS_ENCODE(T)                                                                                              \
     onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,        \
                                                   ws.tcol.ptr + c_lo, off, ds->d_vals.ptr, as_f32, n, pc, (int64_t)Kb, \
                                                   ws.ldt, ws.ldc, Uo, Wo, Ao, Co, codes, So, Ko, all_ident, ws.u_lo,    \
-                                                  ws.u_hi, To)
+                                                  ws.u_hi, To, uk0)
             switch (ds->dtype) {
                 case FS_U8: FS_ENCODE(uint8_t); break;
                 case FS_I8: FS_ENCODE(int8_t); break;
@@ -734,6 +740,13 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     };
     if (!split) {
         launch(0, pt, ops, true, ws.have_codes);
+    } else if (ops && (a0 % ENC_COLS) == 0 && (ws.p_toff.ptr[a0] & 31) == 0 &&
+               (a1 == pt || ((a1 % ENC_COLS) == 0 && (ws.p_toff.ptr[a1] & 31) == 0))) {
+        // the slice in ONE fused launch (distance and accumulation operands, as on one GPU), the other
+        // columns distance-only: no column is staged twice
+        launch(a0, a1, true, true, false);
+        launch(0, a0, true, false, false);
+        launch(a1, pt, true, false, false);
     } else {
         // (the distance launch addresses U / Wd by the GLOBAL one-hot offsets of toff, the slice launch
         // addresses At / krow by the slice-local ones)

@@ -284,7 +284,7 @@ def test_integration_stubs_bind_the_built_library(tmp_path):
 
     text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     blocks = [b for b in re.findall(r"```python\n(.*?)```", text, flags=re.S) if "_b200.py" in b.splitlines()[0]]
-    assert len(blocks) == 2
+    assert len(blocks) == 3          # single GPU, several GPUs of one process, joint-count path
     src = "\n".join(blocks).replace('C.CDLL("libfastselect_b200.so")', f"C.CDLL({_native.LIB_PATH!r})")
     ns = {}
     exec(compile(src, "INTEGRATION.md", "exec"), ns)
@@ -294,6 +294,8 @@ def test_integration_stubs_bind_the_built_library(tmp_path):
     if not ns["available"]():
         with pytest.raises(RuntimeError, match="no usable NVIDIA sm_100"):
             ns["score"](x, y, 2, np.ones(6, bool), np.ones(6, np.float32), algo=2)
+        with pytest.raises(RuntimeError, match="no usable NVIDIA sm_100"):
+            ns["score_multi"](x, y, 2, np.ones(6, bool), np.ones(6, np.float32), algo=2, devices=[0, 1])
         with pytest.raises(RuntimeError, match="no usable NVIDIA sm_100"):
             ns["joint_matrix"](np.column_stack([x, y]), 0, np.log(2.0))
         return
