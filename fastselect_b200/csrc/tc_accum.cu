@@ -271,13 +271,6 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
             long long ah0 = 0, ah1 = 0, al0 = 0, al1 = 0;     // exact fixed-point sums (two chains)
             for (int t = g * group_tiles; t < tile_end; ++t) {
                 const TileDesc d = s_tiles[t];
-                // (ncu, round 2: a tenth of the epilogue's stall samples sat on the first use of the value
-                // codes below, another tenth on the per-target constants: both are prefetched one step ahead)
-                if (contiguous && t + 1 < tile_end) {
-                    const uint8_t *nx = at_row + ids0 + s_tiles[t + 1].row0 + half * HALF;
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + HALF));
-                }
                 // value codes of this thread's 128 targets in its column (issued before the
                 // accumulator wait so the loads overlap the MMAs); shared by both phases.
                 // Targets beyond the tile's rows get whatever follows: their coefficient is 0.
@@ -364,12 +357,6 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                     // per-target constants of this work item (accum_consts_kernel): uniform loads
                     const int2 *s_c = limbs + ((size_t)t * 2 + phase) * 256;
                     const int32_t *s_rs = rsum + ((size_t)t * 2 + phase) * 256;
-                    // the NEXT item's constants (3 KB, the next slot of both tables; harmless when the next item is
-                    // another one) into L1 while this item's accumulator is being produced
-                    if (half == 0 && q == 0) {
-                        if (lane < 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(s_c + 256) + 128 * lane));
-                        else if (lane < 24) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char *>(s_rs + 256) + 128 * (lane - 16)));
-                    }
                     tc::mbar_wait(&tfull_bar[buf], tph);
                     tc::tc_fence_after();
                     const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * HALF);

@@ -19,6 +19,7 @@
 
 #include "../fastselect_b200/csrc/tc_common.cuh"
 
+// (stand-alone probe from before these helpers moved into tc_common.cuh: it keeps its own copies under other names)
 using namespace fs::tc;
 
 namespace {
@@ -35,12 +36,12 @@ constexpr int TMEM_COLS = 512;
 constexpr int SF_COL = BN;         // unit UE8M0 scales in columns 256..287
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address: the pair's leader
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
+__device__ __forceinline__ uint32_t probe_cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
-__device__ __forceinline__ void cluster_sync() {
+__device__ __forceinline__ void probe_cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -71,29 +72,29 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
     __trap();
 }
 // 2-D tile load issued by either CTA of the pair; completion bytes go to the LEADER's mbarrier
-__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int32_t c0, int32_t c1) {
+__device__ __forceinline__ void probe_tma_load_2d_pair(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int32_t c0, int32_t c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
             smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem) {
+__device__ __forceinline__ void probe_tmem_alloc_pair(uint32_t *dst_smem) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr) {
+__device__ __forceinline__ void probe_tmem_dealloc_pair(uint32_t addr) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(TMEM_COLS) : "memory");
 }
 // arrives on the mbarrier at this shared-memory offset in BOTH CTAs when the pair's MMAs retire
-__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {
+__device__ __forceinline__ void probe_tc_commit_pair(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                      smem_u32(bar)),
                  "h"((uint16_t)3)
                  : "memory");
 }
-__device__ __forceinline__ void mma_mxf4_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ void probe_mma_mxf4_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                               uint32_t tmem_sfa, uint32_t tmem_sfb, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -110,7 +111,7 @@ __device__ __forceinline__ void mma_mxf4_pair(uint32_t tmem_d, uint64_t desc_a, 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int num_k_blocks,
                  int32_t *__restrict__ D, int64_t M, int64_t N, int64_t ldd, int tiles_x) {
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t rank = probe_cluster_ctarank();
     const int tile = (int)(blockIdx.x >> 1);
     const int tile_y = tile / tiles_x, tile_x = tile % tiles_x;
     const int64_t m0 = (int64_t)tile_y * 2 * BM + rank * BM;      // this CTA's A rows = its D rows
@@ -136,10 +137,10 @@ dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc_pair(tmem_slot);     // same warp id in both CTAs, same slot offset
+    if (warp == 1) probe_tmem_alloc_pair(tmem_slot);     // same warp id in both CTAs, same slot offset
     tc_fence_before();
     __syncthreads();
-    cluster_sync();                                // the peer's barriers exist before anything signals them
+    probe_cluster_sync();                                // the peer's barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (warp >= 2) {
@@ -148,7 +149,7 @@ dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync();                                // both CTAs' scale factors are in place before the leader issues
+    probe_cluster_sync();                                // both CTAs' scale factors are in place before the leader issues
     tc_fence_after();
 
     if (warp == 0) {
@@ -158,8 +159,8 @@ dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait_bounded(&empty_bar[s], ph ^ 1, 100 + s);
                 if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * (A_BYTES + B_BYTES));
-                tma_load_2d_pair(smem_a + s * A_BYTES, &tmap_a, &full_bar[s], kb * BK, (int32_t)m0);
-                tma_load_2d_pair(smem_b + s * B_BYTES, &tmap_b, &full_bar[s], kb * BK, (int32_t)(n0 + rank * BNH));
+                probe_tma_load_2d_pair(smem_a + s * A_BYTES, &tmap_a, &full_bar[s], kb * BK, (int32_t)m0);
+                probe_tma_load_2d_pair(smem_b + s * B_BYTES, &tmap_b, &full_bar[s], kb * BK, (int32_t)(n0 + rank * BNH));
             }
         }
     } else if (warp == 1) {
@@ -174,11 +175,11 @@ dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + s * B_BYTES));
 #pragma unroll
                 for (int k = 0; k < BK / 32; ++k)
-                    mma_mxf4_pair(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, tmem_base + SF_COL,
+                    probe_mma_mxf4_pair(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, tmem_base + SF_COL,
                                   tmem_base + SF_COL, (kb | k) != 0);
-                tc_commit_pair(&empty_bar[s]);
+                probe_tc_commit_pair(&empty_bar[s]);
             }
-            tc_commit_pair(accum_bar);
+            probe_tc_commit_pair(accum_bar);
         }
     } else {
         const int q = warp & 3;
@@ -199,10 +200,10 @@ dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tc_fence_before();
     }
     __syncthreads();
-    cluster_sync();                                // neither CTA leaves (or frees TMEM) while the pair is still in flight
+    probe_cluster_sync();                                // neither CTA leaves (or frees TMEM) while the pair is still in flight
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc_pair(tmem_base);
+        probe_tmem_dealloc_pair(tmem_base);
     }
 }
 
