@@ -243,6 +243,7 @@ struct WorkSet {
     DevBuf<int32_t> atoff;         // [a1 - a0 + 1] first reduced row of each slice column, from 0
     PinnedBuf<int32_t> p_atoff;
     bool acc_split = false;
+    bool group_call = false;       // built for a collective call of a multi-GPU group (restricted Wd rows)
 };
 
 }  // namespace fs
@@ -365,7 +366,8 @@ namespace fs {
 // slab fits one chunk -- decides between a full, an incremental and no distance computation
 // want_split: a multi-GPU group call that may shard the accumulation by one-hot columns (WorkSet::acc_split)
 void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool allow_tensor, bool need_codes,
-                   int64_t r0, int64_t R, bool contiguous, bool slab_cacheable, bool want_split, int *launches);
+                   int64_t r0, int64_t R, bool contiguous, bool slab_cacheable, bool want_split, bool group_call,
+                   int *launches);
 
 // comm.cu
 void comm_barrier(fs_comm *c, cudaStream_t st, int *launches);

@@ -360,7 +360,8 @@ static int plan_dist(fs_dataset *ds, const int64_t *tcol, int64_t pt, int64_t r0
 }
 
 void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool allow_tensor, bool need_codes,
-                   int64_t r0, int64_t R, bool contiguous, bool slab_cacheable, bool want_split, int *launches) {
+                   int64_t r0, int64_t R, bool contiguous, bool slab_cacheable, bool want_split, bool group_call,
+                   int *launches) {
     WorkSet &ws = ds->ws;
     // sample rows the target-side distance operand U has to hold
     const int64_t want_lo = contiguous ? r0 : 0, want_hi = contiguous ? r0 + R : ds->n;
@@ -368,7 +369,8 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
     // cache key: flags + the explicit column list (none when every column is active)
     const bool all = feat_idx == nullptr;
     std::vector<int64_t> key(3 + (all ? 0 : n_kept));
-    key[0] = (allow_tensor ? 1 : 0) | (want_split ? 2 : 0);
+    key[0] = (allow_tensor ? 1 : 0) | (want_split ? 2 : 0) | (group_call ? 4 : 0);
+    ws.group_call = group_call;
     key[1] = ds->arith;
     key[2] = all ? -1 : n_kept;
     if (!all) memcpy(key.data() + 3, feat_idx, n_kept * sizeof(int64_t));

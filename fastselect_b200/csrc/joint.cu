@@ -90,9 +90,11 @@ __global__ void __launch_bounds__(128) joint_tables_kernel(const int32_t *__rest
     const int sc = start[c], lc = start[c + 1] - sc, sg = start[g], lg = start[g + 1] - sg;
     const int64_t ra = sc - b0, cb = sg - b0;
     auto cnt = [=](int i, int j) { return -D[(ra + i) * ldd + cb + j]; };
+    JointSums s;
+    joint_sums(lc, lg, marg + sc, marg + sg, cnt, s);
     int64_t *t = tables + q * 256;
     const bool swapped = a > b;
-    joint_visit(lc, lg, marg + sc, marg + sg, cnt, n, [&](int i, int j, int64_t nij, int64_t, int64_t) {
+    joint_visit(lc, lg, marg + sc, marg + sg, cnt, n, s, [&](int i, int j, int64_t nij, int64_t, int64_t) {
         t[swapped ? j * 16 + i : i * 16 + j] = nij;
     });
 }
@@ -173,7 +175,7 @@ void run_joint(fs_dataset *ds, int kind, double log_base, const int64_t *feat_id
     tm.begin(PH_ENCODE);
     ds->no_dist_ops = true;
     try {
-        build_workset(ds, feat_idx, n_kept, true, false, 0, n, true, false, false, &launches);
+        build_workset(ds, feat_idx, n_kept, true, false, 0, n, true, false, false, false, &launches);
     } catch (...) {
         ds->no_dist_ops = false;
         throw;

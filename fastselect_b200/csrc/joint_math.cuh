@@ -21,29 +21,47 @@ namespace fs {
 enum : int { kJointMI = 0, kJointSU = 1 };
 constexpr int kJointMaxReduced = 15;          // FS_DISTINCT_CAP - 1 reduced rows per column
 
-// Calls visit(i, j, n_ij, n_i, n_j) for every cell of the full table in the reference's loop order
-// (value codes ascending, the implied last value last: mutual_information.py:41-42, CFS.py:60-61).
+// Sums needed to recover the implied last value of both columns.
+struct JointSums {
+    int32_t colsum[kJointMaxReduced];         // colsum[j] = sum_i c(i, j)
+    int64_t sa, sb, tot;                      // sum of a's / b's reduced marginals, sum of all c(i, j)
+};
+
 // la / lb: reduced rows (V - 1) of columns a / b; ma / mb: their marginal counts;
 // cnt(i, j): joint count of reduced row i of a and reduced row j of b.
+template <class Cnt>
+FS_HD void joint_sums(int la, int lb, const int32_t *ma, const int32_t *mb, Cnt cnt, JointSums &s) {
+    s.sa = 0;
+    s.sb = 0;
+    s.tot = 0;
+    for (int j = 0; j < lb; ++j) {
+        s.colsum[j] = 0;
+        s.sb += mb[j];
+    }
+    for (int i = 0; i < la; ++i) {
+        s.sa += ma[i];
+        for (int j = 0; j < lb; ++j) {
+            const int32_t c = cnt(i, j);
+            s.colsum[j] += c;
+            s.tot += c;
+        }
+    }
+}
+
+// Calls visit(i, j, n_ij, n_i, n_j) for every cell of the full table in the reference's loop order
+// (value codes ascending, the implied last value last: mutual_information.py:41-42, CFS.py:60-61).
 //   n_ij = c(i, j)                          i < la, j < lb
 //        = ma[i] - sum_j c(i, j)            j = lb   (b carries its last value)
 //        = mb[j] - sum_i c(i, j)            i = la
 //        = n - sa - sb + tot                both last
-// Everything lives in scalars (no indexed scratch arrays, nothing whose address escapes): the column
-// sums of the last row are re-read from the slab instead of being kept in an array, which keeps the
-// whole visit in registers on the device.
 template <class Cnt, class Visit>
-FS_HD void joint_visit(int la, int lb, const int32_t *ma, const int32_t *mb, Cnt cnt, int64_t n, Visit visit) {
-    int64_t sa = 0, sb = 0, tot = 0;
-    for (int i = 0; i < la; ++i) sa += ma[i];
-    for (int j = 0; j < lb; ++j) sb += mb[j];
-    for (int i = 0; i < la; ++i)
-        for (int j = 0; j < lb; ++j) tot += cnt(i, j);
+FS_HD void joint_visit(int la, int lb, const int32_t *ma, const int32_t *mb, Cnt cnt, int64_t n, const JointSums &s,
+                       Visit visit) {
     for (int i = 0; i <= la; ++i) {
-        const int64_t ni = i < la ? (int64_t)ma[i] : n - sa;
+        const int64_t ni = i < la ? (int64_t)ma[i] : n - s.sa;
         int64_t rowsum = 0;
         for (int j = 0; j <= lb; ++j) {
-            const int64_t nj = j < lb ? (int64_t)mb[j] : n - sb;
+            const int64_t nj = j < lb ? (int64_t)mb[j] : n - s.sb;
             int64_t nij;
             if (i < la && j < lb) {
                 nij = cnt(i, j);
@@ -51,11 +69,9 @@ FS_HD void joint_visit(int la, int lb, const int32_t *ma, const int32_t *mb, Cnt
             } else if (i < la) {
                 nij = ni - rowsum;
             } else if (j < lb) {
-                int64_t colsum = 0;
-                for (int ii = 0; ii < la; ++ii) colsum += cnt(ii, j);
-                nij = nj - colsum;
+                nij = nj - s.colsum[j];
             } else {
-                nij = n - sa - sb + tot;
+                nij = n - s.sa - s.sb + s.tot;
             }
             visit(i, j, nij, ni, nj);
         }
@@ -80,10 +96,12 @@ FS_HD double joint_entropy_bits(int l, const int32_t *m, int64_t n) {          /
 template <class Cnt>
 FS_HD double joint_statistic(int kind, int la, int lb, const int32_t *ma, const int32_t *mb, Cnt cnt, int64_t n,
                              double log_base) {
+    JointSums s;
+    joint_sums(la, lb, ma, mb, cnt, s);
     const double dn = (double)n;
     double acc = 0.0;
     if (kind == kJointMI) {
-        joint_visit(la, lb, ma, mb, cnt, n, [&](int, int, int64_t nij, int64_t ni, int64_t nj) {
+        joint_visit(la, lb, ma, mb, cnt, n, s, [&](int, int, int64_t nij, int64_t ni, int64_t nj) {
             const double pxy = (double)nij / dn;
             if (pxy > 1e-12) acc += pxy * log(pxy / (((double)ni / dn) * ((double)nj / dn) + 1e-12));
         });
@@ -91,7 +109,7 @@ FS_HD double joint_statistic(int kind, int la, int lb, const int32_t *ma, const 
     }
     const double h = joint_entropy_bits(la, ma, n) + joint_entropy_bits(lb, mb, n);
     if (h < 1e-12) return 0.0;
-    joint_visit(la, lb, ma, mb, cnt, n, [&](int, int, int64_t nij, int64_t ni, int64_t nj) {
+    joint_visit(la, lb, ma, mb, cnt, n, s, [&](int, int, int64_t nij, int64_t ni, int64_t nj) {
         const double pxy = (double)nij / dn, px = (double)ni / dn, py = (double)nj / dn;
         if (pxy > 1e-12 && px > 1e-12 && py > 1e-12) acc += pxy * log2(pxy / (px * py));
     });
@@ -109,7 +127,9 @@ FS_HD double joint_pair_from_slab(const int32_t *D, int64_t ldd, int64_t ra, int
 FS_HD void joint_table_from_slab(const int32_t *D, int64_t ldd, int64_t ra, int64_t cb, int la, int lb,
                                  const int32_t *ma, const int32_t *mb, int64_t n, int64_t *table, int ld_out) {
     auto cnt = [=](int i, int j) { return -D[(ra + i) * ldd + cb + j]; };
-    joint_visit(la, lb, ma, mb, cnt, n, [&](int i, int j, int64_t nij, int64_t, int64_t) { table[i * ld_out + j] = nij; });
+    JointSums s;
+    joint_sums(la, lb, ma, mb, cnt, s);
+    joint_visit(la, lb, ma, mb, cnt, n, s, [&](int i, int j, int64_t nij, int64_t, int64_t) { table[i * ld_out + j] = nij; });
 }
 
 }  // namespace fs

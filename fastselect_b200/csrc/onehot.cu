@@ -114,13 +114,23 @@ __device__ __forceinline__ uint2 pack_fp4_flags16(uint32_t e0, uint32_t e1, uint
     return make_uint2(pack_fp4_flags(e0) | (pack_fp4_flags(e1) << 16), pack_fp4_flags(e2) | (pack_fp4_flags(e3) << 16));
 }
 
+// Sample rows (internal order) whose Wd rows somebody reads: everything on one GPU; inside a multi-GPU
+// group the rank's own samples and those of the floor(G/2) ranks after it on the ring (tc_dist.cu), i.e.
+// at most two ranges.
+struct WdRows {
+    int64_t lo0, hi0, lo1, hi1;
+    __host__ __device__ bool has(int64_t r) const { return (r >= lo0 && r < hi0) || (r >= lo1 && r < hi1); }
+    __host__ __device__ bool touches(int64_t a, int64_t b) const { return (a < hi0 && b > lo0) || (a < hi1 && b > lo1); }
+};
+
 template <typename Tin>
 __global__ void __launch_bounds__(256) onehot_encode_kernel(
     const Tin *__restrict__ x, int64_t ldx, const int64_t *__restrict__ perm, const int64_t *__restrict__ tcol,
     const int32_t *__restrict__ toff, const double *__restrict__ vals, int as_f32, int64_t n, int64_t pt, int64_t K,
     int64_t ldt, int64_t ldc, int8_t *__restrict__ U, int8_t *__restrict__ Wd, int8_t *__restrict__ At,
     uint8_t *__restrict__ codesT, uint8_t *__restrict__ codes, int32_t *__restrict__ srow,
-    uint32_t *__restrict__ krow, int all_ident, int64_t u_lo, int64_t u_hi, const int32_t *__restrict__ tpos, int uk0) {
+    uint32_t *__restrict__ krow, int all_ident, int64_t u_lo, int64_t u_hi, const int32_t *__restrict__ tpos, int uk0,
+    WdRows wr) {
     // uk0: one-hot row of U / Wd that this launch's row 0 of `toff` stands for (a launch over a slice of the
     // columns numbers At / krow rows from 0 but addresses the distance operands globally)
     __shared__ __align__(16) uint8_t code_rc[ENC_ROWS][ENC_COLS];       // [sample][column]
@@ -138,6 +148,8 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
     const int ncols = (int)(pt - c0 < ENC_COLS ? pt - c0 : ENC_COLS);
     const int nrows = (int)(n - r0 < ENC_ROWS ? n - r0 : ENC_ROWS);
     const int k0 = toff[c0], k1 = toff[c0 + ncols];
+    // a distance-only launch has nothing to do for a row tile whose samples' Wd rows nobody reads
+    if (At == nullptr && codes == nullptr && !wr.touches(r0, r0 + nrows)) return;
     if (tid < ENC_ROWS) sperm[tid] = tid < nrows ? perm[r0 + tid] : 0;
 
     // ---- step 1: value codes
@@ -261,7 +273,7 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
                 const int64_t o = (r0 + rr) * K + (kg0 >> 1) + 16 * g;     // K = row pitch in bytes
                 // U holds only the rows [u_lo, u_hi) (the target rows of this rank)
                 if (r0 + rr >= u_lo && r0 + rr < u_hi) *reinterpret_cast<uint4 *>(U + o - u_lo * K) = u;
-                *reinterpret_cast<uint4 *>(Wd + o) = w;
+                if (wr.has(r0 + rr)) *reinterpret_cast<uint4 *>(Wd + o) = w;
             }
             cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
             cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
@@ -293,12 +305,13 @@ __global__ void __launch_bounds__(256) onehot_encode_kernel(
                     }
                     const int64_t o = (r0 + rr) * K + 4 * (int64_t)w;         // K = row pitch in bytes
                     const bool in_u = r0 + rr >= u_lo && r0 + rr < u_hi;      // U holds only those rows
+                    const bool in_w = wr.has(r0 + rr);
                     if (full) {
                         if (in_u) *reinterpret_cast<uint32_t *>(U + o - u_lo * K) = uw;
-                        *reinterpret_cast<uint32_t *>(Wd + o) = ww;
+                        if (in_w) *reinterpret_cast<uint32_t *>(Wd + o) = ww;
                     } else {
                         if (in_u && uw) atomicOr(reinterpret_cast<unsigned int *>(U + o - u_lo * K), uw);
-                        if (ww) atomicOr(reinterpret_cast<unsigned int *>(Wd + o), ww);
+                        if (in_w && ww) atomicOr(reinterpret_cast<unsigned int *>(Wd + o), ww);
                     }
                 }
                 for (int c = lane; c < ncols; c += 32) cnt += code_rc[rr][c] != clast[c] ? 1 : 0;
@@ -381,7 +394,7 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
     const uint8_t *__restrict__ x, int64_t ldx, const int64_t *__restrict__ perm, const int64_t *__restrict__ tcol,
     int64_t n, int64_t pt, int64_t K, int64_t ldt, int64_t ldc, int8_t *__restrict__ U, int8_t *__restrict__ Wd,
     int8_t *__restrict__ At, uint8_t *__restrict__ codesT, uint8_t *__restrict__ codes, int32_t *__restrict__ srow,
-    uint32_t *__restrict__ krow, int64_t u_lo, int64_t u_hi, const int32_t *__restrict__ tpos, int64_t ucol0) {
+    uint32_t *__restrict__ krow, int64_t u_lo, int64_t u_hi, const int32_t *__restrict__ tpos, int64_t ucol0, WdRows wr) {
     // ucol0: column of U / Wd that this launch's column 0 stands for (see onehot_encode_kernel's uk0)
     __shared__ __align__(16) uint8_t code_rc[ENC_ROWS][ENC_COLS];       // [sample][column]
     __shared__ __align__(16) uint8_t code_cr[ENC_COLS][ENC_CR_LD];      // [column][sample]
@@ -395,6 +408,8 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
     const int ncols = (int)(pt - c0 < ENC_COLS ? pt - c0 : ENC_COLS);
     const int nrows = (int)(n - r0 < ENC_ROWS ? n - r0 : ENC_ROWS);
     const int64_t k0 = 2 * c0;
+    // a distance-only launch has nothing to do for a row tile whose samples' Wd rows nobody reads
+    if (At == nullptr && codes == nullptr && !wr.touches(r0, r0 + nrows)) return;
     if (tid < ENC_ROWS) sperm[tid] = tid < nrows ? perm[r0 + tid] : 0;
     const int c = tid & (ENC_COLS - 1);
     const int64_t f = c < ncols ? tcol[c0 + c] : 0, f0 = tcol[c0];
@@ -492,7 +507,7 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
                     const int64_t o = (r0 + rr) * K + ucol0 + c0 + 16 * g;       // K = row pitch in bytes; one byte per column
                     // U holds only the rows [u_lo, u_hi) (the target rows of this rank)
                     if (r0 + rr >= u_lo && r0 + rr < u_hi) *reinterpret_cast<uint4 *>(U + o - u_lo * K) = u;
-                    *reinterpret_cast<uint4 *>(Wd + o) = w;
+                    if (wr.has(r0 + rr)) *reinterpret_cast<uint4 *>(Wd + o) = w;
                 }
                 cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
                 cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
@@ -508,7 +523,7 @@ __global__ void __launch_bounds__(256, 6) onehot_encode_v3_kernel(
                         const int64_t o = (r0 + rr) * K + ucol0 + c0 + cc;
                         if (r0 + rr >= u_lo && r0 + rr < u_hi)
                             U[o - u_lo * K] = (int8_t)(code == 0u ? 0x02u : code == 1u ? 0x20u : 0u);
-                        Wd[o] = (int8_t)(code == 0u ? 0x24u : code == 1u ? 0x42u : 0u);
+                        if (wr.has(r0 + rr)) Wd[o] = (int8_t)(code == 0u ? 0x24u : code == 1u ? 0x42u : 0u);
                         cnt += code != 2u ? 1 : 0;
                     }
 #pragma unroll
@@ -600,7 +615,7 @@ static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
     if (lean) {
         onehot_encode_v3_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(ds->x), ds->ldx, ds->d_perm.ptr,
                                                       ws.rcol.ptr, n, pr, (int64_t)Kb, ws.ldt, 0, ws.Ur.ptr, ws.Wdr.ptr, nullptr,
-                                                      nullptr, nullptr, ws.srow_r.ptr, nullptr, 0, n, nullptr, 0);
+                                                      nullptr, nullptr, ws.srow_r.ptr, nullptr, 0, n, nullptr, 0, WdRows{0, n, 0, 0});
         FS_CUDA(cudaGetLastError());
         ++*launches;
         return;
@@ -609,7 +624,7 @@ static void build_removed(fs_dataset *ds, WorkSet &ws, int *launches) {
     onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,        \
                                                   ws.rcol.ptr, ws.roff.ptr, ds->d_vals.ptr, as_f32, n, pr, (int64_t)Kb, \
                                                   ws.ldt, 0, ws.Ur.ptr, ws.Wdr.ptr, nullptr, nullptr, nullptr,    \
-                                                  ws.srow_r.ptr, nullptr, all_ident, 0, n, nullptr, 0)
+                                                  ws.srow_r.ptr, nullptr, all_ident, 0, n, nullptr, 0, WdRows{0, n, 0, 0})
     switch (ds->dtype) {
         case FS_U8: FS_ENCODE_R(uint8_t); break;
         case FS_I8: FS_ENCODE_R(int8_t); break;
@@ -702,6 +717,20 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
     // One fused launch when the accumulation operands cover the same columns as the distance operands;
     // in a multi-GPU group two: the distance operands of ALL active columns (every rank needs Wd of all
     // samples), then the accumulation operands of this rank's slice only.
+    // Wd rows this rank's distance kernel reads (see WdRows)
+    WdRows wr{0, n, 0, 0};
+    {
+        const char *env_sym = getenv("FS_B200_SYMMETRIC");
+        if (ws.group_call && ds->peers_on && ds->peers.world > 1 && !(env_sym && env_sym[0] == '0')) {
+            const DistPeers &pr = ds->peers;
+            const int G = pr.world, r = pr.rank, last = r + G / 2;          // ranks r .. r + floor(G / 2) on the ring
+            if (last < G) {
+                wr = WdRows{pr.starts[r], pr.starts[last + 1], 0, 0};
+            } else {
+                wr = WdRows{pr.starts[r], n, 0, pr.starts[last - G + 1]};
+            }
+        }
+    }
     auto launch = [&](int64_t c_lo, int64_t c_hi, bool want_dist, bool want_acc, bool want_codes) {
         const int64_t pc = c_hi - c_lo;
         if (pc <= 0 || (!want_dist && !want_acc && !want_codes)) return;
@@ -720,13 +749,13 @@ void build_onehot(fs_dataset *ds, WorkSet &ws, int *launches) {
         if (lean) {
             onehot_encode_v3_kernel<<<grid, 256, 0, st>>>(static_cast<const uint8_t *>(ds->x), ds->ldx, ds->d_perm.ptr,
                                                           ws.tcol.ptr + c_lo, n, pc, (int64_t)Kb, ws.ldt, ws.ldc, Uo, Wo, Ao, Co,
-                                                          codes, So, Ko, ws.u_lo, ws.u_hi, To, c_lo);
+                                                          codes, So, Ko, ws.u_lo, ws.u_hi, To, c_lo, wr);
         } else {
 #define FS_ENCODE(T)                                                                                              \
     onehot_encode_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(ds->x), ds->ldx, ds->d_perm.ptr,        \
                                                   ws.tcol.ptr + c_lo, off, ds->d_vals.ptr, as_f32, n, pc, (int64_t)Kb, \
                                                   ws.ldt, ws.ldc, Uo, Wo, Ao, Co, codes, So, Ko, all_ident, ws.u_lo,    \
-                                                  ws.u_hi, To, uk0)
+                                                  ws.u_hi, To, uk0, wr)
             switch (ds->dtype) {
                 case FS_U8: FS_ENCODE(uint8_t); break;
                 case FS_I8: FS_ENCODE(int8_t); break;

@@ -157,7 +157,7 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
     timer.begin(PH_GATHER);
     const auto prep0 = std::chrono::steady_clock::now();
     build_workset(ds, feat_idx, n_kept, allow_tensor, algo == FS_RELIEFF, targets[0], (int64_t)targets.size(),
-                  contiguous, slab_cacheable, want_split, &launches);
+                  contiguous, slab_cacheable, want_split, group_call, &launches);
     const double ms_prep = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - prep0).count();
     timer.end();
     const WorkSet &ws = ds->ws;
@@ -182,7 +182,7 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
                 ds->dd_valid = false;
                 ds->ws.valid = false;
                 build_workset(ds, feat_idx, n_kept, allow_tensor, algo == FS_RELIEFF, targets[0], (int64_t)targets.size(),
-                              contiguous, slab_cacheable, want_split, &launches);
+                              contiguous, slab_cacheable, want_split, group_call, &launches);
             }
             ds->dd_valid = false;
         }

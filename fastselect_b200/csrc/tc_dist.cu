@@ -54,7 +54,19 @@ constexpr int BAND = 16;        // row blocks per rasterisation band
 // operand slabs through L2 -- one GPU uses groups of 8, i.e. one rasterisation band), and inside
 // a group on the diagonal the single super-blocks alternate.  Across GPUs the groups are single
 // super-blocks, which balances the ranks' shares best.
-__host__ __device__ inline bool dist_row_side(int sb_i, int sb_j, int coarse_shift) {
+// Between two RANKS the blocks go by distance on the ring of ranks: rank r computes every block against
+// the ranks r+1 .. r+ceil(G/2)-1 (and none against the ranks that far behind it); with an even number of
+// ranks the opposite rank's blocks are split by the checkerboard.  Every rank then needs the sample
+// operand Wd only for its own samples and those of the floor(G/2) ranks after it (onehot.cu encodes no
+// more), and the work stays balanced.
+__host__ __device__ inline bool dist_row_side(int sb_i, int sb_j, int coarse_shift, int rank_i = 0, int rank_j = 0,
+                                              int world = 1) {
+    if (rank_i != rank_j) {
+        const int d = (rank_j - rank_i + world) % world;
+        if (2 * d < world) return true;
+        if (2 * d > world) return false;
+        return (((sb_i + sb_j) & 1) == 0) == (rank_j > rank_i);
+    }
     if (sb_i == sb_j) return true;
     const int ci = sb_i >> coarse_shift, cj = sb_j >> coarse_shift;
     if (ci != cj) return (((ci + cj) & 1) == 0) == (cj > ci);
@@ -155,7 +167,7 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // symmetric mode: checkerboard over super-blocks (see the header); sb_i = this tile's super-row
     const int sb_i = peers.sb_base[peers.rank] + (tile_y >> 1), sb_j = tile_x;
     const bool diagonal = sb_i == sb_j;
-    if (symmetric && !dist_row_side(sb_i, sb_j, peers.coarse_shift)) return;
+    if (symmetric && !dist_row_side(sb_i, sb_j, peers.coarse_shift, peers.rank, owner, peers.world)) return;
     const bool mirror = symmetric && !diagonal;
     int32_t *Dd = peers.slab[peers.rank];                         // may alias Dm: no __restrict__
     int32_t *Dm = peers.slab[owner];                  // slab that receives the transposed tile
@@ -282,7 +294,7 @@ tc_dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int64_t cend = n0 + BN < peers.starts[owner + 1] ? n0 + BN : peers.starts[owner + 1];
     const int sb_i = peers.sb_base[peers.rank] + pair_y, sb_j = tile_x;
     const bool diagonal = sb_i == sb_j;
-    if (symmetric && !dist_row_side(sb_i, sb_j, peers.coarse_shift)) return;      // both CTAs of the pair take the same exit
+    if (symmetric && !dist_row_side(sb_i, sb_j, peers.coarse_shift, peers.rank, owner, peers.world)) return;      // both CTAs of the pair take the same exit
     const bool mirror = symmetric && !diagonal;
     int32_t *Dd = peers.slab[peers.rank];
     int32_t *Dm = peers.slab[owner];
@@ -401,7 +413,9 @@ void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, const 
         for (int by = 0; by < rows_y; ++by)
             for (int bx = 0; bx < tiles_x; ++bx) {
                 const int sb_i = peers.sb_base[peers.rank] + (by >> 1);
-                tiles += (!symmetric || dist_row_side(sb_i, bx, peers.coarse_shift)) ? 1 : 0;
+                int owner = 0;
+                while (owner + 1 < peers.world && bx >= peers.sb_base[owner + 1]) ++owner;
+                tiles += (!symmetric || dist_row_side(sb_i, bx, peers.coarse_shift, peers.rank, owner, peers.world)) ? 1 : 0;
             }
         *ops += 2.0 * BM * BN * (2.0 * (double)K) * (double)tiles;      // K is the operand row length in bytes
     }
