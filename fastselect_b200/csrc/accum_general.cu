@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(kAccThreads)
 accum_general_kernel(const T *__restrict__ xg, int64_t n, int64_t ld, const float *__restrict__ recip,
                      const uint8_t *__restrict__ ctype, const T *__restrict__ xa, const int8_t *__restrict__ sel,
                      int64_t ldn, const RowInfo *__restrict__ rinfo, int64_t R, int64_t rows_per_cta,
-                     double *__restrict__ partial) {
-    constexpr int FT = kChunkBytes / sizeof(T);
+                     double *__restrict__ partial, int FT) {
+    // FT: columns per 128-byte chunk of the matrix the chunk types were laid out for (32 float32 / 16 float64)
     __shared__ __align__(16) float scoef[2][kAccJT][kAccRows];
     __shared__ float stab[kAccRows][5];
 
@@ -227,14 +227,28 @@ void launch_accum_general(const WorkSet &ws, int64_t n, const void *xa, const in
     if (ws.pg == 0 || R == 0) return;
     const int64_t rows = rows_per_cta_for(R, ws.ldg);
     dim3 grid((unsigned)n_part, (unsigned)ceil_div(ws.ldg, kAccThreads));
-    if (ws.elem == 4)
+    // float64 arithmetic (SURF) with only continuous columns: the reference STORES each term as float32
+    // (diffs_from_i, SURF.py:143-158) and adds float32 sums, so the accumulation runs on the float32 image
+    // of the offset-free columns (x - column minimum: |x'| <= range, so the image keeps 2^-24 of the RANGE,
+    // not of |x|) with the float32 kernel -- FP32 pipe instead of three FP64 operations per (pair, feature).
+    // Target rows given as a view into xg (the production path); a gathered copy (fs_debug_rows) stays on
+    // the float64 kernel.
+    const char *xg_lo = ws.xg.ptr, *xg_hi = ws.xg.ptr + (size_t)n * ws.ldg * ws.elem;
+    const char *env32 = getenv("FS_B200_SURF_ACCUM_F32");
+    const bool view = static_cast<const char *>(xa) >= xg_lo && static_cast<const char *>(xa) < xg_hi;
+    if (ws.elem == 8 && ws.have_xg32 && view && !(env32 && env32[0] == '0')) {
+        const int64_t row0 = (static_cast<const char *>(xa) - xg_lo) / ((int64_t)ws.ldg * ws.elem);
+        accum_general_kernel<float><<<grid, kAccThreads, 0, st>>>(
+            ws.xg32.ptr, n, ws.ldg, ws.rg.ptr, ws.ctype.ptr, ws.xg32.ptr + (size_t)row0 * ws.ldg, sel, ldn, rinfo, R, rows,
+            partial, kChunkBytes / 8);
+    } else if (ws.elem == 4)
         accum_general_kernel<float><<<grid, kAccThreads, 0, st>>>(
             reinterpret_cast<const float *>(ws.xg.ptr), n, ws.ldg, ws.rg.ptr, ws.ctype.ptr,
-            static_cast<const float *>(xa), sel, ldn, rinfo, R, rows, partial);
+            static_cast<const float *>(xa), sel, ldn, rinfo, R, rows, partial, kChunkBytes / 4);
     else
         accum_general_kernel<double><<<grid, kAccThreads, 0, st>>>(
             reinterpret_cast<const double *>(ws.xg.ptr), n, ws.ldg, ws.rg.ptr, ws.ctype.ptr,
-            static_cast<const double *>(xa), sel, ldn, rinfo, R, rows, partial);
+            static_cast<const double *>(xa), sel, ldn, rinfo, R, rows, partial, kChunkBytes / 8);
     FS_CUDA(cudaGetLastError());
     ++*launches;
 }

@@ -187,6 +187,8 @@ struct WorkSet {
     int64_t ldg = 0;       // padded column count (multiple of the chunk)
     int elem = 4;          // sizeof(T): 4 (FS_ARITH_F32) or 8 (FS_ARITH_F64)
     DevBuf<char> xg;       // [n, ldg] of T, internal row order
+    DevBuf<float> xg32;    // [n, ldg] float32 image of (x - column minimum): SURF's accumulation (float64 arithmetic, continuous columns only)
+    bool have_xg32 = false;
     DevBuf<float> rg;      // [ldg] recip (0 in padding)
     DevBuf<uint8_t> ctype; // [ldg / chunk]
     DevBuf<int64_t> gcol;  // [pg] original column of each general column

@@ -314,6 +314,17 @@ __global__ void __launch_bounds__(256) gather_general_kernel(const Tin *__restri
     }
 }
 
+// xg32[r, c] = (float)(xg[r, c] - min of the column): see launch_accum_general
+__global__ void __launch_bounds__(256) narrow_general_kernel(const double *__restrict__ xg, const int64_t *__restrict__ col,
+                                                             const double *__restrict__ cmin, int64_t n, int64_t ldg,
+                                                             float *__restrict__ out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ldg) return;
+    const int64_t src = col[c];
+    const double m = src >= 0 ? cmin[src] : 0.0;
+    for (int64_t r = blockIdx.y; r < n; r += gridDim.y) out[r * ldg + c] = (float)(xg[r * ldg + c] - m);
+}
+
 template <typename Tin>
 static void run_gather(fs_dataset *ds, WorkSet &ws, int *launches) {
     dim3 grid((unsigned)ceil_div(ws.ldg, 256), (unsigned)std::min<int64_t>(ds->n, 4096));
@@ -519,6 +530,7 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
     ++ws.lists_version;
     ws.lists_uploaded = false;
     }   // !lists_ok
+    ws.have_xg32 = false;
     if (ws.pg > 0) {
         ws.xg.reserve((size_t)ds->n * ws.ldg * ws.elem);
         switch (ds->dtype) {
@@ -526,6 +538,15 @@ void build_workset(fs_dataset *ds, const int64_t *feat_idx, int64_t n_kept, bool
             case FS_I8: run_gather<int8_t>(ds, ws, launches); break;
             case FS_F32: run_gather<float>(ds, ws, launches); break;
             case FS_F64: run_gather<double>(ds, ws, launches); break;
+        }
+        ws.have_xg32 = ws.elem == 8 && ws.n_cmp == 0;
+        if (ws.have_xg32) {
+            ws.xg32.reserve((size_t)ds->n * ws.ldg);
+            dim3 grid((unsigned)ceil_div(ws.ldg, 256), (unsigned)std::min<int64_t>(ds->n, 4096));
+            narrow_general_kernel<<<grid, 256, 0, ds->stream>>>(reinterpret_cast<const double *>(ws.xg.ptr), ws.gcol.ptr,
+                                                                ds->d_cmin.ptr, ds->n, ws.ldg, ws.xg32.ptr);
+            FS_CUDA(cudaGetLastError());
+            ++*launches;
         }
     }
     ws.K = 0;
