@@ -179,3 +179,33 @@ def test_turf_on_genotypes_matches_oracle_driven_turf(native):
     # reference's order: up to 7.7e-7 * max|W| away from the exact value), hence 2e-6
     np.testing.assert_allclose(t.feature_importances_, first, rtol=1e-5, atol=2e-6 * np.abs(first).max())
     assert np.array_equal(t.top_features_, np.sort(active))
+
+
+def test_non_integer_labels_follow_the_reference_cpu_semantics(native):
+    """Labels are only compared for equality (MultiSURF.py:216), so y = {0.2, 0.7} must score like y = {0, 1}
+    (the reference's CPU semantics; its own GPU branch truncates with astype(int32), MultiSURF.py:424, which
+    would merge these two classes).  SURF keeps the reference's truncation on every backend (SURF.py:363,371)."""
+    from datasets import mixed
+
+    x, y = mixed(51, 160, 24, 2)
+    yf = np.where(y == 0, 0.2, 0.7)
+    a = fsb.MultiSURF(n_features_to_select=4, backend="gpu").fit(x, y)
+    b = fsb.MultiSURF(n_features_to_select=4, backend="gpu").fit(x, yf)
+    assert np.array_equal(a.feature_importances_, b.feature_importances_)
+    r = fsb.ReliefF(n_features_to_select=4, n_neighbors=5, backend="gpu").fit(x, yf)
+    r0 = fsb.ReliefF(n_features_to_select=4, n_neighbors=5, backend="gpu").fit(x, y)
+    assert np.array_equal(r.feature_importances_, r0.feature_importances_)
+
+
+def test_wide_integer_input_is_narrowed_not_converted(native):
+    """np.random.randint returns int64: the estimators narrow it to int8 before validation (values
+    unchanged) instead of letting sklearn convert it to float32; the scores are those of the int8 matrix."""
+    from datasets import epistatic_genotypes
+
+    x8, y = epistatic_genotypes(52, 300, 200)
+    a = fsb.MultiSURF(n_features_to_select=5, backend="gpu").fit(x8, y)
+    b = fsb.MultiSURF(n_features_to_select=5, backend="gpu").fit(x8.astype(np.int64), y)
+    assert np.array_equal(a.feature_importances_, b.feature_importances_)
+    t = fsb.TuRF(fsb.MultiSURF(backend="gpu", n_features_to_select=5), n_features_to_select=8, pct_remove=0.3).fit(x8.astype(np.int64), y)
+    t0 = fsb.TuRF(fsb.MultiSURF(backend="gpu", n_features_to_select=5), n_features_to_select=8, pct_remove=0.3).fit(x8, y)
+    assert np.array_equal(t.top_features_, t0.top_features_)
