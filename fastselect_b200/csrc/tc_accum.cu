@@ -101,7 +101,7 @@ __device__ __forceinline__ int2 coef_limbs(double c) {
 // (broadcast) loads instead of staging them through shared memory behind a barrier per item.
 __global__ void __launch_bounds__(256) accum_consts_kernel(const TileDesc *__restrict__ tiles, int num_tiles,
                                                            const RowInfo *__restrict__ rinfo, int2 *__restrict__ limbs,
-                                                           int32_t *__restrict__ rsum, int rsum_as_float, int coef_as_double) {
+                                                           int32_t *__restrict__ rsum, int rsum_as_float) {
     const int t = blockIdx.x >> 1, phase = blockIdx.x & 1, e = threadIdx.x;
     if (t >= num_tiles) return;
     const TileDesc d = tiles[t];
@@ -112,9 +112,7 @@ __global__ void __launch_bounds__(256) accum_consts_kernel(const TileDesc *__res
         c = phase == 0 ? ri.coef[FS_MASK_NEAR_HIT] : ri.coef[FS_MASK_NEAR_MISS];
         rs = phase == 0 ? ri.n_hit - ri.n_far_hit : ri.n_miss - ri.n_far_miss;
     }
-    // (experiment FS_B200_ACCUM_F64=1: the coefficient itself as a double, for a DFMA epilogue)
-    const long long cbits = __double_as_longlong(c);
-    limbs[(size_t)blockIdx.x * 256 + e] = coef_as_double ? make_int2((int)(cbits & 0xffffffffLL), (int)(cbits >> 32)) : coef_limbs(c);
+    limbs[(size_t)blockIdx.x * 256 + e] = coef_limbs(c);
     // the paired epilogue works on the FP32 accumulators directly: |rs| <= n < 2^22 is exact in float
     rsum[(size_t)blockIdx.x * 256 + e] = rsum_as_float ? __float_as_int((float)rs) : rs;
 }
@@ -131,7 +129,7 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                 const TileDesc *__restrict__ tiles, int num_tiles, int groups, int group_tiles, int m_blocks,
                 const int64_t *__restrict__ ids, int contiguous, const int2 *__restrict__ limbs,
                 const int32_t *__restrict__ rsum, const uint8_t *__restrict__ codesT, int64_t ldt,
-                const uint32_t *__restrict__ krow, int64_t K_rows, double *__restrict__ tpartial, int use_f64) {
+                const uint32_t *__restrict__ krow, int64_t K_rows, double *__restrict__ tpartial) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // pointer arithmetic only (no integer round trip), so the compiler keeps the shared address space
     unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -271,7 +269,6 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
             const uint32_t last4 = (meta >> 28) * 0x01010101u;
             const uint32_t oth4 = own4 ^ 0x01010101u;            // kPair: the partner lane's plane (codes 0 <-> 1)
             long long ah0 = 0, ah1 = 0, al0 = 0, al1 = 0;     // exact fixed-point sums (two chains)
-            double da0 = 0.0, da1 = 0.0;                      // use_f64 (paired epilogue only): float64 sums
             for (int t = g * group_tiles; t < tile_end; ++t) {
                 const TileDesc d = s_tiles[t];
                 // value codes of this thread's 128 targets in its column (issued before the
@@ -388,7 +385,7 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                                 const float4 rs4 = __ldg(rr + (e >> 2));
                                 const int4 ca = __ldg(cc + (e >> 1)), cb = __ldg(cc + (e >> 1) + 1);
                                 const float rsv[4] = {rs4.x, rs4.y, rs4.z, rs4.w};
-                                uint32_t tb4[4];
+                                int tt[4];
 #pragma unroll
                                 for (int b = 0; b < 4; ++b) {
                                     const float gm = __uint_as_float(mine[e + b]), go = __uint_as_float(oth[e + b]);
@@ -398,22 +395,12 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
                                     const uint32_t ta = __float_as_uint(rsv[b] - gm), tb = __float_as_uint(rsv[b] - go);
                                     const uint32_t tl = __float_as_uint(gm + go);
                                     const uint32_t t1 = (ta & mo) | (tl & ~mo);
-                                    tb4[b] = (tb & mt) | (t1 & ~mt);
+                                    tt[b] = tc::f32_to_int_exact((tb & mt) | (t1 & ~mt));
                                 }
-                                if (use_f64) {
-                                    // float64 scaling: one convert and one DFMA per (column, target)
-                                    da0 = fma((double)__uint_as_float(tb4[0]), __hiloint2double(ca.y, ca.x), da0);
-                                    da1 = fma((double)__uint_as_float(tb4[1]), __hiloint2double(ca.w, ca.z), da1);
-                                    da0 = fma((double)__uint_as_float(tb4[2]), __hiloint2double(cb.y, cb.x), da0);
-                                    da1 = fma((double)__uint_as_float(tb4[3]), __hiloint2double(cb.w, cb.z), da1);
-                                } else {
-                                    const int tt0 = tc::f32_to_int_exact(tb4[0]), tt1 = tc::f32_to_int_exact(tb4[1]);
-                                    const int tt2 = tc::f32_to_int_exact(tb4[2]), tt3 = tc::f32_to_int_exact(tb4[3]);
-                                    ah0 += (long long)tt0 * ca.x; al0 += (long long)tt0 * ca.y;
-                                    ah1 += (long long)tt1 * ca.z; al1 += (long long)tt1 * ca.w;
-                                    ah0 += (long long)tt2 * cb.x; al0 += (long long)tt2 * cb.y;
-                                    ah1 += (long long)tt3 * cb.z; al1 += (long long)tt3 * cb.w;
-                                }
+                                ah0 += (long long)tt[0] * ca.x; al0 += (long long)tt[0] * ca.y;
+                                ah1 += (long long)tt[1] * ca.z; al1 += (long long)tt[1] * ca.w;
+                                ah0 += (long long)tt[2] * cb.x; al0 += (long long)tt[2] * cb.y;
+                                ah1 += (long long)tt[3] * cb.z; al1 += (long long)tt[3] * cb.w;
                             }
                         } else {
                         const int4 *cc = reinterpret_cast<const int4 *>(s_c + half * HALF + c0);
@@ -447,7 +434,7 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
             // and unit: the sums stay below 2^60
             if (row_live)
                 tpartial[((int64_t)g * PARTS + half) * K_rows + mrow] =
-                    ((double)(ah0 + ah1) * (double)(1 << kLimbBits) + (double)(al0 + al1)) * (1.0 / 4503599627370496.0) + (da0 + da1);
+                    ((double)(ah0 + ah1) * (double)(1 << kLimbBits) + (double)(al0 + al1)) * (1.0 / 4503599627370496.0);
         }
     }
     __syncthreads();
@@ -543,17 +530,14 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
         consts.reserve((size_t)nt * 2 * 256 * 3 + 512);   // slack: the epilogue prefetches one item ahead
         int2 *limbs = reinterpret_cast<int2 *>(consts.ptr);
         int32_t *rsum = consts.ptr + (size_t)nt * 2 * 256 * 2;
-        const char *env_f64 = getenv("FS_B200_ACCUM_F64");
-        const int use_f64 = (paired && env_f64 && env_f64[0] == '1') ? 1 : 0;
-        accum_consts_kernel<<<2 * nt, 256, 0, st>>>(reinterpret_cast<const TileDesc *>(d_tiles), nt, rinfo, limbs, rsum, paired ? 1 : 0,
-                                                    use_f64);
+        accum_consts_kernel<<<2 * nt, 256, 0, st>>>(reinterpret_cast<const TileDesc *>(d_tiles), nt, rinfo, limbs, rsum, paired ? 1 : 0);
         ++*launches;
         const int units = m_blocks * groups;
         const int grid = units < sms ? units : sms;
         kernel<<<grid, THREADS, SMEM_BYTES, st>>>(
             tmap_at, tmap_mh, tmap_mm, (int)ceil_div(n, KS), R, reinterpret_cast<const TileDesc *>(d_tiles), nt,
             groups, group_tiles, m_blocks, d_ids, contiguous ? 1 : 0, limbs, rsum, codesT, ldt, krow, K_rows,
-            tpartial.ptr + (size_t)groups_done * PARTS * K_rows, use_f64);
+            tpartial.ptr + (size_t)groups_done * PARTS * K_rows);
         FS_CUDA(cudaGetLastError());
         ++*launches;
         groups_done += groups;
