@@ -561,7 +561,7 @@ def own_arm(args):
                  if kernels[top]["bound"] == "fp32-issue" else "measured copy (MEASURED_PEAKS.json)"))
 
     # the CPU baseline is reported at N = 1 only (rank 0)
-    cpu = cpu_baseline(w) if world == 1 else None
+    cpu = cpu_baseline(w) if world == 1 and not os.environ.get("FS_BENCH_SKIP_CPU") else None   # (kernel experiments skip the CPU leg)
     sharding = f"target rows x{world}"
     if collective:
         sharding += (", symmetric distance tiles / neighbour masks / weight slices stored into the peers' arenas over NVLink, "

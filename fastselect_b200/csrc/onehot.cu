@@ -25,7 +25,7 @@ void launch_tc_dist(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, const 
                     const DistPeers &peers, cudaStream_t st, int *launches, double *ops);
 int tc_accum_tile_desc_ints();
 int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
-                    int64_t R, const int64_t *d_ids, bool contiguous, bool paired, const RowInfo *rinfo, const uint8_t *codesT,
+                    int64_t R, const int64_t *d_ids, bool contiguous, int pair_mode, const RowInfo *rinfo, const uint8_t *codesT,
                     int64_t ldt, const uint32_t *krow, int64_t K_rows, DevBuf<double> &tpartial, int32_t *d_tiles,
                     DevBuf<int32_t> &consts, cudaStream_t st, int *launches, const int64_t *h_ids, const int32_t *h_y,
                     const int64_t *h_cls_start, double *ops);
@@ -64,6 +64,25 @@ CUtensorMap make_tmap_u8_sw128(const void *base, uint64_t row_bytes, uint64_t ro
     FS_REQUIRE(rc == CUDA_SUCCESS, FS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): base=%p row_bytes=%llu rows=%llu pitch=%llu",
                (int)rc, base, (unsigned long long)row_bytes, (unsigned long long)rows, (unsigned long long)pitch_bytes);
     return m;
+}
+
+bool make_tmap_u8_sw128_nd(CUtensorMap *out, const void *base, int rank, const uint64_t *dims, const uint64_t *strides,
+                           const uint32_t *box) {
+    CUtensorMap m;
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gd[i] = dims[i];
+        bx[i] = box[i];
+        estr[i] = 1;
+        if (i + 1 < rank) gs[i] = strides[i];
+    }
+    const CUresult rc = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return false;
+    *out = m;
+    return true;
 }
 
 // ---------------------------------------------------------------------------
@@ -934,11 +953,35 @@ void launch_accum_tensor(fs_dataset *ds, const WorkSet &ws, int algo, const int6
     ds->tile_desc.reserve(tc_accum_tile_desc_ints());
     // K of this GEMM is the sample index; At and the masks hold FP4 nibbles: rows of (n + 1) / 2 bytes
     const uint64_t row_bytes = (uint64_t)((n + 1) / 2);
-    const CUtensorMap tat = make_tmap_u8_sw128(ws.At.ptr, row_bytes, (uint64_t)ws.Ka, (uint64_t)(ws.ldt / 2), 128);
-    const CUtensorMap tmh = make_tmap_u8_sw128(mask_h, row_bytes, (uint64_t)R, (uint64_t)(ldn / 2), 240);
-    const CUtensorMap tmm = make_tmap_u8_sw128(mask_m, row_bytes, (uint64_t)R, (uint64_t)(ldn / 2), 240);
-    // every column with exactly three values: one-hot rows 2c, 2c + 1 are column c's two planes (paired epilogue)
-    const int parts = launch_tc_accum(tat, tmh, tmm, n, R, d_row_ids, contiguous, ws.all_v3, rinfo, ws.codesT.ptr, ws.ldt,
+    CUtensorMap tat = make_tmap_u8_sw128(ws.At.ptr, row_bytes, (uint64_t)ws.Ka, (uint64_t)(ws.ldt / 2), 128);
+    CUtensorMap tmh = make_tmap_u8_sw128(mask_h, row_bytes, (uint64_t)R, (uint64_t)(ldn / 2), 240);
+    CUtensorMap tmm = make_tmap_u8_sw128(mask_m, row_bytes, (uint64_t)R, (uint64_t)(ldn / 2), 240);
+    // every column with exactly three values: one-hot rows 2c, 2c + 1 are column c's two planes.  Default: the
+    // merged-plane epilogue, whose operands are staged in a permuted row order (tc_accum.cu): At rows as
+    // (column mod 8, plane, column / 8), mask rows as (e, j, g, chunk) with row strides 1, 4, 2, 16 -- the box of a
+    // tile may run up to 239 rows past the tile's first row, hence the padding behind both masks.
+    // FS_B200_ACCUM_PAIR = 1: paired epilogue (planes meet by shuffle), 0: one thread per one-hot row.
+    // 3 (default): the merged-plane kernel as clusters of two CTAs (cta_group::2): tiles of <= 224 rows, every CTA
+    // stages half of a tile's chunks (box of 7)
+    int pair_mode = ws.all_v3 ? 3 : 0;
+    if (const char *e = getenv("FS_B200_ACCUM_PAIR"))
+        if (ws.all_v3 && e[0] >= '0' && e[0] <= '3') pair_mode = e[0] - '0';
+    if (pair_mode >= 2) {
+        const uint64_t pa_b = (uint64_t)(ws.ldt / 2), pm_b = (uint64_t)(ldn / 2);
+        const uint64_t da[4] = {row_bytes, 8, 2, (uint64_t)(ws.Ka / 16)}, sa[3] = {2 * pa_b, pa_b, 16 * pa_b};
+        const uint32_t ba[4] = {128, 8, 2, 8};
+        const uint64_t dm[5] = {row_bytes, (uint64_t)R, 4, 2, pair_mode == 3 ? 14u : 15u}, sm[4] = {pm_b, 4 * pm_b, 2 * pm_b, 16 * pm_b};
+        const uint32_t bm[5] = {128, 2, 4, 2, pair_mode == 3 ? 7u : 15u};
+        const bool ok = make_tmap_u8_sw128_nd(&tat, ws.At.ptr, 4, da, sa, ba) && make_tmap_u8_sw128_nd(&tmh, mask_h, 5, dm, sm, bm) &&
+                        make_tmap_u8_sw128_nd(&tmm, mask_m, 5, dm, sm, bm);
+        if (!ok) {   // the driver refused a permuted map: the 2-D maps above and the paired epilogue still apply
+            tat = make_tmap_u8_sw128(ws.At.ptr, row_bytes, (uint64_t)ws.Ka, (uint64_t)(ws.ldt / 2), 128);
+            tmh = make_tmap_u8_sw128(mask_h, row_bytes, (uint64_t)R, (uint64_t)(ldn / 2), 240);
+            tmm = make_tmap_u8_sw128(mask_m, row_bytes, (uint64_t)R, (uint64_t)(ldn / 2), 240);
+            pair_mode = 1;
+        }
+    }
+    const int parts = launch_tc_accum(tat, tmh, tmm, n, R, d_row_ids, contiguous, pair_mode, rinfo, ws.codesT.ptr, ws.ldt,
                                       ws.krow.ptr, ws.Ka_used, ds->tpartial, ds->tile_desc.ptr, ds->tile_consts, st, launches,
                                       h_row_ids, ds->y_sorted.data(), ds->cls_start.data(), ops);
     reduce_tensor_partials_kernel<<<(unsigned)ceil_div(pa, 256), 256, 0, st>>>(ds->tpartial.ptr, parts, ws.Ka_used,

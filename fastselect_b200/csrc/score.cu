@@ -201,8 +201,10 @@ static void run_pipeline(fs_dataset *ds, int algo, int use_star, int32_t k, cons
         rinfo_buf = reinterpret_cast<RowInfo *>(arena + ds->glayout.off_rinfo) + shard0;
     } else {
         if (use_masks) {
-            ds->maskH.reserve((size_t)Rmax * ldn);
-            ds->maskM.reserve((size_t)Rmax * ldn);
+            // rows of ldn / 2 bytes; 256 rows of padding: the accumulation kernel's permuted tile box may
+            // run up to 239 rows past a tile's first row (onehot.cu::launch_accum_tensor)
+            ds->maskH.reserve((size_t)(Rmax + 256) * (ldn / 2));
+            ds->maskM.reserve((size_t)(Rmax + 256) * (ldn / 2));
             mask_h = ds->maskH.ptr;
             mask_m = ds->maskM.ptr;
         }

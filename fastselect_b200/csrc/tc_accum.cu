@@ -42,6 +42,7 @@
 // for 3-valued genotypes.  Partials are written per (tile group, column part, one-hot row) and
 // reduced in a fixed order.
 #include <algorithm>
+#include <cstring>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -69,6 +70,14 @@ constexpr int HALF = BN / (EPI_WARPS / 4); // 80 target columns per epilogue thr
 constexpr int PARTS = EPI_WARPS / 4;      // column parts = partial vectors per (group, one-hot row)
 constexpr int TMEM_COLS = 512;            // 2 accumulator buffers x 240 columns + scale factors
 constexpr int SF_COL = 2 * BN;            // 8 columns of UE8M0 1.0 (0x7f) for both operands' block scales
+// CTA pairs (merged-plane kernel): tiles of <= 224 target rows, each CTA stages half of them (7 chunks of 16)
+constexpr int CG2_BN = 224;
+constexpr int CG2_B_BYTES = (CG2_BN / 2) * BK;   // 14 KB
+constexpr int CG2_STAGES = 6;
+constexpr int PREFETCH_MAX_K_BLOCKS = 32;   // L2 prefetch of the next unit's At block: up to 8192 samples
+constexpr int CG2_SMEM_BYTES = CG2_STAGES * (A_BYTES + CG2_B_BYTES) + 1024 + BAR_BYTES;
+constexpr int MERGED_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
+static_assert(CG2_B_BYTES % 1024 == 0 && CG2_SMEM_BYTES <= 232448, "pair stage shape");
 
 // A tile of target rows and the K blocks (of 128 samples) its two masks can be non-zero in:
 // hit mask: blocks [hb0, hb1); miss mask: blocks [0, ib0) and [ib1, num_k_blocks).
@@ -78,6 +87,16 @@ struct __align__(16) TileDesc {
     int32_t pad0, pad1;
 };
 static_assert(sizeof(TileDesc) == 32, "TileDesc layout");
+// merged-plane kernel: the tile table travels as a kernel parameter (constant bank, uniform loads)
+constexpr int MERGED_MAX_TILES = 112;
+struct TileTable {
+    TileDesc t[MERGED_MAX_TILES];
+};
+// 16 epilogue warps (four per TMEM lane quarter = four column parts; chunks of 16 targets are dealt to the parts
+// round-robin, at most M_CHUNKS each), then the producer and the MMA issuer
+constexpr int M_EPI_WARPS = 16, M_PARTS = M_EPI_WARPS / 4, M_CHUNKS = (BN / 16 + M_PARTS - 1) / M_PARTS;
+constexpr int M_THREADS = 32 * (M_EPI_WARPS + 2);
+constexpr int PRODUCER_WARP = M_EPI_WARPS, MMA_WARP = M_EPI_WARPS + 1;
 static_assert(STAGE_BYTES % 1024 == 0 && HALF % 16 == 0 && SF_COL + 8 <= TMEM_COLS, "tile shape");
 
 // Fixed-point image of a per-target coefficient c (|c| <= 1): C = round(c * 2^52) split into a
@@ -113,8 +132,10 @@ __global__ void __launch_bounds__(256) accum_consts_kernel(const TileDesc *__res
         rs = phase == 0 ? ri.n_hit - ri.n_far_hit : ri.n_miss - ri.n_far_miss;
     }
     limbs[(size_t)blockIdx.x * 256 + e] = coef_limbs(c);
-    // the paired epilogue works on the FP32 accumulators directly: |rs| <= n < 2^22 is exact in float
-    rsum[(size_t)blockIdx.x * 256 + e] = rsum_as_float ? __float_as_int((float)rs) : rs;
+    // the paired epilogue works on the FP32 accumulators directly: |rs| <= n < 2^22 is exact in float;
+    // the merged-plane epilogue (mode 2) wants it with the float -> int bias already added
+    rsum[(size_t)blockIdx.x * 256 + e] =
+        rsum_as_float == 2 ? __float_as_int((float)rs + 12582912.0f) : (rsum_as_float ? __float_as_int((float)rs) : rs);
 }
 
 // kPair: every active column has exactly three values, so one-hot rows 2c and 2c + 1 (two adjacent
@@ -444,6 +465,426 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Merged-plane variant for 0/1/2 columns (every active column owns the two one-hot rows 2c, 2c + 1).
+//
+// The paired kernel above lets the two planes of a column meet through a shuffle; here they meet in
+// ONE thread, because the operands are staged in a permuted row order and the accumulator is read with
+// the 16x256b TMEM fragment (thread t <- lanes t/4 and t/4 + 8, columns 2(t%4), 2(t%4) + 1 of every
+// group of 8; measured, profiles/r02_tmem_frag_probe.txt):
+//   * At tile: 4-D tensor map (bytes, column mod 8, plane, column / 8): shared-memory row = TMEM lane
+//     16 * (c / 8) + 8 * plane + c % 8 for the tile's column c < 64, so lanes L and L + 8 are the two planes
+//     of one column;
+//   * mask tile: 5-D tensor map (bytes, e, j, g, chunk) with row strides 1, 4, 2, 16: shared-memory row =
+//     TMEM column 16 chunk + 8 g + 2 j + e holds target 16 chunk + 4 j + 2 g + e of the tile, so thread
+//     j = t % 4 owns the four CONSECUTIVE targets 16 chunk + 4 j .. + 3 of every chunk (one aligned word of
+//     codesT, two int4 of coefficient limbs, one float4 of row sums).
+// Per (column, target) the thread then has G_0 and G_1 in registers and needs one of rs - G_0, rs - G_1,
+// G_0 + G_1 (selected by the target's own code) times the coefficient: no shuffle, no swap of
+// accumulators, the float -> int bias rides on the row sum, and a thread serves two columns (lane
+// offsets 0 and 16), i.e. two independent dependency chains.  TMEM loads and the per-target constants
+// are double-buffered in registers; the accumulator buffer is handed back to the MMA issuer as soon as
+// the LAST chunk is in registers (before its arithmetic).  Chunks of 16 targets are dealt to the three
+// column parts round-robin (part, part + 3, ...), so a class-tail tile of 80 rows costs two chunk
+// times instead of five.  The four threads of a column fold their sums at the end of a work unit; the
+// partial goes to the slot of one-hot row 2c (0 to the slot of row 2c + 1): the reducer is unchanged.
+constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23: float(kMagic + t) has the bits kBias + t for |t| < 2^22
+constexpr int kBias = 0x4B400000;
+
+struct ChunkConsts {
+    int4 ca, cb;      // (Chi, Clo) of targets 0, 1 and 2, 3 of the thread's four
+    float4 rs;        // mask row sums + kMagic
+};
+
+//
+// kCg2: the kernel runs as CLUSTERS OF TWO CTAs (tcgen05.mma.cta_group::2, M = 256): the pair takes two adjacent
+// blocks of 128 one-hot rows through the same tiles; each CTA stages its own At block and HALF of the mask
+// tile (chunks [0, nch / 2) or [nch / 2, nch), N rounded up to 32), the leader issues the MMAs for both and waits
+// for both epilogues.  The single-CTA kernel moves 46 KB from L2 into shared memory per four MMAs -- with
+// the epilogue switched off it still ran C3 in 1.12 ms against 0.78 ms of MMA time (18.5 TB/s out of L2 over the
+// GPU: the same ceiling the distance GEMM hit before it became CTA pairs) -- the pair moves 30 KB.
+#ifdef FS_ACCUM_EXPERIMENTS
+#define FS_EXP(bit) ((kExp & (bit)) != 0)
+template <bool kCg2, int kExp>
+#else
+#define FS_EXP(bit) false
+template <bool kCg2>
+#endif
+__global__ void __launch_bounds__(M_THREADS, 1)
+tc_accum_merged_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_constant__ CUtensorMap tmap_mh,
+                       const __grid_constant__ CUtensorMap tmap_mm, int num_k_blocks, int64_t R,
+                       const __grid_constant__ TileTable tt, int num_tiles, int groups, int group_tiles, int m_blocks,
+                       const int64_t *__restrict__ ids, int contiguous, const int2 *__restrict__ limbs,
+                       const int32_t *__restrict__ rsum, const uint8_t *__restrict__ codesT, int64_t ldt,
+                       const uint32_t *__restrict__ krow, int64_t K_rows, double *__restrict__ tpartial) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int kStages = kCg2 ? CG2_STAGES : STAGES;
+    constexpr int kBBytes = kCg2 ? CG2_B_BYTES : B_BYTES;            // mask rows this CTA stages per K block
+    constexpr int kStageBytes = A_BYTES + kBBytes;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
+    uint64_t *empty_bar = full_bar + kStages;
+    uint64_t *tfull_bar = empty_bar + kStages;    // [2] accumulator buffer ready
+    uint64_t *tempty_bar = tfull_bar + 2;         // [2] accumulator buffer drained (pairs: the leader's, for both CTAs)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // pairs: both CTAs of a cluster walk the same units; the CTA's block of one-hot rows is 2 * (u / groups) + rank
+    const uint32_t crank = kCg2 ? tc::cluster_ctarank() : 0u;
+    const int worker = kCg2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int workers = kCg2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int units = (kCg2 ? (m_blocks + 1) / 2 : m_blocks) * groups;
+
+    if (warp == PRODUCER_WARP && lane == 0) {
+        tc::prefetch_tmap(&tmap_at);
+        tc::prefetch_tmap(&tmap_mh);
+        tc::prefetch_tmap(&tmap_mm);
+        for (int s = 0; s < kStages; ++s) {
+            tc::mbar_init(&full_bar[s], 1);
+            tc::mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(&tfull_bar[b], 1);
+            // single CTA: every epilogue thread arrives; pairs: one lane per epilogue warp of BOTH CTAs
+            tc::mbar_init(&tempty_bar[b], kCg2 ? 2 * M_EPI_WARPS : 32 * M_EPI_WARPS);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == MMA_WARP) {
+        if constexpr (kCg2) tc::tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+        else tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if constexpr (kCg2) tc::cluster_sync_all();       // the peer's barriers exist before anything signals them
+    tc::tc_fence_after();
+    // the kernel owns ALL 512 TMEM columns, so the allocation starts at column 0, lane 0: a constant the compiler
+    // can keep in uniform registers (checked here, trapped otherwise)
+    if (*tmem_slot != 0u) __trap();
+    constexpr uint32_t tmem_base = 0u;
+    if (warp < 4) {
+        for (int c = 0; c < 8; ++c) tc::tmem_st_32x1(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + SF_COL + c, 0x7f7f7f7fu);
+        tc::tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if constexpr (kCg2) tc::cluster_sync_all();       // both CTAs' scale factors are in place before the leader issues
+    tc::tc_fence_after();
+
+    if (warp == PRODUCER_WARP) {
+        // ===== TMA producer: both operands in the permuted row order described above.  elect.sync rather than
+        // lane == 0 (here and in the MMA issuer): it tells the compiler that ONE thread runs the loop, so the
+        // operands of the TMA / tcgen05 instructions stay in uniform registers =====
+        if (tc::elect_one()) {
+            int it = 0;
+            for (int u = worker; u < units; u += workers) {
+                const int m0 = ((u / groups) * (kCg2 ? 2 : 1) + (int)crank) * BM, g = u % groups;
+                const int tile_end = (g + 1) * group_tiles < num_tiles ? (g + 1) * group_tiles : num_tiles;
+                // the At block of this worker's NEXT unit starts its way from HBM into L2 now (short K loops
+                // only: the first tile of a unit otherwise waits for HBM behind a ring of a few K blocks)
+                if (FS_EXP(32) && u + workers < units && num_k_blocks <= PREFETCH_MAX_K_BLOCKS) {
+                    const int m0n = (((u + workers) / groups) * (kCg2 ? 2 : 1) + (int)crank) * BM;
+                    if (m0n != m0)
+                        for (int kb = 0; kb < num_k_blocks; ++kb) tc::tma_prefetch_4d(&tmap_at, kb * BK, 0, 0, m0n >> 4);
+                }
+                for (int t = g * group_tiles; t < tile_end; ++t) {
+                    const TileDesc d = tt.t[t];
+                    // pairs: this CTA's half of the tile's chunks of 16 target rows (N is a multiple of 32)
+                    const int c_half = kCg2 ? (int)crank * ((d.rows + 31) >> 5) : 0;
+                    for (int phase = 0; phase < 2; ++phase) {
+                        const CUtensorMap *tm = phase == 0 ? &tmap_mh : &tmap_mm;
+                        int kb = phase == 0 ? d.hb0 : (d.ib0 > 0 ? 0 : d.ib1);
+                        const int kend = phase == 0 ? d.hb1 : num_k_blocks;
+                        while (kb < kend) {
+                            const int s = it % kStages;
+                            const uint32_t ph = (it / kStages) & 1;
+                            ++it;
+                            tc::mbar_wait(&empty_bar[s], ph ^ 1);
+                            unsigned char *st = smem + s * kStageBytes;
+                            if (FS_EXP(16)) {      // experiment: no operand traffic at all
+                                if (crank == 0) tc::mbar_arrive(&full_bar[s]);
+                            } else if constexpr (kCg2) {
+                                // both CTAs' bytes are credited to the LEADER's barrier
+                                if (crank == 0) tc::mbar_arrive_expect_tx(&full_bar[s], 2 * kStageBytes);
+                                tc::tma_load_4d_pair(st, &tmap_at, &full_bar[s], kb * BK, 0, 0, m0 >> 4);
+                                tc::tma_load_5d_pair(st + A_BYTES, tm, &full_bar[s], kb * BK, d.row0, 0, 0, c_half);
+                            } else {
+                                tc::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                                tc::tma_load_4d(st, &tmap_at, &full_bar[s], kb * BK, 0, 0, m0 >> 4);
+                                tc::tma_load_5d(st + A_BYTES, tm, &full_bar[s], kb * BK, d.row0, 0, 0, 0);
+                            }
+                            ++kb;
+                            if (phase == 1 && kb == d.ib0) kb = d.ib1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ===== MMA issuer: one thread (pairs: of the leader CTA, for both).  Everything the tcgen05 instructions
+        // take is derived from kernel parameters (the tile table is one) and loop counters, so that it stays in
+        // uniform registers: with the table in shared memory every tcgen05.mma was wrapped in an elect / broadcast
+        // sequence of ~20 instructions and the issuing thread, not the tensor pipe, set the pace. =====
+        if (crank == 0 && tc::elect_one()) {
+            int it = 0, item = 0;
+            for (int u = worker; u < units; u += workers) {
+                const int g = u % groups;
+                const int tile_end = (g + 1) * group_tiles < num_tiles ? (g + 1) * group_tiles : num_tiles;
+                for (int t = g * group_tiles; t < tile_end; ++t) {
+                    const TileDesc d = tt.t[t];
+                    const uint32_t idesc = kCg2 ? tc::make_idesc_mxf4(2 * BM, ((d.rows + 31) >> 5) << 5)
+                                                : tc::make_idesc_mxf4(BM, ((d.rows + 15) >> 4) << 4);
+                    for (int phase = 0; phase < 2; ++phase) {
+                        const int nblk = phase == 0 ? d.hb1 - d.hb0 : d.ib0 + (num_k_blocks - d.ib1);
+                        if (nblk == 0) continue;
+                        const int buf = item & 1;
+                        const uint32_t tph = (item >> 1) & 1;
+                        ++item;
+                        tc::mbar_wait(&tempty_bar[buf], tph ^ 1);
+                        tc::tc_fence_after();
+                        const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+                        uint32_t have = 0;
+                        for (int b = 0; b < nblk; ++b) {
+                            const int s = it % kStages;
+                            const uint32_t ph = (it / kStages) & 1;
+                            ++it;
+                            tc::mbar_wait(&full_bar[s], ph);
+                            tc::tc_fence_after();
+                            const uint32_t sa = tc::smem_u32(smem + s * kStageBytes);
+                            const uint64_t da = tc::make_smem_desc_sw128(sa);
+                            const uint64_t db = tc::make_smem_desc_sw128(sa + A_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BK / 32; ++k) {
+                                if (FS_EXP(16)) break;
+                                if constexpr (kCg2)
+                                    tc::mma_mxf4_pair(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, tmem_base + SF_COL,
+                                                      tmem_base + SF_COL, have);
+                                else
+                                    tc::mma_mxf4(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, tmem_base + SF_COL,
+                                                 tmem_base + SF_COL, have);
+                                have = 1;
+                            }
+                            if constexpr (kCg2) tc::tc_commit_pair(&empty_bar[s]);
+                            else tc::tc_commit(&empty_bar[s]);
+                        }
+                        if constexpr (kCg2) tc::tc_commit_pair(&tfull_bar[buf]);
+                        else tc::tc_commit(&tfull_bar[buf]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue (warps 0 .. 11: lane quarter = warp % 4, column part = warp / 4).  The producer and the MMA
+        // issuer are the LAST two warps: the schedulers favour the highest warp id, and these two must never
+        // queue behind epilogue arithmetic. =====
+        const int q = warp & 3;
+        const int part = warp >> 2;
+        const int j = lane & 3, r8 = lane >> 2;
+        const int64_t ids0 = contiguous ? ids[0] : 0;
+        const uint32_t tquarter = tmem_base + ((uint32_t)(q * 32) << 16);
+        // hand an accumulator buffer back to the MMA issuer (this thread's TMEM loads have completed)
+        auto release_acc = [&](uint64_t *bar) {
+            tc::tc_fence_before();
+            if constexpr (kCg2) {
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive_cluster(bar, 0);
+            } else {
+                tc::mbar_arrive(bar);
+            }
+        };
+        int item = 0;
+        for (int u = worker; u < units; u += workers) {
+            const int g = u % groups;
+            const int tile_end = (g + 1) * group_tiles < num_tiles ? (g + 1) * group_tiles : num_tiles;
+            // this thread's two columns: the tile's columns (2q + h) * 8 + r8, h = 0, 1 (lane offsets 0, 16)
+            const int64_t mrow0 = (int64_t)((u / groups) * (kCg2 ? 2 : 1) + (int)crank) * BM + 2 * ((2 * q) * 8 + r8);
+            const int64_t mrow1 = mrow0 + 16;
+            const uint8_t *at0 = codesT + (int64_t)((mrow0 < K_rows ? krow[mrow0] : 0u) & 0xffffffu) * ldt;
+            const uint8_t *at1 = codesT + (int64_t)((mrow1 < K_rows ? krow[mrow1] : 0u) & 0xffffffu) * ldt;
+            // ... and the value codes of the NEXT unit's columns (the launch's targets [ids0, ids0 + R) of each row)
+            if (FS_EXP(64) && contiguous && j == 0 && part == 0 && u + workers < units) {
+                const int64_t nrow0 = mrow0 + (int64_t)(((u + workers) / groups - u / groups) * (kCg2 ? 2 : 1)) * BM;
+                const uint32_t pf_bytes = (uint32_t)(((ids0 & 15) + R + 15) & ~(int64_t)15);
+                if (nrow0 != mrow0 && nrow0 < K_rows)
+                    tc::bulk_prefetch_l2(codesT + (int64_t)(krow[nrow0] & 0xffffffu) * ldt + (ids0 & ~(int64_t)15), pf_bytes);
+                if (nrow0 != mrow0 && nrow0 + 16 < K_rows)
+                    tc::bulk_prefetch_l2(codesT + (int64_t)(krow[nrow0 + 16] & 0xffffffu) * ldt + (ids0 & ~(int64_t)15), pf_bytes);
+            }
+            unsigned long long ah0 = 0, al0 = 0, ah1 = 0, al1 = 0;   // exact fixed-point sums, one pair per column
+            for (int t = g * group_tiles; t < tile_end; ++t) {
+                const TileDesc d = tt.t[t];
+                const int nch = kCg2 ? ((d.rows + 31) >> 5) << 1 : (d.rows + 15) >> 4;   // chunks of 16 targets in this tile
+                const int n_my = nch > part ? (nch - part + M_PARTS - 1) / M_PARTS : 0;   // this part's chunks: part, part + M_PARTS, ...
+                // value codes of the thread's targets in its two columns: one word per chunk and column
+                // (issued before the accumulator wait; shared by both phases).  Targets beyond the tile's
+                // rows get whatever follows: their coefficient is 0.
+                uint32_t oh0[M_CHUNKS], oh1[M_CHUNKS];
+                if (FS_EXP(1)) {
+#pragma unroll
+                    for (int i = 0; i < M_CHUNKS; ++i) { oh0[i] = 0x00010200u; oh1[i] = 0x02000100u; }
+                } else if (contiguous) {
+                    const int64_t a0 = ids0 + d.row0 + 16 * part + 4 * j;   // chunk i: + 16 M_PARTS i
+                    if ((a0 & 3) == 0) {
+#pragma unroll
+                        for (int i = 0; i < M_CHUNKS; ++i)
+                            if (i < n_my) {
+                                oh0[i] = *reinterpret_cast<const uint32_t *>(at0 + a0 + 16 * M_PARTS * i);
+                                oh1[i] = *reinterpret_cast<const uint32_t *>(at1 + a0 + 16 * M_PARTS * i);
+                            }
+                    } else {
+                        // unaligned start (class-aligned tiles): two aligned words + funnel shift
+                        const uint32_t sh = (uint32_t)(a0 & 3) * 8u;
+                        const int64_t ab = a0 & ~(int64_t)3;
+#pragma unroll
+                        for (int i = 0; i < M_CHUNKS; ++i)
+                            if (i < n_my) {
+                                const uint32_t *s0 = reinterpret_cast<const uint32_t *>(at0 + ab + 16 * M_PARTS * i);
+                                const uint32_t *s1 = reinterpret_cast<const uint32_t *>(at1 + ab + 16 * M_PARTS * i);
+                                oh0[i] = __funnelshift_r(s0[0], s0[1], sh);
+                                oh1[i] = __funnelshift_r(s1[0], s1[1], sh);
+                            }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < M_CHUNKS; ++i)
+                        if (i < n_my) {
+                            uint32_t x0 = 0, x1 = 0;
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                const int64_t r = (int64_t)d.row0 + 16 * (part + M_PARTS * i) + 4 * j + b;
+                                const int64_t id = r < R ? ids[r] : -1;
+                                x0 |= (id >= 0 ? (uint32_t)at0[id] : 0xffu) << (8 * b);
+                                x1 |= (id >= 0 ? (uint32_t)at1[id] : 0xffu) << (8 * b);
+                            }
+                            oh0[i] = x0;
+                            oh1[i] = x1;
+                        }
+                }
+                for (int phase = 0; phase < 2; ++phase) {
+                    const int nblk = phase == 0 ? d.hb1 - d.hb0 : d.ib0 + (num_k_blocks - d.ib1);
+                    if (nblk == 0) continue;
+                    const int buf = item & 1;
+                    const uint32_t tph = (item >> 1) & 1;
+                    ++item;
+                    // per-target constants of this work item (accum_consts_kernel), target 16 chunk + 4 j + b
+                    const int2 *s_c = limbs + ((size_t)t * 2 + phase) * 256 + 16 * part + 4 * j;
+                    const float *s_rs = reinterpret_cast<const float *>(rsum) + ((size_t)t * 2 + phase) * 256 + 16 * part + 4 * j;
+                    ChunkConsts kc{}, kn{};
+                    if (FS_EXP(2)) {
+                        kc.ca = make_int4(3, 5, 7, 9); kc.cb = make_int4(11, 13, 15, 17); kc.rs = make_float4(kMagic, kMagic, kMagic, kMagic);
+                    } else if (n_my > 0) {
+                        kc.ca = __ldg(reinterpret_cast<const int4 *>(s_c));
+                        kc.cb = __ldg(reinterpret_cast<const int4 *>(s_c + 2));
+                        kc.rs = __ldg(reinterpret_cast<const float4 *>(s_rs));
+                    }
+                    kn = kc;
+                    tc::mbar_wait(&tfull_bar[buf], tph);
+                    tc::tc_fence_after();
+                    const uint32_t tacc = tquarter + (uint32_t)(buf * BN + 16 * part);   // chunk i: + 16 M_PARTS i
+                    // v[buffer][column h][group g of 8 TMEM columns][r0..r3]
+                    uint32_t v[2][2][2][4];
+                    if (FS_EXP(8)) {
+                        release_acc(&tempty_bar[buf]);
+                        continue;
+                    }
+                    if (n_my > 0) {
+                        tc::tmem_ld_16x256b(tacc, v[0][0][0]);
+                        tc::tmem_ld_16x256b(tacc + 8, v[0][0][1]);
+                        tc::tmem_ld_16x256b(tacc + (16u << 16), v[0][1][0]);
+                        tc::tmem_ld_16x256b(tacc + (16u << 16) + 8, v[0][1][1]);
+                    } else {
+                        release_acc(&tempty_bar[buf]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < M_CHUNKS; ++i) {
+                        if (i < n_my) {
+                            uint32_t (&vc)[2][2][4] = v[i & 1];
+                            tc::tmem_ld_wait_on(vc[0][0], vc[0][1], vc[1][0], vc[1][1]);
+                            if (i + 1 < n_my) {
+                                uint32_t (&vn)[2][2][4] = v[(i + 1) & 1];
+                                const uint32_t ta = tacc + 16 * M_PARTS * (i + 1);
+                                tc::tmem_ld_16x256b(ta, vn[0][0]);
+                                tc::tmem_ld_16x256b(ta + 8, vn[0][1]);
+                                tc::tmem_ld_16x256b(ta + (16u << 16), vn[1][0]);
+                                tc::tmem_ld_16x256b(ta + (16u << 16) + 8, vn[1][1]);
+                                if (!FS_EXP(2)) {
+                                kn.ca = __ldg(reinterpret_cast<const int4 *>(s_c + 16 * M_PARTS * (i + 1)));
+                                kn.cb = __ldg(reinterpret_cast<const int4 *>(s_c + 16 * M_PARTS * (i + 1) + 2));
+                                kn.rs = __ldg(reinterpret_cast<const float4 *>(s_rs + 16 * M_PARTS * (i + 1)));
+                                }
+                            } else {
+                                // the last chunk is in registers: the MMA issuer may reuse the buffer
+                                release_acc(&tempty_bar[buf]);
+                            }
+                            const int chi[4] = {kc.ca.x, kc.ca.z, kc.cb.x, kc.cb.z};
+                            const int clo[4] = {kc.ca.y, kc.ca.w, kc.cb.y, kc.cb.w};
+                            const float rsb[4] = {kc.rs.x, kc.rs.y, kc.rs.z, kc.rs.w};
+                            if (FS_EXP(4)) {
+#pragma unroll
+                                for (int b = 0; b < 4; ++b) {
+                                    ah0 += vc[0][b >> 1][b & 1] ^ vc[0][b >> 1][2 + (b & 1)] ^ (uint32_t)chi[b] ^ oh0[i];
+                                    ah1 += vc[1][b >> 1][b & 1] ^ vc[1][b >> 1][2 + (b & 1)] ^ (uint32_t)clo[b] ^ oh1[i] ^ __float_as_uint(rsb[b]);
+                                }
+                            } else
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint32_t w = h == 0 ? oh0[i] : oh1[i];
+#pragma unroll
+                                for (int b = 0; b < 4; ++b) {
+                                    // target 4 j + b of the chunk sits in TMEM column 8 (b / 2) + 2 j + b % 2
+                                    const float g0 = __uint_as_float(vc[h][b >> 1][b & 1]);
+                                    const float g1 = __uint_as_float(vc[h][b >> 1][2 + (b & 1)]);
+                                    const bool c1 = (w & (1u << (8 * b))) != 0;      // the target's code is 1
+                                    const bool c2 = (w & (2u << (8 * b))) != 0;      // ... is 2 (the implied plane)
+                                    // biased t: rs - G_code for codes 0 / 1, G_0 + G_1 (= rs - G_last) for code 2
+                                    const float t01 = __fsub_rn(rsb[b], c1 ? g1 : g0);
+                                    const float tl = __fadd_rn(__fadd_rn(g0, kMagic), g1);
+                                    const int ti = __float_as_int(c2 ? tl : t01) - kBias;
+                                    if (h == 0) {
+                                        ah0 += (unsigned long long)((long long)ti * chi[b]);
+                                        al0 += (unsigned long long)((long long)ti * clo[b]);
+                                    } else {
+                                        ah1 += (unsigned long long)((long long)ti * chi[b]);
+                                        al1 += (unsigned long long)((long long)ti * clo[b]);
+                                    }
+                                }
+                            }
+                            kc = kn;
+                        }
+                    }
+                }
+            }
+            // the four threads j of a column fold their sums; |t| <= n < 2^22 (checked by the launcher),
+            // limbs < 2^27, at most 2^9 terms per thread and unit: no overflow
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                ah0 += __shfl_xor_sync(0xffffffffu, ah0, o);
+                al0 += __shfl_xor_sync(0xffffffffu, al0, o);
+                ah1 += __shfl_xor_sync(0xffffffffu, ah1, o);
+                al1 += __shfl_xor_sync(0xffffffffu, al1, o);
+            }
+            double *out = tpartial + ((int64_t)g * M_PARTS + part) * K_rows;
+            if (j == 0) {
+                if (mrow0 < K_rows)
+                    out[mrow0] = ((double)(long long)ah0 * (double)(1 << kLimbBits) + (double)(long long)al0) * (1.0 / 4503599627370496.0);
+                if (mrow1 < K_rows)
+                    out[mrow1] = ((double)(long long)ah1 * (double)(1 << kLimbBits) + (double)(long long)al1) * (1.0 / 4503599627370496.0);
+            } else if (j == 1) {
+                if (mrow0 + 1 < K_rows) out[mrow0 + 1] = 0.0;
+                if (mrow1 + 1 < K_rows) out[mrow1 + 1] = 0.0;
+            }
+        }
+    }
+    __syncthreads();
+    if constexpr (kCg2) tc::cluster_sync_all();       // neither CTA leaves (or frees TMEM) while the pair is in flight
+    if (warp == MMA_WARP) {
+        tc::tc_fence_after();
+        if constexpr (kCg2) tc::tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+        else tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
 // Host plan: class-aligned tiles of <= 256 target rows and the K blocks their masks need.
 struct AccumPlan {
     std::vector<TileDesc> tiles;
@@ -451,7 +892,7 @@ struct AccumPlan {
 };
 
 static AccumPlan make_plan(int64_t n, int64_t R, bool contiguous, const int64_t *h_ids, const int32_t *h_y,
-                           const int64_t *h_cls_start) {
+                           const int64_t *h_cls_start, int bn, int n_round) {
     AccumPlan plan;
     const int nkb = (int)ceil_div(n, KS);
     auto add = [&](int64_t row0, int64_t rows, int64_t hs, int64_t he, bool mixed) {
@@ -468,11 +909,12 @@ static AccumPlan make_plan(int64_t n, int64_t R, bool contiguous, const int64_t 
             d.ib1 = he == n ? nkb : (int32_t)(he / KS);
             if (d.ib1 < d.ib0) d.ib1 = d.ib0;
         }
-        plan.blocks += (double)((d.hb1 - d.hb0) + d.ib0 + (nkb - d.ib1)) * (double)(((rows + 15) >> 4) << 4) / BN;
+        // MMA N: the tile's rows rounded up to n_round (16; CTA pairs 32), in units of full 240-column tiles
+        plan.blocks += (double)((d.hb1 - d.hb0) + d.ib0 + (nkb - d.ib1)) * (double)(ceil_div(rows, n_round) * n_round) / BN;
         plan.tiles.push_back(d);
     };
     if (!contiguous) {
-        for (int64_t r = 0; r < R; r += BN) add(r, std::min<int64_t>(BN, R - r), 0, n, true);
+        for (int64_t r = 0; r < R; r += bn) add(r, std::min<int64_t>(bn, R - r), 0, n, true);
         return plan;
     }
     const int64_t id0 = h_ids[0];
@@ -480,7 +922,7 @@ static AccumPlan make_plan(int64_t n, int64_t R, bool contiguous, const int64_t 
     while (r < R) {
         const int c = h_y[id0 + r];
         const int64_t cls_end = std::min<int64_t>(h_cls_start[c + 1] - id0, R);   // first row past this class
-        for (; r < cls_end; r += BN) add(r, std::min<int64_t>(BN, cls_end - r), h_cls_start[c], h_cls_start[c + 1], false);
+        for (; r < cls_end; r += bn) add(r, std::min<int64_t>(bn, cls_end - r), h_cls_start[c], h_cls_start[c + 1], false);
         r = cls_end;
     }
     return plan;
@@ -488,20 +930,35 @@ static AccumPlan make_plan(int64_t n, int64_t R, bool contiguous, const int64_t 
 
 // Returns the number of partial vectors written ([groups x PARTS][K_rows] doubles).
 int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, const CUtensorMap &tmap_mm, int64_t n,
-                    int64_t R, const int64_t *d_ids, bool contiguous, bool paired, const RowInfo *rinfo, const uint8_t *codesT,
+                    int64_t R, const int64_t *d_ids, bool contiguous, int pair_mode, const RowInfo *rinfo, const uint8_t *codesT,
                     int64_t ldt, const uint32_t *krow, int64_t K_rows, DevBuf<double> &tpartial, int32_t *d_tiles,
                     DevBuf<int32_t> &consts, cudaStream_t st, int *launches, const int64_t *h_ids, const int32_t *h_y,
                     const int64_t *h_cls_start, double *ops) {
-    // paired epilogue: every column owns exactly two one-hot rows (2c, 2c + 1), see the kernel
-    const char *env_pair = getenv("FS_B200_ACCUM_PAIR");
-    if (env_pair && env_pair[0] == '0') paired = false;
-    auto kernel = paired ? tc_accum_kernel<true> : tc_accum_kernel<false>;
-    FS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    // pair_mode 1 / 2 / 3: every column owns exactly two one-hot rows (2c, 2c + 1): paired epilogue (planes meet by
+    // shuffle), merged-plane epilogue (planes meet in one thread; the caller built the permuted tensor maps), and
+    // the merged-plane kernel as clusters of two CTAs (cta_group::2; tiles of <= 224 rows)
+    const bool cg2 = pair_mode == 3;
+#ifdef FS_ACCUM_EXPERIMENTS
+    int exp = 0;
+    if (const char *e = getenv("FS_B200_ACCUM_EXP")) exp = atoi(e);
+#define FS_PICK(c) (exp == 8 ? tc_accum_merged_kernel<c, 8> : exp == 16 ? tc_accum_merged_kernel<c, 16> : exp == 17 ? tc_accum_merged_kernel<c, 17> : \
+                    exp == 18 ? tc_accum_merged_kernel<c, 18> : exp == 20 ? tc_accum_merged_kernel<c, 20> : exp == 23 ? tc_accum_merged_kernel<c, 23> : \
+                    exp == 24 ? tc_accum_merged_kernel<c, 24> : exp == 32 ? tc_accum_merged_kernel<c, 32> : exp == 64 ? tc_accum_merged_kernel<c, 64> : \
+                    tc_accum_merged_kernel<c, 0>)
+    auto merged = cg2 ? FS_PICK(true) : FS_PICK(false);
+#undef FS_PICK
+#else
+    auto merged = cg2 ? tc_accum_merged_kernel<true> : tc_accum_merged_kernel<false>;
+#endif
+    auto kernel = pair_mode == 1 ? tc_accum_kernel<true> : tc_accum_kernel<false>;
+    const int smem_bytes = pair_mode >= 2 ? (cg2 ? CG2_SMEM_BYTES : MERGED_SMEM_BYTES) : SMEM_BYTES;
+    if (pair_mode >= 2) FS_CUDA(cudaFuncSetAttribute(merged, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    else FS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     int dev = 0, sms = 0;
     FS_CUDA(cudaGetDevice(&dev));
     FS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     FS_REQUIRE(n < (1LL << 22), FS_ERR_INVALID, "one-hot accumulation supports up to 2^22 samples (got %lld)", (long long)n);
-    const AccumPlan plan = make_plan(n, R, contiguous, h_ids, h_y, h_cls_start);
+    const AccumPlan plan = make_plan(n, R, contiguous, h_ids, h_y, h_cls_start, cg2 ? CG2_BN : BN, cg2 ? 32 : 16);
     const int m_blocks = (int)ceil_div(K_rows, BM);
     // Tile groups.  Work units (128 one-hot rows x one group) are dealt round-robin, so the ~sms
     // units resident at one time span sms / groups one-hot row blocks, each streaming its own
@@ -513,14 +970,16 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
         const int64_t g = std::max<int64_t>(ceil_div(nt, GROUP), std::min<int64_t>(nt, want));
         return (int)g;
     };
+    const size_t max_tiles = pair_mode >= 2 ? MERGED_MAX_TILES : MAX_TILES;
     int total_groups = 0;
-    for (size_t t0 = 0; t0 < plan.tiles.size(); t0 += MAX_TILES)
-        total_groups += groups_for((int)std::min<size_t>(MAX_TILES, plan.tiles.size() - t0));
-    tpartial.reserve((size_t)total_groups * PARTS * K_rows);
+    for (size_t t0 = 0; t0 < plan.tiles.size(); t0 += max_tiles)
+        total_groups += groups_for((int)std::min<size_t>(max_tiles, plan.tiles.size() - t0));
+    const int parts = pair_mode >= 2 ? M_PARTS : PARTS;
+    tpartial.reserve((size_t)total_groups * parts * K_rows);
     int groups_done = 0;
     // at most MAX_TILES tile descriptors per launch
-    for (size_t t0 = 0; t0 < plan.tiles.size(); t0 += MAX_TILES) {
-        const int nt = (int)std::min<size_t>(MAX_TILES, plan.tiles.size() - t0);
+    for (size_t t0 = 0; t0 < plan.tiles.size(); t0 += max_tiles) {
+        const int nt = (int)std::min<size_t>(max_tiles, plan.tiles.size() - t0);
         // equal-sized groups (work units are dealt round-robin: unequal units would unbalance the SMs)
         const int group_tiles = (int)ceil_div(nt, groups_for(nt));
         const int groups = (int)ceil_div(nt, group_tiles);
@@ -530,20 +989,45 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
         consts.reserve((size_t)nt * 2 * 256 * 3 + 512);   // slack: the epilogue prefetches one item ahead
         int2 *limbs = reinterpret_cast<int2 *>(consts.ptr);
         int32_t *rsum = consts.ptr + (size_t)nt * 2 * 256 * 2;
-        accum_consts_kernel<<<2 * nt, 256, 0, st>>>(reinterpret_cast<const TileDesc *>(d_tiles), nt, rinfo, limbs, rsum, paired ? 1 : 0);
+        accum_consts_kernel<<<2 * nt, 256, 0, st>>>(reinterpret_cast<const TileDesc *>(d_tiles), nt, rinfo, limbs, rsum, pair_mode >= 2 ? 2 : pair_mode);
         ++*launches;
-        const int units = m_blocks * groups;
-        const int grid = units < sms ? units : sms;
-        kernel<<<grid, THREADS, SMEM_BYTES, st>>>(
-            tmap_at, tmap_mh, tmap_mm, (int)ceil_div(n, KS), R, reinterpret_cast<const TileDesc *>(d_tiles), nt,
-            groups, group_tiles, m_blocks, d_ids, contiguous ? 1 : 0, limbs, rsum, codesT, ldt, krow, K_rows,
-            tpartial.ptr + (size_t)groups_done * PARTS * K_rows);
+        if (pair_mode >= 2) {
+            // single CTAs, or clusters of two CTAs: a cluster takes two adjacent blocks of one-hot rows through a
+            // group of tiles.  The tile table is a kernel parameter.
+            TileTable table;
+            memcpy(table.t, plan.tiles.data() + t0, (size_t)nt * sizeof(TileDesc));
+            const int units = (cg2 ? (m_blocks + 1) / 2 : m_blocks) * groups;
+            const int workers = cg2 ? sms / 2 : sms;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)((cg2 ? 2 : 1) * (units < workers ? units : workers)));
+            cfg.blockDim = dim3(M_THREADS);
+            cfg.dynamicSmemBytes = (size_t)smem_bytes;
+            cfg.stream = st;
+            cudaLaunchAttribute attr{};
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = cg2 ? 2 : 1;
+            attr.val.clusterDim.y = 1;
+            attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr;
+            cfg.numAttrs = 1;
+            FS_CUDA(cudaLaunchKernelEx(&cfg, merged, tmap_at, tmap_mh, tmap_mm, (int)ceil_div(n, KS), R, table, nt, groups,
+                                       group_tiles, m_blocks, d_ids, contiguous ? 1 : 0, (const int2 *)limbs,
+                                       (const int32_t *)rsum, codesT, ldt, krow, K_rows,
+                                       tpartial.ptr + (size_t)groups_done * parts * K_rows));
+        } else {
+            const int units = m_blocks * groups;
+            const int grid = units < sms ? units : sms;
+            kernel<<<grid, THREADS, smem_bytes, st>>>(
+                tmap_at, tmap_mh, tmap_mm, (int)ceil_div(n, KS), R, reinterpret_cast<const TileDesc *>(d_tiles), nt,
+                groups, group_tiles, m_blocks, d_ids, contiguous ? 1 : 0, limbs, rsum, codesT, ldt, krow, K_rows,
+                tpartial.ptr + (size_t)groups_done * PARTS * K_rows);
+        }
         FS_CUDA(cudaGetLastError());
         ++*launches;
         groups_done += groups;
     }
-    if (ops) *ops += 2.0 * BM * BN * KS * plan.blocks * (double)m_blocks;
-    return PARTS * groups_done;
+    if (ops) *ops += 2.0 * BM * BN * KS * plan.blocks * (double)(cg2 ? (m_blocks + 1) / 2 * 2 : m_blocks);
+    return parts * groups_done;
 }
 
 int tc_accum_tile_desc_ints() { return MAX_TILES * (int)(sizeof(TileDesc) / sizeof(int32_t)); }

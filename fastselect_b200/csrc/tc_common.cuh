@@ -50,6 +50,34 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
+// 4-D / 5-D tile loads: the outer box dimensions enumerate ROWS of the operand in a permuted order (the
+// accumulation kernel's merged-plane epilogue); c0 = coordinate along the contiguous (byte) dimension
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int32_t c0, int32_t c1,
+                                            int32_t c2, int32_t c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int32_t c0, int32_t c1,
+                                            int32_t c2, int32_t c3, int32_t c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+// L2 prefetches: a 4-D tile of a tensor map, and a run of bytes (16-byte aligned, size a multiple of 16)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *m, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void *gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(gptr)), "r"(bytes) : "memory");
+}
+
 // 1-D bulk copy global -> shared (size a multiple of 16 bytes), completion on a local mbarrier
 __device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
@@ -111,6 +139,24 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
+}
+// 16 lanes x 256 bits (8 columns) of this warp's lane quarter, starting at the lane in the address
+// (offset 0 or 16): thread t receives (lane t/4, columns 2(t%4), 2(t%4)+1) in r0, r1 and
+// (lane t/4 + 8, the same columns) in r2, r3 -- measured, profiles/r02_tmem_frag_probe.txt
+__device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+// tcgen05.wait::ld that names the registers it makes valid, so that the compiler cannot move their
+// first use above the wait
+__device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&a)[4], uint32_t (&b)[4], uint32_t (&c)[4], uint32_t (&d)[4]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(c[0]),
+                   "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 :
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // one 32-bit column of this warp's 32 lanes
@@ -191,6 +237,23 @@ __device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorM
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1)
         : "memory");
 }
+// the permuted 4-D / 5-D tile loads of the accumulation kernel, by either CTA of the pair
+__device__ __forceinline__ void tma_load_4d_pair(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int32_t c0, int32_t c1,
+                                                 int32_t c2, int32_t c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int32_t c0, int32_t c1,
+                                                 int32_t c2, int32_t c3, int32_t c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(kCols)
@@ -226,6 +289,78 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta)
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
+// The four K = 64 steps of one 128-byte K block (descriptor start address + 2 per step) and commits, executed by a
+// CONVERGED warp: elect.sync picks the issuing lane inside the statement, so the operands stay warp-uniform.
+template <bool kPair>
+__device__ __forceinline__ void mma_mxf4_x4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t tmem_sf,
+                                            uint32_t accumulate) {
+    if constexpr (kPair) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p, e;\n\t"
+            ".reg .b64 a, b;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "@e tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%5], p;\n\t"
+            "setp.eq.b32 p, 0, 0;\n\t"
+            "add.s64 a, %1, 2;\n\t"
+            "add.s64 b, %2, 2;\n\t"
+            "@e tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], a, b, %3, [%5], [%5], p;\n\t"
+            "add.s64 a, %1, 4;\n\t"
+            "add.s64 b, %2, 4;\n\t"
+            "@e tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], a, b, %3, [%5], [%5], p;\n\t"
+            "add.s64 a, %1, 6;\n\t"
+            "add.s64 b, %2, 6;\n\t"
+            "@e tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], a, b, %3, [%5], [%5], p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sf)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p, e;\n\t"
+            ".reg .b64 a, b;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%5], p;\n\t"
+            "setp.eq.b32 p, 0, 0;\n\t"
+            "add.s64 a, %1, 2;\n\t"
+            "add.s64 b, %2, 2;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], a, b, %3, [%5], [%5], p;\n\t"
+            "add.s64 a, %1, 4;\n\t"
+            "add.s64 b, %2, 4;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], a, b, %3, [%5], [%5], p;\n\t"
+            "add.s64 a, %1, 6;\n\t"
+            "add.s64 b, %2, 6;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], a, b, %3, [%5], [%5], p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sf)
+            : "memory");
+    }
+}
+// tcgen05.commit by one elected lane of a converged warp (pairs: multicast to both CTAs' barriers)
+template <bool kPair>
+__device__ __forceinline__ void tc_commit_elected(uint64_t *bar) {
+    if constexpr (kPair) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred e;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+            "}\n" ::"r"(smem_u32(bar)),
+            "h"((uint16_t)3)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred e;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+            "}\n" ::"r"(smem_u32(bar))
+            : "memory");
+    }
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(
@@ -243,5 +378,9 @@ __device__ __forceinline__ bool elect_one() {
 // Host: 2-D uint8 tensor map, box = 128 bytes x box_rows, 128-byte swizzle.
 CUtensorMap make_tmap_u8_sw128(const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch_bytes,
                                uint32_t box_rows);
+// Host: rank-`rank` (3..5) uint8 tensor map, 128-byte swizzle; dims[0] / box[0] along the contiguous bytes,
+// strides[i] = byte stride of dimension i + 1.  Returns false (map untouched) when the driver refuses it.
+bool make_tmap_u8_sw128_nd(CUtensorMap *out, const void *base, int rank, const uint64_t *dims, const uint64_t *strides,
+                           const uint32_t *box);
 
 }  // namespace fs
