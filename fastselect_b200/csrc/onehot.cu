@@ -963,9 +963,10 @@ void launch_accum_tensor(fs_dataset *ds, const WorkSet &ws, int algo, const int6
     // FS_B200_ACCUM_PAIR = 1: paired epilogue (planes meet by shuffle), 0: one thread per one-hot row.
     // 3 (default): the merged-plane kernel as clusters of two CTAs (cta_group::2): tiles of <= 224 rows, every CTA
     // stages half of a tile's chunks (box of 7)
-    int pair_mode = ws.all_v3 ? 3 : 0;
+    // (the merged kernel's per-column 64-bit sums need n^2 * 2^27 < 2^63)
+    int pair_mode = ws.all_v3 ? (n < (1 << 17) ? 3 : 1) : 0;
     if (const char *e = getenv("FS_B200_ACCUM_PAIR"))
-        if (ws.all_v3 && e[0] >= '0' && e[0] <= '3') pair_mode = e[0] - '0';
+        if (ws.all_v3 && e[0] >= '0' && e[0] <= (n < (1 << 17) ? '3' : '1')) pair_mode = e[0] - '0';
     if (pair_mode >= 2) {
         const uint64_t pa_b = (uint64_t)(ws.ldt / 2), pm_b = (uint64_t)(ldn / 2);
         const uint64_t da[4] = {row_bytes, 8, 2, (uint64_t)(ws.Ka / 16)}, sa[3] = {2 * pa_b, pa_b, 16 * pa_b};

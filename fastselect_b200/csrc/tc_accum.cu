@@ -74,7 +74,6 @@ constexpr int SF_COL = 2 * BN;            // 8 columns of UE8M0 1.0 (0x7f) for b
 constexpr int CG2_BN = 224;
 constexpr int CG2_B_BYTES = (CG2_BN / 2) * BK;   // 14 KB
 constexpr int CG2_STAGES = 6;
-constexpr int PREFETCH_MAX_K_BLOCKS = 32;   // L2 prefetch of the next unit's At block: up to 8192 samples
 constexpr int CG2_SMEM_BYTES = CG2_STAGES * (A_BYTES + CG2_B_BYTES) + 1024 + BAR_BYTES;
 constexpr int MERGED_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
 static_assert(CG2_B_BYTES % 1024 == 0 && CG2_SMEM_BYTES <= 232448, "pair stage shape");
@@ -198,7 +197,7 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (tc::elect_one()) {   // one thread, and the compiler knows it: uniform-register issue code
             int it = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 const int m0 = (u / groups) * BM, g = u % groups;
@@ -228,7 +227,7 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (tc::elect_one()) {   // one thread, and the compiler knows it: uniform-register issue code
             int it = 0, item = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 const int g = u % groups;
@@ -514,7 +513,7 @@ template <bool kCg2>
 __global__ void __launch_bounds__(M_THREADS, 1)
 tc_accum_merged_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_constant__ CUtensorMap tmap_mh,
                        const __grid_constant__ CUtensorMap tmap_mm, int num_k_blocks, int64_t R,
-                       const __grid_constant__ TileTable tt, int num_tiles, int groups, int group_tiles, int m_blocks,
+                       const __grid_constant__ TileTable tt, int num_tiles, int groups, int group_tiles, int m_blocks, int group_major,
                        const int64_t *__restrict__ ids, int contiguous, const int2 *__restrict__ limbs,
                        const int32_t *__restrict__ rsum, const uint8_t *__restrict__ codesT, int64_t ldt,
                        const uint32_t *__restrict__ krow, int64_t K_rows, double *__restrict__ tpartial) {
@@ -534,7 +533,11 @@ tc_accum_merged_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid
     const uint32_t crank = kCg2 ? tc::cluster_ctarank() : 0u;
     const int worker = kCg2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int workers = kCg2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    const int units = (kCg2 ? (m_blocks + 1) / 2 : m_blocks) * groups;
+    // work units: (block of one-hot rows, group of tiles).  Blocks-major order lets the groups of a block share its
+    // At rows in L2; group-major order (large n: the masks no longer fit L2) lets all workers share one group's
+    // mask tiles and streams At once per group
+    const int m_units = kCg2 ? (m_blocks + 1) / 2 : m_blocks;
+    const int units = m_units * groups;
 
     if (warp == PRODUCER_WARP && lane == 0) {
         tc::prefetch_tmap(&tmap_at);
@@ -579,15 +582,9 @@ tc_accum_merged_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid
         if (tc::elect_one()) {
             int it = 0;
             for (int u = worker; u < units; u += workers) {
-                const int m0 = ((u / groups) * (kCg2 ? 2 : 1) + (int)crank) * BM, g = u % groups;
+                const int ub = group_major ? u % m_units : u / groups, g = group_major ? u / m_units : u % groups;
+                const int m0 = (ub * (kCg2 ? 2 : 1) + (int)crank) * BM;
                 const int tile_end = (g + 1) * group_tiles < num_tiles ? (g + 1) * group_tiles : num_tiles;
-                // the At block of this worker's NEXT unit starts its way from HBM into L2 now (short K loops
-                // only: the first tile of a unit otherwise waits for HBM behind a ring of a few K blocks)
-                if (FS_EXP(32) && u + workers < units && num_k_blocks <= PREFETCH_MAX_K_BLOCKS) {
-                    const int m0n = (((u + workers) / groups) * (kCg2 ? 2 : 1) + (int)crank) * BM;
-                    if (m0n != m0)
-                        for (int kb = 0; kb < num_k_blocks; ++kb) tc::tma_prefetch_4d(&tmap_at, kb * BK, 0, 0, m0n >> 4);
-                }
                 for (int t = g * group_tiles; t < tile_end; ++t) {
                     const TileDesc d = tt.t[t];
                     // pairs: this CTA's half of the tile's chunks of 16 target rows (N is a multiple of 32)
@@ -629,7 +626,7 @@ tc_accum_merged_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid
         if (crank == 0 && tc::elect_one()) {
             int it = 0, item = 0;
             for (int u = worker; u < units; u += workers) {
-                const int g = u % groups;
+                const int g = group_major ? u / m_units : u % groups;
                 const int tile_end = (g + 1) * group_tiles < num_tiles ? (g + 1) * group_tiles : num_tiles;
                 for (int t = g * group_tiles; t < tile_end; ++t) {
                     const TileDesc d = tt.t[t];
@@ -688,29 +685,20 @@ tc_accum_merged_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid
             tc::tc_fence_before();
             if constexpr (kCg2) {
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive_cluster(bar, 0);
+                if (lane == 0) tc::mbar_arrive_cluster_relaxed(bar, 0);   // no memory fence: TMEM reads are ordered by tcgen05.fence
             } else {
                 tc::mbar_arrive(bar);
             }
         };
         int item = 0;
         for (int u = worker; u < units; u += workers) {
-            const int g = u % groups;
+            const int ub = group_major ? u % m_units : u / groups, g = group_major ? u / m_units : u % groups;
             const int tile_end = (g + 1) * group_tiles < num_tiles ? (g + 1) * group_tiles : num_tiles;
             // this thread's two columns: the tile's columns (2q + h) * 8 + r8, h = 0, 1 (lane offsets 0, 16)
-            const int64_t mrow0 = (int64_t)((u / groups) * (kCg2 ? 2 : 1) + (int)crank) * BM + 2 * ((2 * q) * 8 + r8);
+            const int64_t mrow0 = (int64_t)(ub * (kCg2 ? 2 : 1) + (int)crank) * BM + 2 * ((2 * q) * 8 + r8);
             const int64_t mrow1 = mrow0 + 16;
             const uint8_t *at0 = codesT + (int64_t)((mrow0 < K_rows ? krow[mrow0] : 0u) & 0xffffffu) * ldt;
             const uint8_t *at1 = codesT + (int64_t)((mrow1 < K_rows ? krow[mrow1] : 0u) & 0xffffffu) * ldt;
-            // ... and the value codes of the NEXT unit's columns (the launch's targets [ids0, ids0 + R) of each row)
-            if (FS_EXP(64) && contiguous && j == 0 && part == 0 && u + workers < units) {
-                const int64_t nrow0 = mrow0 + (int64_t)(((u + workers) / groups - u / groups) * (kCg2 ? 2 : 1)) * BM;
-                const uint32_t pf_bytes = (uint32_t)(((ids0 & 15) + R + 15) & ~(int64_t)15);
-                if (nrow0 != mrow0 && nrow0 < K_rows)
-                    tc::bulk_prefetch_l2(codesT + (int64_t)(krow[nrow0] & 0xffffffu) * ldt + (ids0 & ~(int64_t)15), pf_bytes);
-                if (nrow0 != mrow0 && nrow0 + 16 < K_rows)
-                    tc::bulk_prefetch_l2(codesT + (int64_t)(krow[nrow0 + 16] & 0xffffffu) * ldt + (ids0 & ~(int64_t)15), pf_bytes);
-            }
             unsigned long long ah0 = 0, al0 = 0, ah1 = 0, al1 = 0;   // exact fixed-point sums, one pair per column
             for (int t = g * group_tiles; t < tile_end; ++t) {
                 const TileDesc d = tt.t[t];
@@ -864,15 +852,19 @@ tc_accum_merged_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid
                 ah1 += __shfl_xor_sync(0xffffffffu, ah1, o);
                 al1 += __shfl_xor_sync(0xffffffffu, al1, o);
             }
-            double *out = tpartial + ((int64_t)g * M_PARTS + part) * K_rows;
+            // exact integers, so the order of the additions does not matter: one pair of 64-bit sums per column for the
+            // whole launch (slot of one-hot row 2c: high limbs, of row 2c + 1: low limbs), added with fire-and-forget
+            // atomics; merged_finish_kernel turns them into doubles.  No float64 instruction in this kernel.
             if (j == 0) {
-                if (mrow0 < K_rows)
-                    out[mrow0] = ((double)(long long)ah0 * (double)(1 << kLimbBits) + (double)(long long)al0) * (1.0 / 4503599627370496.0);
-                if (mrow1 < K_rows)
-                    out[mrow1] = ((double)(long long)ah1 * (double)(1 << kLimbBits) + (double)(long long)al1) * (1.0 / 4503599627370496.0);
-            } else if (j == 1) {
-                if (mrow0 + 1 < K_rows) out[mrow0 + 1] = 0.0;
-                if (mrow1 + 1 < K_rows) out[mrow1 + 1] = 0.0;
+                unsigned long long *out = reinterpret_cast<unsigned long long *>(tpartial);
+                if (mrow0 < K_rows) {
+                    atomicAdd(out + mrow0, ah0);
+                    atomicAdd(out + mrow0 + 1, al0);
+                }
+                if (mrow1 < K_rows) {
+                    atomicAdd(out + mrow1, ah1);
+                    atomicAdd(out + mrow1 + 1, al1);
+                }
             }
         }
     }
@@ -883,6 +875,17 @@ tc_accum_merged_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid
         if constexpr (kCg2) tc::tmem_dealloc_pair<TMEM_COLS>(tmem_base);
         else tc::tmem_dealloc<TMEM_COLS>(tmem_base);
     }
+}
+
+// (sum of high limbs, sum of low limbs) of every column -> its weight as a double in the slot of one-hot row 2c, 0 in
+// the slot of row 2c + 1: the layout reduce_tensor_partials_kernel expects (one partial vector)
+__global__ void __launch_bounds__(256) merged_finish_kernel(double *__restrict__ tpartial, int64_t K_rows) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (2 * c + 1 >= K_rows) return;
+    const long long hi = reinterpret_cast<const long long *>(tpartial)[2 * c];
+    const long long lo = reinterpret_cast<const long long *>(tpartial)[2 * c + 1];
+    tpartial[2 * c] = ((double)hi * (double)(1 << kLimbBits) + (double)lo) * (1.0 / 4503599627370496.0);
+    tpartial[2 * c + 1] = 0.0;
 }
 
 // Host plan: class-aligned tiles of <= 256 target rows and the K blocks their masks need.
@@ -971,11 +974,17 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
         return (int)g;
     };
     const size_t max_tiles = pair_mode >= 2 ? MERGED_MAX_TILES : MAX_TILES;
+    // both masks of the launch's R rows (n / 2 bytes per row each): once they outgrow about half of L2 the units
+    // are walked group by group (merged kernel), see the kernel
+    int group_major = (double)R * (double)n > 48.0 * 1048576.0 ? 1 : 0;
+    if (const char *e = getenv("FS_B200_ACCUM_ORDER")) group_major = e[0] == '1' ? 1 : 0;
     int total_groups = 0;
     for (size_t t0 = 0; t0 < plan.tiles.size(); t0 += max_tiles)
         total_groups += groups_for((int)std::min<size_t>(max_tiles, plan.tiles.size() - t0));
-    const int parts = pair_mode >= 2 ? M_PARTS : PARTS;
-    tpartial.reserve((size_t)total_groups * parts * K_rows);
+    // merged kernel: one pair of exact 64-bit sums per column for the whole call (zeroed here, finished below)
+    const int parts = pair_mode >= 2 ? 0 : PARTS;
+    tpartial.reserve(pair_mode >= 2 ? (size_t)K_rows + 2 : (size_t)total_groups * parts * K_rows);
+    if (pair_mode >= 2) FS_CUDA(cudaMemsetAsync(tpartial.ptr, 0, (size_t)K_rows * sizeof(double), st));
     int groups_done = 0;
     // at most MAX_TILES tile descriptors per launch
     for (size_t t0 = 0; t0 < plan.tiles.size(); t0 += max_tiles) {
@@ -1011,7 +1020,7 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
             cfg.attrs = &attr;
             cfg.numAttrs = 1;
             FS_CUDA(cudaLaunchKernelEx(&cfg, merged, tmap_at, tmap_mh, tmap_mm, (int)ceil_div(n, KS), R, table, nt, groups,
-                                       group_tiles, m_blocks, d_ids, contiguous ? 1 : 0, (const int2 *)limbs,
+                                       group_tiles, m_blocks, group_major, d_ids, contiguous ? 1 : 0, (const int2 *)limbs,
                                        (const int32_t *)rsum, codesT, ldt, krow, K_rows,
                                        tpartial.ptr + (size_t)groups_done * parts * K_rows));
         } else {
@@ -1027,6 +1036,12 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
         groups_done += groups;
     }
     if (ops) *ops += 2.0 * BM * BN * KS * plan.blocks * (double)(cg2 ? (m_blocks + 1) / 2 * 2 : m_blocks);
+    if (pair_mode >= 2) {
+        merged_finish_kernel<<<(unsigned)ceil_div(K_rows / 2 + 1, 256), 256, 0, st>>>(tpartial.ptr, K_rows);
+        FS_CUDA(cudaGetLastError());
+        ++*launches;
+        return 1;
+    }
     return parts * groups_done;
 }
 

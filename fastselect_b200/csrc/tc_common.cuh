@@ -288,6 +288,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t cta)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// the same without the cluster-scope release (which compiles to MEMBAR.ALL.GPU): for hand-offs whose payload is
+// ordered by tcgen05.fence (TMEM reads completed), not by generic-proxy memory ordering
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t *bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 
 // The four K = 64 steps of one 128-byte K block (descriptor start address + 2 per step) and commits, executed by a
 // CONVERGED warp: elect.sync picks the issuing lane inside the statement, so the operands stay warp-uniform.

@@ -210,7 +210,7 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (tc::elect_one()) {   // one thread, and the compiler knows it: uniform-register issue code
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
@@ -222,7 +222,7 @@ tc_dist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        if (tc::elect_one()) {   // one thread, and the compiler knows it: uniform-register issue code
             constexpr uint32_t idesc = tc::make_idesc_mxf4(BM, BN);
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 const int s = kb % STAGES;
@@ -338,7 +338,7 @@ tc_dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     if (warp == 0) {
         // ===== TMA producer (one per CTA: own A rows, own half of the B rows) =====
-        if (lane == 0) {
+        if (tc::elect_one()) {   // one thread, and the compiler knows it: uniform-register issue code
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 const int s = kb % P_STAGES;
                 const uint32_t ph = (kb / P_STAGES) & 1;
@@ -350,7 +350,7 @@ tc_dist_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one thread of the leader CTA, for the pair =====
-        if (lane == 0 && crank == 0) {
+        if (crank == 0 && tc::elect_one()) {
             constexpr uint32_t idesc = tc::make_idesc_mxf4(2 * BM, BN);
             for (int kb = 0; kb < num_k_blocks; ++kb) {
                 const int s = kb % P_STAGES;
