@@ -73,7 +73,10 @@ constexpr int SF_COL = 2 * BN;            // 8 columns of UE8M0 1.0 (0x7f) for b
 // CTA pairs (merged-plane kernel): tiles of <= 224 target rows, each CTA stages half of them (7 chunks of 16)
 constexpr int CG2_BN = 224;
 constexpr int CG2_B_BYTES = (CG2_BN / 2) * BK;   // 14 KB
-constexpr int CG2_STAGES = 6;
+#ifndef FS_CG2_STAGES
+#define FS_CG2_STAGES 6
+#endif
+constexpr int CG2_STAGES = FS_CG2_STAGES;
 constexpr int CG2_SMEM_BYTES = CG2_STAGES * (A_BYTES + CG2_B_BYTES) + 1024 + BAR_BYTES;
 constexpr int MERGED_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + BAR_BYTES;
 static_assert(CG2_B_BYTES % 1024 == 0 && CG2_SMEM_BYTES <= 232448, "pair stage shape");
@@ -513,7 +516,7 @@ template <bool kCg2>
 __global__ void __launch_bounds__(M_THREADS, 1)
 tc_accum_merged_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_constant__ CUtensorMap tmap_mh,
                        const __grid_constant__ CUtensorMap tmap_mm, int num_k_blocks, int64_t R,
-                       const __grid_constant__ TileTable tt, int num_tiles, int groups, int group_tiles, int m_blocks, int group_major,
+                       const __grid_constant__ TileTable tt, int num_tiles, int groups, int group_tiles, int m_blocks, int group_span,
                        const int64_t *__restrict__ ids, int contiguous, const int2 *__restrict__ limbs,
                        const int32_t *__restrict__ rsum, const uint8_t *__restrict__ codesT, int64_t ldt,
                        const uint32_t *__restrict__ krow, int64_t K_rows, double *__restrict__ tpartial) {
@@ -533,11 +536,19 @@ tc_accum_merged_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid
     const uint32_t crank = kCg2 ? tc::cluster_ctarank() : 0u;
     const int worker = kCg2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int workers = kCg2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    // work units: (block of one-hot rows, group of tiles).  Blocks-major order lets the groups of a block share its
-    // At rows in L2; group-major order (large n: the masks no longer fit L2) lets all workers share one group's
-    // mask tiles and streams At once per group
+    // work units: (block of one-hot rows, group of tiles), walked in bands of `group_span` groups: inside a band the
+    // blocks advance slowest-varying-last (unit = band, block, group within band), so that the workers running at one
+    // time cover group_span groups x (workers / group_span) blocks -- their mask tiles AND their At rows stay in L2
+    // (group_span = groups: all groups of a block together; 1: one group for all workers)
     const int m_units = kCg2 ? (m_blocks + 1) / 2 : m_blocks;
     const int units = m_units * groups;
+    const int band_units = m_units * group_span;
+    auto unit_block = [&](int u, int &g) {
+        const int band = u / band_units, rem = u - band * band_units;
+        const int span = groups - band * group_span < group_span ? groups - band * group_span : group_span;
+        g = band * group_span + rem % span;
+        return rem / span;
+    };
 
     if (warp == PRODUCER_WARP && lane == 0) {
         tc::prefetch_tmap(&tmap_at);
@@ -582,7 +593,8 @@ tc_accum_merged_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid
         if (tc::elect_one()) {
             int it = 0;
             for (int u = worker; u < units; u += workers) {
-                const int ub = group_major ? u % m_units : u / groups, g = group_major ? u / m_units : u % groups;
+                int g;
+                const int ub = unit_block(u, g);
                 const int m0 = (ub * (kCg2 ? 2 : 1) + (int)crank) * BM;
                 const int tile_end = (g + 1) * group_tiles < num_tiles ? (g + 1) * group_tiles : num_tiles;
                 for (int t = g * group_tiles; t < tile_end; ++t) {
@@ -626,7 +638,8 @@ tc_accum_merged_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid
         if (crank == 0 && tc::elect_one()) {
             int it = 0, item = 0;
             for (int u = worker; u < units; u += workers) {
-                const int g = group_major ? u / m_units : u % groups;
+                int g;
+                (void)unit_block(u, g);
                 const int tile_end = (g + 1) * group_tiles < num_tiles ? (g + 1) * group_tiles : num_tiles;
                 for (int t = g * group_tiles; t < tile_end; ++t) {
                     const TileDesc d = tt.t[t];
@@ -692,7 +705,8 @@ tc_accum_merged_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid
         };
         int item = 0;
         for (int u = worker; u < units; u += workers) {
-            const int ub = group_major ? u % m_units : u / groups, g = group_major ? u / m_units : u % groups;
+            int g;
+            const int ub = unit_block(u, g);
             const int tile_end = (g + 1) * group_tiles < num_tiles ? (g + 1) * group_tiles : num_tiles;
             // this thread's two columns: the tile's columns (2q + h) * 8 + r8, h = 0, 1 (lane offsets 0, 16)
             const int64_t mrow0 = (int64_t)(ub * (kCg2 ? 2 : 1) + (int)crank) * BM + 2 * ((2 * q) * 8 + r8);
@@ -968,16 +982,24 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
     // 128 x n bytes of At again for every tile of the group: keep that footprint within about half
     // of L2 (else every re-read goes to HBM and the kernel turns DRAM-bound for large n) by
     // cutting the tiles into more, smaller groups of equal size.
+    // merged kernel: band of groups walked together (see the kernel); 0 = all groups of a block together
+    // Large n (the two masks, n^2 bytes, no longer fit L2): groups of two tiles walked in bands of twelve keep the
+    // mask tiles and the At rows of the ~74 running clusters inside L2 -- measured on a C5 cut (20 000 x 100 000):
+    // 226 -> 204 ms of accumulation per TuRF run (profiles/r02_accum_l2_blocking_c5cut.txt)
+    int group_span = 0, group_tiles_env = 0;
+    if (pair_mode >= 2 && n > 8192) {
+        group_span = 12;
+        group_tiles_env = 2;
+    }
+    if (const char *e = getenv("FS_B200_ACCUM_SPAN")) group_span = atoi(e);
+    if (const char *e = getenv("FS_B200_ACCUM_GROUP_TILES")) group_tiles_env = atoi(e);
     auto groups_for = [&](int nt) {
         const int64_t want = ceil_div((int64_t)sms * BM * (n / 2), (int64_t)60 << 20);   // At rows are n / 2 bytes
         const int64_t g = std::max<int64_t>(ceil_div(nt, GROUP), std::min<int64_t>(nt, want));
+        if (pair_mode >= 2 && group_tiles_env > 0) return (int)ceil_div(nt, group_tiles_env);
         return (int)g;
     };
     const size_t max_tiles = pair_mode >= 2 ? MERGED_MAX_TILES : MAX_TILES;
-    // both masks of the launch's R rows (n / 2 bytes per row each): once they outgrow about half of L2 the units
-    // are walked group by group (merged kernel), see the kernel
-    int group_major = (double)R * (double)n > 48.0 * 1048576.0 ? 1 : 0;
-    if (const char *e = getenv("FS_B200_ACCUM_ORDER")) group_major = e[0] == '1' ? 1 : 0;
     int total_groups = 0;
     for (size_t t0 = 0; t0 < plan.tiles.size(); t0 += max_tiles)
         total_groups += groups_for((int)std::min<size_t>(max_tiles, plan.tiles.size() - t0));
@@ -1020,7 +1042,7 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
             cfg.attrs = &attr;
             cfg.numAttrs = 1;
             FS_CUDA(cudaLaunchKernelEx(&cfg, merged, tmap_at, tmap_mh, tmap_mm, (int)ceil_div(n, KS), R, table, nt, groups,
-                                       group_tiles, m_blocks, group_major, d_ids, contiguous ? 1 : 0, (const int2 *)limbs,
+                                       group_tiles, m_blocks, group_span > 0 && group_span < groups ? group_span : groups, d_ids, contiguous ? 1 : 0, (const int2 *)limbs,
                                        (const int32_t *)rsum, codesT, ldt, krow, K_rows,
                                        tpartial.ptr + (size_t)groups_done * parts * K_rows));
         } else {
