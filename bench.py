@@ -470,11 +470,13 @@ def own_arm(args):
     dt = time.perf_counter() - t0
     # the same from PAGEABLE host memory (what a caller's numpy array usually is)
     x_page = np.array(x_in)
+    make_estimator(w).fit(x_page, w["y"])       # untimed: like the timed steps above, the pageable fit is measured warm
     barrier()
     t0 = time.perf_counter()
-    make_estimator(w).fit(x_page, w["y"])
+    for _ in range(e2e_steps):
+        make_estimator(w).fit(x_page, w["y"])
     barrier()
-    dt_page = time.perf_counter() - t0
+    dt_page = (time.perf_counter() - t0) / e2e_steps
     del x_page
     tt = torch.tensor([dt, dt_page], dtype=torch.float64, device="cuda")
     if world > 1:
