@@ -209,3 +209,39 @@ def test_wide_integer_input_is_narrowed_not_converted(native):
     t = fsb.TuRF(fsb.MultiSURF(backend="gpu", n_features_to_select=5), n_features_to_select=8, pct_remove=0.3).fit(x8.astype(np.int64), y)
     t0 = fsb.TuRF(fsb.MultiSURF(backend="gpu", n_features_to_select=5), n_features_to_select=8, pct_remove=0.3).fit(x8, y)
     assert np.array_equal(t.top_features_, t0.top_features_)
+
+
+def test_staged_upload_of_pageable_views(native, monkeypatch):
+    """fs_dataset_create copies a PAGEABLE source through page-locked blocks with a pool of host threads
+    (dataset.cu); contiguous arrays, row-strided views and the driver's own staging must give the same fit."""
+    rs = np.random.RandomState(11)
+    n, p = 300, 40000                                          # 12 MB of int8: above the staging threshold
+    y = rs.randint(0, 2, n)
+    wide = rs.randint(0, 3, (n, p + 64)).astype(np.int8)
+    wide[:, 7] = (y + rs.randint(0, 2, n)) % 3
+    view = wide[:, :p]                                         # row stride p + 64
+    assert not view.flags["C_CONTIGUOUS"]
+    fit = lambda a: fsb.MultiSURF(n_features_to_select=5, backend="gpu").fit(a, y).feature_importances_
+    w_view, w_copy = fit(view), fit(np.ascontiguousarray(view))
+    monkeypatch.setenv("FS_B200_NO_STAGED_UPLOAD", "1")
+    w_driver = fit(view)
+    assert np.array_equal(w_view, w_copy) and np.array_equal(w_view, w_driver)
+    assert np.argmax(w_view) == 7
+
+
+def test_accumulation_kernels_agree_many_tiles(native, monkeypatch):
+    """More target tiles than one launch of the merged-plane accumulation kernel takes (112 tiles of 224 rows):
+    the launches add into the same exact column sums; the older paired kernel (one launch) must agree."""
+    rs = np.random.RandomState(12)
+    n, p = 26000, 48
+    y = rs.randint(0, 3, n)
+    x = rs.randint(0, 3, (n, p)).astype(np.int8)
+    x[:, 5] = (y + rs.randint(0, 2, n)) % 3
+    w = {}
+    for mode in ("3", "2", "1"):
+        monkeypatch.setenv("FS_B200_ACCUM_PAIR", mode)
+        w[mode] = fsb.MultiSURF(n_features_to_select=3, backend="gpu").fit(x, y).feature_importances_
+    scale = float(np.abs(w["1"]).max())
+    np.testing.assert_allclose(w["3"], w["1"], rtol=0, atol=1e-6 * scale)
+    np.testing.assert_allclose(w["2"], w["1"], rtol=0, atol=1e-6 * scale)
+    assert np.argmax(w["3"]) == 5
