@@ -42,6 +42,22 @@ def shard_rows(n: int, world_size: int, rank: int, align: int = 1) -> tuple[int,
     return start(rank), start(rank + 1)
 
 
+def group_shard_starts(n: int, world_size: int) -> list[int]:
+    """Shard starts of a multi-GPU group.  The distance GEMM works in super-blocks of 256 target rows, and a
+    rank whose shard ends inside a super-block pays for a whole row of tiles (two GPUs on 5656 samples: 12 + 12
+    row super-blocks and 150 tiles per rank = three waves of 74 clusters, against 23 super-blocks and 138 tiles
+    = two waves).  So the ``ceil(n / 256)`` super-blocks are dealt to the ranks as evenly as whole super-blocks
+    allow (the last ranks take the odd ones: the last super-block is the partial one); shards shorter than four super-blocks keep the plain balanced split (multiples of 4)."""
+    blocks = -(-n // 256)
+    if world_size < 1:
+        raise ValueError(f"bad world_size {world_size}")
+    if blocks < 4 * world_size:
+        return shard_starts(n, world_size, 4)
+    base, extra = divmod(blocks, world_size)
+    # the LAST `extra` ranks take one super-block more: the last super-block is the partial one
+    return [256 * (r * base + max(0, r - (world_size - extra))) for r in range(world_size)] + [n]
+
+
 def shard_starts(n: int, world_size: int, align: int = 1) -> list[int]:
     """``[lo_0, lo_1, ..., lo_{world-1}, n]`` of :func:`shard_rows`."""
     return [shard_rows(n, world_size, r, align)[0] for r in range(world_size)] + [n]
@@ -209,7 +225,7 @@ def open_dataset(x, y_enc, n_classes):
         return _native.Dataset(x, y_enc, n_classes)
     ds = _native.Dataset(x, y_enc, n_classes, comm=comm)
     try:
-        ds.attach_comm(comm, shard_starts(ds.n, world, 4))
+        ds.attach_comm(comm, group_shard_starts(ds.n, world))
     except BaseException:
         ds.close()
         raise

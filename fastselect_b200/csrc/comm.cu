@@ -321,7 +321,7 @@ uint64_t fs_comm_required_bytes(int64_t n, int64_t p, int32_t dtype, int32_t wor
     if (n < 1 || p < 1 || world < 1) return 0;
     size_t es = dtype == FS_F32 ? 4 : dtype == FS_F64 ? 8 : 1;
     const int64_t ldx = round_up(p, 16 / (int64_t)es);
-    const int64_t shard = ceil_div(n, world) + 4;
+    const int64_t shard = ceil_div(n, world) + kShardSlack;
     return group_layout(n, p, shard, world, with_x ? (size_t)n * ldx * es : 0).total;
 }
 

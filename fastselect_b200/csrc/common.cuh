@@ -178,6 +178,8 @@ struct GroupLayout {
     size_t off_x;         // raw X (optional; sharded upload)
     size_t total;
 };
+// a rank's shard may exceed n / world by this many rows (shard boundaries on super-blocks of 256 target rows)
+constexpr int64_t kShardSlack = 256;
 GroupLayout group_layout(int64_t n, int64_t p, int64_t max_shard_rows, int world, size_t x_bytes);
 
 // Working set of one fs_score call: the active columns split by path.

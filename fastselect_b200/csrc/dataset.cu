@@ -905,9 +905,9 @@ int fs_dataset_attach_comm(fs_dataset *ds, fs_comm *comm, const int64_t *row_sta
         // sets created by fs_dataset_create_group (then ds->x already points there)
         const size_t es = dtype_size(ds->dtype);
         const bool x_in_arena = ds->x_in_arena;
-        const GroupLayout L = group_layout(ds->n, ds->p, ceil_div(ds->n, world) + 4, world,
+        const GroupLayout L = group_layout(ds->n, ds->p, ceil_div(ds->n, world) + kShardSlack, world,
                                            x_in_arena ? (size_t)ds->n * ds->ldx * es : 0);
-        FS_REQUIRE(max_shard <= ceil_div(ds->n, world) + 4, FS_ERR_INVALID,
+        FS_REQUIRE(max_shard <= ceil_div(ds->n, world) + kShardSlack, FS_ERR_INVALID,
                    "fs_dataset_attach_comm: shards must be balanced (largest %lld rows)", (long long)max_shard);
         FS_REQUIRE(L.total <= comm->arena_bytes, FS_ERR_INVALID,
                    "fs_dataset_attach_comm: arena of %llu bytes is smaller than the %llu this data set needs",
@@ -943,7 +943,7 @@ int fs_dataset_create_group(fs_dataset **out, fs_comm *comm, const void *x, int 
         const size_t es = dtype_size(dtype);
         ds->ldx = round_up(p, 16 / (int64_t)es > 0 ? 16 / (int64_t)es : 1);
         const int world = comm->world, rank = comm->rank;
-        const GroupLayout L = group_layout(n, p, ceil_div(n, world) + 4, world, (size_t)n * ds->ldx * es);
+        const GroupLayout L = group_layout(n, p, ceil_div(n, world) + kShardSlack, world, (size_t)n * ds->ldx * es);
         FS_REQUIRE(L.total <= comm->arena_bytes, FS_ERR_INVALID,
                    "fs_dataset_create_group: arena of %llu bytes is smaller than the %llu this data set needs",
                    (unsigned long long)comm->arena_bytes, (unsigned long long)L.total);

@@ -153,11 +153,19 @@ int fs_multi_create(fs_multi **out, const void *x, int dtype, int64_t n, int64_t
             return fs_dataset_create_group(&m->sets[r], m->comms[r], x, dtype, n, p, row_stride_elems, y_enc, n_classes,
                                            m->streams[r]);
         });
-        // balanced shards of the (class-sorted) target rows, starts multiples of 4
+        // balanced shards of the (class-sorted) target rows: whole super-blocks of 256 rows when every rank gets at
+        // least four of them (the distance GEMM works in such blocks; see _shard.py::group_shard_starts), else
+        // starts that are multiples of 4
         m->starts.assign(world + 1, n);
+        const int64_t blocks = ceil_div(n, 256);
         for (int r = 0; r < world; ++r) {
-            const int64_t base = n / world, extra = n % world;
-            m->starts[r] = (r * base + std::min<int64_t>(r, extra)) / 4 * 4;
+            if (blocks >= 4 * (int64_t)world) {
+                const int64_t base = blocks / world, extra = blocks % world;
+                m->starts[r] = 256 * (r * base + std::max<int64_t>(0, r - (world - extra)));   // the last ranks take the odd blocks
+            } else {
+                const int64_t base = n / world, extra = n % world;
+                m->starts[r] = (r * base + std::min<int64_t>(r, extra)) / 4 * 4;
+            }
         }
         if (world > 1) run_ranks(world, [&](int r) { return fs_dataset_attach_comm(m->sets[r], m->comms[r], m->starts.data()); });
         *out = m;

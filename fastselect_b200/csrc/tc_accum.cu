@@ -23,6 +23,10 @@
 // fixed-point number in two 26-bit limbs, t an integer, the sums two int64 -- no float64
 // instruction in the inner loop (FP64 and the tensor pipe did not overlap on B200).
 //
+// Two kernels.  tc_accum_merged_kernel (below, the default for 0/1/2 columns: clusters of two CTAs, both
+// planes of a column in one epilogue thread, exact 64-bit column sums by atomics) and the older
+// tc_accum_kernel for every other value count, described first:
+//
 // Kernel: persistent, one CTA per SM.  A work unit is 128 one-hot rows (UMMA M = TMEM
 // lanes) x a group of tiles of <= 240 target rows (UMMA N); units are dealt
 // round-robin and the TMA / MMA / epilogue pipelines run across unit boundaries without
@@ -108,7 +112,7 @@ static_assert(STAGE_BYTES % 1024 == 0 && HALF % 16 == 0 && SF_COL + 8 <= TMEM_CO
 // busy at the same time (ncu on the earlier float64 epilogue: math-pipe throttle on every FP64
 // instruction while the MMA issuer waited for the epilogue; FP64 time and MMA time added up
 // instead of overlapping).
-constexpr int kCoefBits = 52, kLimbBits = 26;
+constexpr int kLimbBits = 26;            // C = round(c * 2^52) = Chi * 2^26 + Clo
 __device__ __forceinline__ int2 coef_limbs(double c) {
     const long long C = __double2ll_rn(c * 4503599627370496.0);       // 2^52
     return make_int2((int)(C >> kLimbBits), (int)(C & ((1LL << kLimbBits) - 1)));

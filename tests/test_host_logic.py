@@ -246,6 +246,27 @@ def test_aligned_shards_partition_every_row_once():
             assert [shard_rows(n, w, r, 4) for r in range(w)] == list(zip(starts, starts[1:]))
 
 
+def test_group_shards_fall_on_distance_super_blocks():
+    """group_shard_starts: a multi-GPU group's shards end on super-blocks of 256 target rows (the tile of the
+    distance GEMM) when every rank gets at least four of them, stay within one super-block of the balanced
+    split (the arena's slab is sized for ceil(n / world) + 256 rows), and cover every row exactly once."""
+    from fastselect_b200._shard import group_shard_starts, shard_starts
+
+    for n in (5, 61, 1000, 4000, 5656, 8000, 11312, 20000, 26000):
+        for w in (1, 2, 3, 4, 8):
+            starts = group_shard_starts(n, w)
+            assert starts[0] == 0 and starts[-1] == n and len(starts) == w + 1
+            rows = [b - a for a, b in zip(starts, starts[1:])]
+            assert all(r >= 0 for r in rows) and max(rows) <= -(-n // w) + 256
+            assert all(s % 4 == 0 for s in starts[:-1])
+            if -(-n // 256) >= 4 * w:
+                assert all(s % 256 == 0 for s in starts[:-1]) and min(rows) > 0
+                # whole super-blocks per rank: the ranks' row super-blocks add up to ceil(n / 256), no more
+                assert sum(-(-r // 256) for r in rows) == -(-n // 256)
+            else:
+                assert starts == shard_starts(n, w, 4)
+
+
 def test_top_features_equal_the_reference_expression():
     """_ReliefBase._top == np.argsort(scores)[::-1][:k] (MultiSURF.py:443), ties included."""
     from fastselect_b200._relief import _ReliefBase
