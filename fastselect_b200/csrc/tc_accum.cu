@@ -103,6 +103,8 @@ struct TileTable {
 constexpr int M_EPI_WARPS = 16, M_PARTS = M_EPI_WARPS / 4, M_CHUNKS = (BN / 16 + M_PARTS - 1) / M_PARTS;
 constexpr int M_THREADS = 32 * (M_EPI_WARPS + 2);
 constexpr int PRODUCER_WARP = M_EPI_WARPS, MMA_WARP = M_EPI_WARPS + 1;
+// the kernel's parameters (three tensor maps, the table, ~15 scalars) must stay within the classic 4 KB
+static_assert(sizeof(TileTable) <= 3584, "tile table too large for the kernel parameter space");
 static_assert(STAGE_BYTES % 1024 == 0 && HALF % 16 == 0 && SF_COL + 8 <= TMEM_COLS, "tile shape");
 
 // Fixed-point image of a per-target coefficient c (|c| <= 1): C = round(c * 2^52) split into a
