@@ -962,12 +962,16 @@ int launch_tc_accum(const CUtensorMap &tmap_at, const CUtensorMap &tmap_mh, cons
     // the merged-plane kernel as clusters of two CTAs (cta_group::2; tiles of <= 224 rows)
     const bool cg2 = pair_mode == 3;
 #ifdef FS_ACCUM_EXPERIMENTS
-    int exp = 0;
-    if (const char *e = getenv("FS_B200_ACCUM_EXP")) exp = atoi(e);
-#define FS_PICK(c) (exp == 8 ? tc_accum_merged_kernel<c, 8> : exp == 16 ? tc_accum_merged_kernel<c, 16> : exp == 17 ? tc_accum_merged_kernel<c, 17> : \
-                    exp == 18 ? tc_accum_merged_kernel<c, 18> : exp == 20 ? tc_accum_merged_kernel<c, 20> : exp == 23 ? tc_accum_merged_kernel<c, 23> : \
-                    exp == 24 ? tc_accum_merged_kernel<c, 24> : exp == 32 ? tc_accum_merged_kernel<c, 32> : exp == 64 ? tc_accum_merged_kernel<c, 64> : \
-                    tc_accum_merged_kernel<c, 0>)
+    // diagnostic build (-DFS_ACCUM_EXPERIMENTS): FS_B200_ACCUM_EXP compiles parts of the merged kernel out --
+    // 1 no value-code loads, 2 no constants loads, 4 no arithmetic, 8 epilogue only waits and arrives, 16 no operand
+    // traffic and no MMAs (sums of these as listed); the results are then wrong on purpose
+    // (profiles/r02_accum_kernel_experiments.txt)
+    int exp_mode = 0;
+    if (const char *e = getenv("FS_B200_ACCUM_EXP")) exp_mode = atoi(e);
+#define FS_PICK(c) (exp_mode == 8 ? tc_accum_merged_kernel<c, 8> : exp_mode == 16 ? tc_accum_merged_kernel<c, 16> : \
+                    exp_mode == 17 ? tc_accum_merged_kernel<c, 17> : exp_mode == 18 ? tc_accum_merged_kernel<c, 18> : \
+                    exp_mode == 20 ? tc_accum_merged_kernel<c, 20> : exp_mode == 23 ? tc_accum_merged_kernel<c, 23> : \
+                    exp_mode == 24 ? tc_accum_merged_kernel<c, 24> : tc_accum_merged_kernel<c, 0>)
     auto merged = cg2 ? FS_PICK(true) : FS_PICK(false);
 #undef FS_PICK
 #else
