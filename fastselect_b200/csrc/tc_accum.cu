@@ -493,10 +493,12 @@ tc_accum_kernel(const __grid_constant__ CUtensorMap tmap_at, const __grid_consta
 // accumulators, the float -> int bias rides on the row sum, and a thread serves two columns (lane
 // offsets 0 and 16), i.e. two independent dependency chains.  TMEM loads and the per-target constants
 // are double-buffered in registers; the accumulator buffer is handed back to the MMA issuer as soon as
-// the LAST chunk is in registers (before its arithmetic).  Chunks of 16 targets are dealt to the three
-// column parts round-robin (part, part + 3, ...), so a class-tail tile of 80 rows costs two chunk
-// times instead of five.  The four threads of a column fold their sums at the end of a work unit; the
-// partial goes to the slot of one-hot row 2c (0 to the slot of row 2c + 1): the reducer is unchanged.
+// the LAST chunk is in registers (before its arithmetic).  Chunks of 16 targets are dealt to the four
+// column parts (16 epilogue warps: lane quarter x part) round-robin (part, part + 4, ...), so a class-tail
+// tile of 80 rows costs two chunk times instead of four.  The four threads of a column fold their sums at the
+// end of a work unit and add them, as exact 64-bit integers, into the column's two slots of the partial
+// buffer (one-hot row 2c: high limbs, row 2c + 1: low limbs); merged_finish_kernel converts, and the reducer of
+// the older kernels is reused unchanged.
 constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23: float(kMagic + t) has the bits kBias + t for |t| < 2^22
 constexpr int kBias = 0x4B400000;
 
